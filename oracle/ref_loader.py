@@ -1,0 +1,74 @@
+"""TEST INFRASTRUCTURE ONLY -- import the *unmodified* reference source from
+``/root/reference`` under the NumPy ``tensorflow`` shim (oracle/tf_shim.py).
+
+Only usable in the build container: ``/root/reference`` does not exist on the GPU
+box, so nothing reachable from ``pytest -m gpu``, ``smoke()`` or ``bench.py`` calls
+this.  It is used by
+
+* ``oracle/make_golden.py`` to generate ``tests/golden/*.npz`` and
+* ``tests/test_oracle_vs_reference.py`` (skipped when the reference is absent)
+  to pin ``oracle/ssd_oracle.py`` against the real thing.
+
+Reference entry points exposed (file:line in /root/reference):
+  utils/bbox.py:6    iou
+  utils/bbox.py:28   iou_n
+  utils/bbox.py:44   match_bbox
+  utils/bbox.py:94   apply_anchor_box
+  models/ssd_model.py:173  SSDObjectDetectionModel._build_prior_box
+  models/ssd_model.py:341  SSDObjectDetectionModel._ssd_loss
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("SSDGEOM_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "utils", "bbox.py"))
+
+
+_cache = {}
+
+
+def load():
+    """Return a namespace with the reference's hot-path callables."""
+    if "ns" in _cache:
+        return _cache["ns"]
+    if not available():
+        raise RuntimeError("reference source not present at %s" % REFERENCE_ROOT)
+    from . import tf_shim
+
+    tf_shim.install()
+    # The reference imports its packages as top-level names (utils, models, data_loaders).
+    # Import them under those names from REFERENCE_ROOT, then restore sys.path.
+    for name in list(sys.modules):
+        if name.split(".")[0] in ("utils", "models", "data_loaders"):
+            raise RuntimeError("a module named %r is already imported; cannot load the reference" % name)
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        bbox = importlib.import_module("utils.bbox")
+        ssd_model = importlib.import_module("models.ssd_model")
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+    model_cls = ssd_model.SSDObjectDetectionModel
+
+    def build_prior_box(size_list, input_size=300):
+        fake_self = types.SimpleNamespace(cfg=types.SimpleNamespace(input_shape=(input_size, input_size, 3)))
+        return model_cls._build_prior_box(fake_self, size_list)
+
+    ns = types.SimpleNamespace(
+        iou=bbox.iou,
+        iou_n=bbox.iou_n,
+        match_bbox=bbox.match_bbox,
+        apply_anchor_box=bbox.apply_anchor_box,
+        build_prior_box=build_prior_box,
+        ssd_loss=model_cls._ssd_loss,
+        bbox_module=bbox,
+        model_module=ssd_model,
+    )
+    _cache["ns"] = ns
+    return ns

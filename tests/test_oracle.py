@@ -1,0 +1,229 @@
+"""CPU: pin the oracle restatement (oracle/ssd_oracle.py) against (i) the reference's own
+known-answer tests (tests/utils/test_bbox.py in /root/reference) and (ii) the fixtures the
+unmodified reference produced (tests/golden/*.npz, oracle/make_golden.py)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ssd_oracle as O
+from ssdgeom import synth
+
+
+def sha(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h.update(str(a.dtype).encode() + str(a.shape).encode() + a.tobytes())
+    return h.hexdigest()
+
+
+# reference tests/utils/test_bbox.py:10-17
+IOU_KAT = [
+    ([10, 10, 2, 2], [10, 10, 2, 2], 1.0),
+    ([10, 10, 1, 1], [20, 20, 1, 1], 0.0),
+    ([10, 10, 2, 2], [10, 10, 4, 4], 0.25),
+    ([10, 10, 0, 0], [20, 20, 0, 0], 0.0),
+    ([10, 10, -1, -1], [10, 10, -1, -1], 0.0),
+    ([10, 10, 2, 2], [11, 11, 2, 2], 1 / 7),
+    ([10, 10, 6, 6], [13, 13, 2, 2], 1 / 39),
+    ([10, -10, 1, 1], [10, -10, 1, 1], 1.0),
+]
+
+
+@pytest.mark.parametrize("a,b,want", IOU_KAT)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_iou_known_answers(a, b, want, dtype):
+    assert abs(float(O.iou(a, b, dtype=dtype)) - want) < 5e-5   # places=4
+
+
+def test_iou_n_probe_values():
+    # reference tests/utils/test_bbox.py:19-23 prints these; SURVEY section 4 recorded them
+    a = np.array([[10, 10, 2, 2], [10, 10, 1, 1], [10, 10, 2, 2]], dtype=np.float32)
+    b = np.array([[10, 10, 2, 2], [20, 20, 1, 1], [10, 10, 4, 4]], dtype=np.float32)
+    got = O.iou_n(a, b)
+    assert got.dtype == np.float32
+    np.testing.assert_allclose(got, [1.0, 5.0000002e-21, 0.25], rtol=1e-6)
+
+
+def test_match_known_answers():
+    # reference tests/utils/test_bbox.py:35-39
+    d = np.array([[10, 10, 1, 1], [20, 20, 1, 1], [20, 20, 0.5, 0.5]])
+    t = np.array([[0, 10, 10, 0.5, 0.5], [1, 20, 20, 1, 1], [2, 20, 20, 0.5, 0.5]])
+    cls, loc, mask = O.match_bbox(t[:, 0], t[:, 1:], d)
+    np.testing.assert_almost_equal(loc, t[:, 1:])
+    # :40-44
+    d = np.array([[10, 10, 1, 1], [20, 20, 1.1, 1.1], [20, 20, 0.5, 0.5]])
+    t = np.array([[0, 15, 15, 13, 13], [1, 15, 15, 14, 14]])
+    cls, loc, mask = O.match_bbox(t[:, 0], t[:, 1:], d)
+    np.testing.assert_almost_equal(loc, np.array([[15, 15, 14, 14], [15, 15, 13, 13], [0, 0, 0, 0]]))
+    assert cls.tolist() == [1, 0, 0] and mask.tolist() == [True, True, False]
+
+
+def test_match_asserts():
+    pri = O.build_prior_box()[:4]
+    g = np.tile(np.array([[0.5, 0.5, 0.2, 0.2]], dtype=np.float32), (5, 1))
+    with pytest.raises(AssertionError):
+        O.match_bbox(np.zeros(5, np.float32), g, pri)          # T > A, utils/bbox.py:50
+    with pytest.raises(AssertionError):
+        O.match_bbox(np.zeros(2, np.float32), g[:2], pri, 0.0)  # thresh, :51
+
+
+def test_priors_golden(golden_dir):
+    want = np.load(os.path.join(golden_dir, "priors_ssd300.npz"))["priors"]
+    got = O.build_prior_box()
+    assert got.dtype == np.float64 and got.shape == (8732, 4)
+    assert np.array_equal(got, want)            # bit-exact
+    t = synth.SSD300
+    assert np.array_equal(O.build_prior_box(t["sizes"], t["s_k_refer"], t["aspect_ratio"], t["input_size"]), want)
+    # SURVEY section 8(a) probe rows
+    np.testing.assert_allclose(got[0], [0.01315789, 0.01315789, 0.07, 0.07], rtol=1e-6)
+    np.testing.assert_allclose(got[-1], [0.5, 0.5, 0.6151829, 1.2303658], rtol=1e-6)
+    assert synth.num_priors(synth.SSD300) == 8732 and synth.num_priors(synth.SSD512) == 24564
+
+
+def _config1_inputs():
+    b_max, c_max, o_max = synth.make_gt(0, 4, 100, "max")
+    b_coco, c_coco, o_coco = synth.make_gt(1, 4, 100, "coco")
+    return (np.concatenate([b_max, b_coco]), np.concatenate([c_max, c_coco]),
+            np.concatenate([o_max, o_coco[1:] + o_max[-1]]).astype(np.int32))
+
+
+@pytest.mark.parametrize("sweeps", [True, False])
+def test_assign_config1_golden(golden_dir, sweeps):
+    """BASELINE config 1: 8 SSD300 images; oracle == unmodified reference, bit for bit."""
+    g = np.load(os.path.join(golden_dir, "assign_ssd300.npz"))
+    boxes, cls, offsets = _config1_inputs()
+    priors = O.build_prior_box()
+    assert sha(boxes, cls, offsets, priors) == str(g["input_sha"])
+    for i in range(8):
+        s, e = offsets[i], offsets[i + 1]
+        lab, box, mask = O.match_bbox(cls[s:e], boxes[s:e], priors, 0.5, sweeps=sweeps)
+        loc = O.apply_anchor_box(box, priors).astype(np.float32)
+        assert sha(lab.astype(np.int32)) == str(g["sha_cls"][i])
+        assert sha(box) == str(g["sha_box"][i])
+        assert sha(mask.astype(bool)) == str(g["sha_mask"][i])
+        assert sha(loc) == str(g["sha_loc"][i])
+        ps, pe = g["pos_offsets"][i], g["pos_offsets"][i + 1]
+        assert np.array_equal(np.nonzero(mask)[0], g["pos_index"][ps:pe])
+        assert np.array_equal(loc[mask], g["pos_loc"][ps:pe])
+
+
+def test_match_small_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "match_small.npz"))
+    for name in g["names"]:
+        for sweeps in (True, False):
+            with np.errstate(all="ignore"):
+                lab, box, mask = O.match_bbox(g[name + "_cls_in"], g[name + "_box_in"], g[name + "_pri_in"],
+                                              float(g[name + "_thresh"]), sweeps=sweeps)
+                enc = O.apply_anchor_box(box, g[name + "_pri_in"])
+            assert np.array_equal(lab, g[name + "_cls"]), name
+            assert np.array_equal(box, g[name + "_box"]), name
+            assert np.array_equal(mask, g[name + "_mask"]), name
+            assert np.array_equal(enc, g[name + "_enc"], equal_nan=True), name
+
+
+def test_columnwise_equals_sweeps_random():
+    rng = np.random.default_rng(7)
+    pri = O.build_prior_box()[::13]
+    for trial in range(20):
+        t = int(rng.integers(1, 30))
+        b, c, _ = synth.make_gt(100 + trial, 1, t, "max")
+        if trial % 4 == 0:              # duplicates
+            b[t // 2:] = b[: t - t // 2]
+        thr = float(rng.choice([0.5, 0.3, 0.7, 1e-9]))
+        m = O.iou_matrix(b, pri)
+        assert O.match_pairs_sweeps(m, thr)[:t] == O.match_pairs_columnwise(m, thr)[:t]
+        assert sorted(O.match_pairs_sweeps(m, thr)[t:]) == sorted(O.match_pairs_columnwise(m, thr)[t:])
+
+
+def test_loss_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "loss_ssd300.npz"))
+    boxes, cls, offsets = _config1_inputs()
+    priors = O.build_prior_box()
+    tgt = [O.assign_encode(cls[offsets[i]:offsets[i + 1]], boxes[offsets[i]:offsets[i + 1]], priors, sweeps=False)
+           for i in range(4)]
+    y_true = tuple(np.stack([t[k] for t in tgt]) for k in range(3))
+    pred_cls, pred_box = synth.make_predictions(0, 4, 8732)
+    assert sha(pred_cls, pred_box, *y_true) == str(g["input_sha"])
+    total, info, aux = O.ssd_loss(y_true, (pred_box, pred_cls), return_masks=True)
+    assert aux["num_pos"] == int(g["num_pos"]) and aux["num_neg"] == int(g["num_neg"])
+    assert np.float32(aux["kth"]) == g["kth"]
+    assert np.array_equal(np.packbits(aux["neg_mask"], axis=1), g["neg_mask_bits"])
+    np.testing.assert_allclose(total, float(g["total"]), rtol=1e-6)
+    np.testing.assert_allclose(info["cls loss pos"], float(g["loss_pos"]), rtol=1e-6)
+    np.testing.assert_allclose(info["cls loss neg"], float(g["loss_neg"]), rtol=1e-6)
+    np.testing.assert_allclose(info["loc loss"], float(g["loss_loc"]), rtol=1e-6)
+
+
+def test_loss_guards():
+    y_true = (np.zeros((1, 8), np.int32), np.zeros((1, 8, 4), np.float32), np.zeros((1, 8), bool))
+    y_pred = (np.zeros((1, 8, 4), np.float32), np.zeros((1, 8, 5), np.float32))
+    with pytest.raises(ValueError):
+        O.ssd_loss(y_true, y_pred)            # num_pos == 0 -> k = 0 (reference: index error)
+    y_true[2][0, :4] = True
+    with pytest.raises(ValueError):
+        O.ssd_loss(y_true, y_pred)            # 3*4 > 8 (reference: top_k error)
+
+
+def test_encode_decode_roundtrip():
+    priors = O.build_prior_box()
+    rng = np.random.default_rng(3)
+    g = np.concatenate([rng.uniform(0, 1, (8732, 2)), np.exp(rng.uniform(np.log(0.02), np.log(0.9), (8732, 2)))],
+                       1).astype(np.float32)
+    enc = O.apply_anchor_box(g, priors).astype(np.float32)
+    for ed in (np.float32, np.float64):
+        dec = O.decode_bbox(enc, priors, scale=1.0, exp_dtype=ed)
+        np.testing.assert_allclose(dec, g, rtol=2e-5, atol=2e-6)
+
+
+def test_loss_grad_matches_finite_difference():
+    rng = np.random.default_rng(5)
+    b, a, c = 2, 40, 6
+    gt_cls = rng.integers(0, c - 1, (b, a)).astype(np.int32)
+    gt_mask = rng.uniform(size=(b, a)) < 0.1
+    gt_mask[0, 0] = True
+    gt_box = rng.normal(size=(b, a, 4)).astype(np.float32)
+    pred_box = rng.normal(size=(b, a, 4)).astype(np.float32)
+    pred_cls = rng.normal(size=(b, a, c)).astype(np.float32)
+    g_box, g_cls = O.ssd_loss_grad((gt_cls, gt_box, gt_mask), (pred_box, pred_cls))
+    # the shim CE is float32-rounded, so finite differences need a float64 re-evaluation
+    def f64_loss(pc):
+        x = pc.astype(np.float64)
+        lse = np.log(np.exp(x - x.max(-1, keepdims=True)).sum(-1)) + x.max(-1)
+        _, _, aux = O.ssd_loss((gt_cls, gt_box, gt_mask), (pred_box, pred_cls), return_masks=True)
+        ce_gt = lse - np.take_along_axis(x, gt_cls[..., None].astype(np.int64), -1)[..., 0]
+        ce_bg = lse - x[..., -1]
+        return ce_gt[gt_mask].sum() / aux["num_pos"] + ce_bg[aux["neg_mask"]].sum() / aux["num_neg"]
+    base = pred_cls.astype(np.float64)
+    for idx in [(0, 0, 1), (1, 5, c - 1), (0, 7, 2)]:
+        h = 1e-6
+        up, dn = base.copy(), base.copy()
+        up[idx] += h
+        dn[idx] -= h
+        fd = (f64_loss(up) - f64_loss(dn)) / (2 * h)
+        assert abs(fd - g_cls[idx]) < 1e-6
+
+
+def test_nms_single_class_basics():
+    boxes = np.array([[0.5, 0.5, 0.2, 0.2], [0.5, 0.5, 0.21, 0.2], [0.1, 0.1, 0.1, 0.1],
+                      [0.5, 0.52, 0.2, 0.2], [0.9, 0.9, 0.1, 0.1]], dtype=np.float32)
+    scores = np.array([0.9, 0.8, 0.7, 0.005, 0.9], dtype=np.float32)
+    kept = O.nms_single_class(scores, boxes)
+    assert kept.tolist() == [0, 4, 2]          # tie 0.9: lower index first; 1 suppressed; 3 below thresh
+    assert O.nms_single_class(scores, boxes, top_k=2).tolist() == [0, 4]
+    assert O.nms_single_class(np.zeros(5, np.float32), boxes).size == 0
+
+
+def test_nms_against_torchvision_sanity():
+    tv = pytest.importorskip("torchvision")
+    import torch
+    rng = np.random.default_rng(11)
+    n = 300
+    b = np.concatenate([rng.uniform(0.2, 0.8, (n, 2)), rng.uniform(0.05, 0.3, (n, 2))], 1).astype(np.float32)
+    s = rng.uniform(0.02, 1, n).astype(np.float32)
+    kept = O.nms_single_class(s, b, top_k=n)
+    xyxy = torch.tensor(np.concatenate([b[:, :2] - b[:, 2:] / 2, b[:, :2] + b[:, 2:] / 2], 1))
+    ref = tv.ops.nms(xyxy, torch.tensor(s), 0.45).numpy()
+    assert kept.tolist() == ref.tolist()
