@@ -1,0 +1,480 @@
+// Multibox loss with batch-global 3:1 hard-negative mining (models/ssd_model.py:341-396).
+//
+//   ce_kernel      one streaming pass over the logits [N,C] (N = B*A).  Each warp owns a ring of
+//                  32-prior tiles filled by 1-D bulk TMA (cp.async.bulk + mbarrier); lane r then
+//                  reads row r from shared memory (stride C words: conflict-free for odd C) and
+//                  produces  log-sum-exp, the ground-truth CE of positives, the background CE of
+//                  non-positives (the mining input, :362-367), the L1 box term (:384-386), and
+//                  the top-11-bit histogram of the mining input.
+//   select_kernel  x2: radix select of the k-th largest background CE (k = ratio*num_pos, :368-369)
+//                  on the order-preserving key, 11 + 11 + 10 bits, over the L2-resident vector.
+//   final_kernel   mask = ce >= k-th (:372, ties kept), masked sum / count, pos&neg overlap check
+//                  (:375), deterministic reduction of the per-CTA partials, result block.
+//   grad_kernel    optional second pass: d total / d logits and d total / d pred_box (:248).
+#include <math_constants.h>
+#include "common.cuh"
+
+namespace ssdg {
+
+constexpr int kCeThreads = 256;
+constexpr int kCeWarps = kCeThreads / 32;
+constexpr int kStages = 2;
+constexpr int kBins = 2048;
+
+struct LossWs {
+  // device-side layout of the workspace head (all 8-byte aligned)
+  double part[256][4];      // per-CTA: sum pos CE, sum L1, num_pos, (unused)
+  double fpart[1024][2];    // per-CTA of final_kernel: masked sum, (unused)
+  u32 fcount[1024][2];      // per-CTA: neg count, pos&neg overlap count
+  u32 hist[3][kBins];       // the three radix levels
+  u32 ticket[4];            // last-block-done counters
+  u32 nparts[4];            // grid sizes used
+};
+
+struct LossParams {
+  const int* gt_cls;
+  const float* gt_box;
+  const uint8_t* gt_mask;
+  const float* pred_box;
+  const float* pred_cls;
+  long long N;
+  int C, ratio;
+  float* neg_ce;        // [N] mining input
+  uint8_t* neg_mask;    // optional
+  double* result;       // [SSDG_LOSS_RESULT_LEN]
+  LossWs* ws;
+  float* grad_box;
+  float* grad_cls;
+};
+
+__device__ __forceinline__ u64 make_evict_first_policy() {
+  u64 pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void* smem_dst, const void* gsrc, u32 bytes, u64* bar, u64 pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+
+// Row statistics from a shared-memory row: max, sum exp(x - max).  Four independent chains.
+__device__ __forceinline__ void row_lse(const float* __restrict__ row, int C, float& m, float& s) {
+  float m0 = -CUDART_INF_F, m1 = m0, m2 = m0, m3 = m0;
+  int c = 0;
+  for (; c + 4 <= C; c += 4) {
+    m0 = fmaxf(m0, row[c]); m1 = fmaxf(m1, row[c + 1]); m2 = fmaxf(m2, row[c + 2]); m3 = fmaxf(m3, row[c + 3]);
+  }
+  for (; c < C; ++c) m0 = fmaxf(m0, row[c]);
+  m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  c = 0;
+  for (; c + 4 <= C; c += 4) {
+    s0 += __expf(row[c] - m); s1 += __expf(row[c + 1] - m); s2 += __expf(row[c + 2] - m); s3 += __expf(row[c + 3] - m);
+  }
+  for (; c < C; ++c) s0 += __expf(row[c] - m);
+  s = (s0 + s1) + (s2 + s3);
+}
+
+struct CeAcc {
+  float pos_ce, l1;
+  int npos;
+};
+
+// Per-prior work shared by the TMA path and the tail path.
+__device__ __forceinline__ void ce_one_prior(const LossParams& P, long long n, const float* row, u32* hist, CeAcc& acc) {
+  const int C = P.C;
+  float m, s;
+  row_lse(row, C, m, s);
+  const float lg = logf(s);
+  const bool pos = P.gt_mask[n] != 0;
+  float neg = 0.f;
+  if (pos) {
+    int lab = P.gt_cls[n];
+    lab = lab < 0 ? 0 : (lab >= C ? C - 1 : lab);
+    acc.pos_ce += lg - (row[lab] - m);
+    const float4 pb = __ldg(reinterpret_cast<const float4*>(P.pred_box) + n);
+    const float4 gb = __ldg(reinterpret_cast<const float4*>(P.gt_box) + n);
+    acc.l1 += (fabsf(pb.x - gb.x) + fabsf(pb.y - gb.y)) + (fabsf(pb.z - gb.z) + fabsf(pb.w - gb.w));
+    acc.npos += 1;
+  } else {
+    neg = lg - (row[C - 1] - m);
+  }
+  P.neg_ce[n] = neg;
+  atomicAdd(&hist[key32(neg) >> 21], 1u);
+}
+
+__global__ void __launch_bounds__(kCeThreads, 1) ce_kernel(LossParams P, int warps_per_cta) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int C = P.C;
+  const u32 tile_bytes = 32u * (u32)C * 4u;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* bufs = reinterpret_cast<float*>(smem_raw);                                   // [warps][stages][32*C]
+  u32* hist = reinterpret_cast<u32*>(smem_raw + (size_t)warps_per_cta * kStages * tile_bytes);
+  u64* bars = reinterpret_cast<u64*>(hist + kBins);                                    // [warps][stages]
+  double* red = reinterpret_cast<double*>(bars + kCeWarps * kStages);                  // [3][kCeWarps]
+
+  for (int i = tid; i < kBins; i += kCeThreads) hist[i] = 0u;
+  if (tid == 0) {
+    for (int i = 0; i < warps_per_cta * kStages; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  CeAcc acc;
+  acc.pos_ce = 0.f; acc.l1 = 0.f; acc.npos = 0;
+  const long long full_tiles = P.N >> 5;
+  if (warp < warps_per_cta) {
+    const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
+    const long long stride = (long long)gridDim.x * warps_per_cta;
+    float* mybuf = bufs + (size_t)warp * kStages * 32 * C;
+    u64* mybar = bars + warp * kStages;
+    const u64 pol = make_evict_first_policy();
+    const char* src = reinterpret_cast<const char*>(P.pred_cls);
+    // prologue
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        long long t = gw + (long long)s * stride;
+        if (t < full_tiles) {
+          mbar_arrive_expect_tx(&mybar[s], tile_bytes);
+          tma_load_1d_hint(mybuf + (size_t)s * 32 * C, src + (size_t)t * tile_bytes, tile_bytes, &mybar[s], pol);
+        }
+      }
+    }
+    int k = 0;
+    for (long long t = gw; t < full_tiles; t += stride, ++k) {
+      const int s = k % kStages;
+      mbar_wait(&mybar[s], (u32)((k / kStages) & 1));
+      const float* row = mybuf + (size_t)s * 32 * C + (size_t)lane * C;
+      ce_one_prior(P, (t << 5) + lane, row, hist, acc);
+      __syncwarp();
+      const long long tn = t + (long long)kStages * stride;
+      if (lane == 0 && tn < full_tiles) {
+        mbar_arrive_expect_tx(&mybar[s], tile_bytes);
+        tma_load_1d_hint(mybuf + (size_t)s * 32 * C, src + (size_t)tn * tile_bytes, tile_bytes, &mybar[s], pol);
+      }
+    }
+    // tail rows (N % 32), plain loads, by the first warp of the grid
+    const int tail = (int)(P.N & 31);
+    if (gw == 0 && tail) {
+      float* buf = mybuf;
+      const float* g = P.pred_cls + (size_t)full_tiles * 32 * C;
+      for (int i = lane; i < tail * C; i += 32) buf[i] = g[i];
+      __syncwarp();
+      if (lane < tail) ce_one_prior(P, (full_tiles << 5) + lane, buf + (size_t)lane * C, hist, acc);
+    }
+  }
+  // block reduction of the three sums (double), one partial per CTA
+  double a = warp_sum((double)acc.pos_ce), b = warp_sum((double)acc.l1), c = warp_sum((double)acc.npos);
+  if (lane == 0) { red[warp] = a; red[kCeWarps + warp] = b; red[2 * kCeWarps + warp] = c; }
+  __syncthreads();
+  if (tid == 0) {
+    double sa = 0, sb = 0, sc = 0;
+    for (int w = 0; w < kCeWarps; ++w) { sa += red[w]; sb += red[kCeWarps + w]; sc += red[2 * kCeWarps + w]; }
+    P.ws->part[blockIdx.x][0] = sa; P.ws->part[blockIdx.x][1] = sb; P.ws->part[blockIdx.x][2] = sc;
+    if (blockIdx.x == 0) P.ws->nparts[0] = gridDim.x;
+  }
+  for (int i = tid; i < kBins; i += kCeThreads) {
+    u32 v = hist[i];
+    if (v) atomicAdd(&P.ws->hist[0][i], v);
+  }
+}
+
+// ---- radix select ------------------------------------------------------------------------------------
+// Every CTA re-derives the state of the select from the (complete) histograms of the previous
+// levels: prefix of the k-th key found so far and the rank still to resolve inside it.
+struct SelectState {
+  long long k;        // remaining rank inside the current prefix (1-based from the top)
+  u32 prefix;         // key bits resolved so far (left-aligned per level)
+  int status;
+  double num_pos;
+};
+
+// Scan one histogram from the top: find bin with  count(bins above) < k <= count(bins >= bin).
+__device__ int scan_level(const u32* __restrict__ ghist, int nbins, long long& k, u32* sh /*[kBins]*/, int tid,
+                          int nthreads, int* sh_bin, long long* sh_above) {
+  for (int i = tid; i < nbins; i += nthreads) sh[i] = ghist[i];
+  __syncthreads();
+  if (tid < 32) {
+    // 32 lanes, each owns a contiguous chunk (from the top)
+    const int per = nbins / 32;
+    const int hi = nbins - 1 - tid * per;
+    long long mine = 0;
+    for (int j = 0; j < per; ++j) mine += sh[hi - j];
+    long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long v = __shfl_up_sync(SSDG_FULL, incl, o);
+      if (tid >= o) incl += v;
+    }
+    const long long above = incl - mine;
+    if (above < k && k <= incl) {
+      long long run = above;
+      int bin = hi;
+      for (int j = 0; j < per; ++j) {
+        long long cnt = sh[hi - j];
+        if (run + cnt >= k) { bin = hi - j; break; }
+        run += cnt;
+      }
+      *sh_bin = bin;
+      *sh_above = run;
+    }
+  }
+  __syncthreads();
+  const int bin = *sh_bin;
+  k -= *sh_above;
+  __syncthreads();
+  return bin;
+}
+
+__device__ void derive_state(const LossParams& P, int levels_done, SelectState& st, u32* sh, int tid, int nthreads,
+                             int* sh_bin, long long* sh_above, double* sh_np) {
+  if (tid == 0) {
+    double np = 0;
+    const int n = (int)P.ws->nparts[0];
+    for (int i = 0; i < n; ++i) np += P.ws->part[i][2];
+    *sh_np = np;
+    *sh_bin = 0; *sh_above = 0;
+  }
+  __syncthreads();
+  st.num_pos = *sh_np;
+  st.k = (long long)P.ratio * (long long)st.num_pos;
+  st.prefix = 0;
+  st.status = 0;
+  if (st.num_pos <= 0 || P.ratio <= 0) { st.status = SSDG_ERR_NO_POSITIVE; return; }
+  if (st.k > P.N) { st.status = SSDG_ERR_TOPK_RANGE; return; }
+  if (levels_done >= 1) st.prefix = (u32)scan_level(P.ws->hist[0], kBins, st.k, sh, tid, nthreads, sh_bin, sh_above) << 21;
+  if (levels_done >= 2) st.prefix |= (u32)scan_level(P.ws->hist[1], kBins, st.k, sh, tid, nthreads, sh_bin, sh_above) << 10;
+  if (levels_done >= 3) st.prefix |= (u32)scan_level(P.ws->hist[2], 1024, st.k, sh, tid, nthreads, sh_bin, sh_above);
+}
+
+// level = 1: histogram bits 20..10 of keys whose bits 31..21 match; level = 2: bits 9..0.
+__global__ void __launch_bounds__(256) select_kernel(LossParams P, int level) {
+  __shared__ u32 sh[kBins];
+  __shared__ int sh_bin;
+  __shared__ long long sh_above;
+  __shared__ double sh_np;
+  SelectState st;
+  derive_state(P, level, st, sh, threadIdx.x, blockDim.x, &sh_bin, &sh_above, &sh_np);
+  if (st.status) return;
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) sh[i] = 0u;
+  __syncthreads();
+  const u32 mask = level == 1 ? 0xffe00000u : 0xfffffc00u;
+  const int shift = level == 1 ? 10 : 0;
+  const u32 dmask = level == 1 ? 2047u : 1023u;
+  const long long n4 = P.N >> 2;
+  const float4* v4 = reinterpret_cast<const float4*>(P.neg_ce);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = v4[i];
+    u32 k0 = key32(v.x), k1 = key32(v.y), k2 = key32(v.z), k3 = key32(v.w);
+    if ((k0 & mask) == st.prefix) atomicAdd(&sh[(k0 >> shift) & dmask], 1u);
+    if ((k1 & mask) == st.prefix) atomicAdd(&sh[(k1 >> shift) & dmask], 1u);
+    if ((k2 & mask) == st.prefix) atomicAdd(&sh[(k2 >> shift) & dmask], 1u);
+    if ((k3 & mask) == st.prefix) atomicAdd(&sh[(k3 >> shift) & dmask], 1u);
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = (n4 << 2) + threadIdx.x; i < P.N; i += blockDim.x) {
+      u32 k0 = key32(P.neg_ce[i]);
+      if ((k0 & mask) == st.prefix) atomicAdd(&sh[(k0 >> shift) & dmask], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
+    u32 v = sh[i];
+    if (v) atomicAdd(&P.ws->hist[level][i], v);
+  }
+}
+
+__global__ void __launch_bounds__(256) final_kernel(LossParams P) {
+  __shared__ u32 sh[kBins];
+  __shared__ int sh_bin;
+  __shared__ long long sh_above;
+  __shared__ double sh_np;
+  __shared__ double redd[8];
+  __shared__ u32 redc[8], redo[8];
+  __shared__ bool is_last;
+  SelectState st;
+  derive_state(P, 3, st, sh, threadIdx.x, blockDim.x, &sh_bin, &sh_above, &sh_np);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 kth = st.prefix;
+  double sum = 0;
+  u32 cnt = 0, ovl = 0;
+  if (!st.status) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < P.N; i += (long long)gridDim.x * blockDim.x) {
+      const float v = P.neg_ce[i];
+      const bool neg = key32(v) >= kth;
+      if (neg) {
+        sum += (double)v;
+        cnt += 1;
+        if (P.gt_mask[i]) ovl += 1;
+      }
+      if (P.neg_mask) P.neg_mask[i] = neg ? 1 : 0;
+    }
+  } else if (P.neg_mask) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < P.N; i += (long long)gridDim.x * blockDim.x) P.neg_mask[i] = 0;
+  }
+  sum = warp_sum(sum);
+  cnt = __reduce_add_sync(SSDG_FULL, cnt);
+  ovl = __reduce_add_sync(SSDG_FULL, ovl);
+  if (lane == 0) { redd[warp] = sum; redc[warp] = cnt; redo[warp] = ovl; }
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0; u32 c = 0, o = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { s += redd[w]; c += redc[w]; o += redo[w]; }
+    P.ws->fpart[blockIdx.x][0] = s;
+    P.ws->fcount[blockIdx.x][0] = c;
+    P.ws->fcount[blockIdx.x][1] = o;
+    __threadfence();
+    is_last = atomicAdd(&P.ws->ticket[0], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last || tid != 0) return;
+  __threadfence();
+  // deterministic final reduction, fixed order
+  double s_pos = 0, s_l1 = 0, s_neg = 0;
+  unsigned long long n_neg = 0, n_ovl = 0;
+  const int np = (int)P.ws->nparts[0];
+  for (int i = 0; i < np; ++i) { s_pos += P.ws->part[i][0]; s_l1 += P.ws->part[i][1]; }
+  for (int i = 0; i < (int)gridDim.x; ++i) {
+    s_neg += ((volatile double*)P.ws->fpart[i])[0];
+    n_neg += ((volatile u32*)P.ws->fcount[i])[0];
+    n_ovl += ((volatile u32*)P.ws->fcount[i])[1];
+  }
+  double* r = P.result;
+  int status = st.status;
+  if (!status && n_ovl) status = SSDG_ERR_POS_NEG_OVERLAP;  // models/ssd_model.py:375 (positives mined as negatives)
+  const double nan = CUDART_NAN;
+  const double l_pos = status ? nan : s_pos / st.num_pos;
+  const double l_neg = status ? nan : s_neg / (double)n_neg;
+  const double l_loc = status ? nan : s_l1 / st.num_pos;
+  r[0] = (l_loc + l_pos) + l_neg;  // models/ssd_model.py:396
+  r[1] = l_pos; r[2] = l_neg; r[3] = l_loc;
+  r[4] = st.num_pos; r[5] = (double)n_neg;
+  r[6] = status ? nan : (double)unkey32(kth);
+  r[7] = (double)status;
+  r[8] = s_pos; r[9] = s_neg; r[10] = s_l1;
+  for (int i = 11; i < SSDG_LOSS_RESULT_LEN; ++i) r[i] = 0;
+}
+
+// ---- gradient (models/ssd_model.py:248 through :355-386) ---------------------------------------------
+//   d/d logits = softmax * (pos/Npos + neg/Nneg) - onehot(gt)*pos/Npos - onehot(bg)*neg/Nneg
+//   d/d pred_box = sign(pred - gt) * pos/Npos
+// One warp per prior row group, coalesced over the class axis; rows that are neither positive nor
+// mined negative are written as zeros without reading the logits.
+__global__ void __launch_bounds__(256) grad_kernel(LossParams P) {
+  const double* r = P.result;
+  const bool bad = r[7] != 0.0;
+  const float wpos = bad ? CUDART_NAN_F : (float)(1.0 / r[4]);
+  const float wneg = bad ? CUDART_NAN_F : (float)(1.0 / r[5]);
+  const u32 kth = key32((float)r[6]);
+  const int C = P.C;
+  const int lane = threadIdx.x & 31;
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long n = gw; n < P.N; n += nw) {
+    const bool pos = P.gt_mask[n] != 0;
+    const bool neg = !bad && key32(P.neg_ce[n]) >= kth;
+    float* g = P.grad_cls + (size_t)n * C;
+    if (!(pos || neg) && !bad) {
+      for (int c = lane; c < C; c += 32) __stcs(&g[c], 0.f);
+    } else {
+      const float* x = P.pred_cls + (size_t)n * C;
+      float m = -CUDART_INF_F;
+      for (int c = lane; c < C; c += 32) m = fmaxf(m, x[c]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(SSDG_FULL, m, o));
+      float s = 0.f;
+      for (int c = lane; c < C; c += 32) s += __expf(x[c] - m);
+      s = warp_sum(s);
+      const float w = (pos ? wpos : 0.f) + (neg ? wneg : 0.f);
+      const float inv = w / s;
+      int lab = P.gt_cls[n];
+      lab = lab < 0 ? 0 : (lab >= C ? C - 1 : lab);
+      for (int c = lane; c < C; c += 32) {
+        float v = __expf(x[c] - m) * inv;
+        if (pos && c == lab) v -= wpos;
+        if (neg && c == C - 1) v -= wneg;
+        __stcs(&g[c], v);
+      }
+    }
+    if (lane < 4) {
+      float v = 0.f;
+      if (pos) {
+        const float d = P.pred_box[n * 4 + lane] - P.gt_box[n * 4 + lane];
+        v = d > 0.f ? wpos : (d < 0.f ? -wpos : 0.f);
+      }
+      P.grad_box[n * 4 + lane] = v;
+    }
+  }
+}
+
+static int ce_warps_for(int C) {
+  const size_t budget = 200 * 1024;
+  size_t per_warp = (size_t)kStages * 32 * C * 4;
+  int w = (int)(budget / per_warp);
+  if (w > kCeWarps) w = kCeWarps;
+  return w;
+}
+static size_t ce_smem_bytes(int C, int warps) {
+  return (size_t)warps * kStages * 32 * C * 4 + kBins * 4 + kCeWarps * kStages * 8 + 3 * kCeWarps * 8 + 128;
+}
+
+}  // namespace ssdg
+
+using namespace ssdg;
+
+extern "C" size_t ssdg_loss_workspace_bytes(int64_t batch, int32_t n_priors, int32_t n_classes) {
+  (void)n_classes;
+  if (batch <= 0 || n_priors <= 0) return 0;
+  return align_up(sizeof(LossWs), 256) + align_up((size_t)batch * n_priors * 4, 256);
+}
+
+extern "C" int ssdg_multibox_loss(const int32_t* gt_cls, const float* gt_box, const uint8_t* gt_mask,
+                                  const float* pred_box, const float* pred_cls, int64_t batch, int32_t n_priors,
+                                  int32_t n_classes, int32_t neg_ratio, double* out_result, uint8_t* out_neg_mask,
+                                  float* out_neg_ce, float* grad_box, float* grad_cls, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  if (!gt_cls || !gt_box || !gt_mask || !pred_box || !pred_cls || !out_result) return SSDG_ERR_ARG;
+  if (batch <= 0 || n_priors <= 0 || n_classes < 2 || neg_ratio <= 0) return SSDG_ERR_ARG;
+  if ((grad_box == nullptr) != (grad_cls == nullptr)) return SSDG_ERR_ARG;
+  if (((uintptr_t)pred_cls | (uintptr_t)pred_box | (uintptr_t)gt_box | (uintptr_t)out_neg_ce) & 15) return SSDG_ERR_ALIGN;
+  if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < ssdg_loss_workspace_bytes(batch, n_priors, n_classes))
+    return SSDG_ERR_WORKSPACE;
+  const int warps = ce_warps_for(n_classes);
+  if (warps < 1) return SSDG_ERR_LIMIT;
+  cudaStream_t st = (cudaStream_t)stream;
+  LossParams P;
+  P.gt_cls = gt_cls; P.gt_box = gt_box; P.gt_mask = gt_mask; P.pred_box = pred_box; P.pred_cls = pred_cls;
+  P.N = (long long)batch * n_priors; P.C = n_classes; P.ratio = neg_ratio;
+  P.ws = (LossWs*)workspace;
+  P.neg_ce = out_neg_ce ? out_neg_ce : (float*)((unsigned char*)workspace + align_up(sizeof(LossWs), 256));
+  P.neg_mask = out_neg_mask; P.result = out_result; P.grad_box = grad_box; P.grad_cls = grad_cls;
+  SSDG_CUDA_TRY(cudaMemsetAsync(&P.ws->hist[0][0], 0, sizeof(P.ws->hist) + sizeof(P.ws->ticket) + sizeof(P.ws->nparts), st));
+  const size_t smem = ce_smem_bytes(n_classes, warps);
+  SSDG_CUDA_TRY(cudaFuncSetAttribute(ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = sm_count();
+  if (grid > 256) grid = 256;
+  const long long tiles = (P.N + 31) / 32;
+  const long long need = (tiles + warps - 1) / warps;
+  if (need < grid) grid = (int)need;
+  prof_begin(SSDG_PROF_CE, st);
+  ce_kernel<<<grid, kCeThreads, smem, st>>>(P, warps);
+  prof_end(SSDG_PROF_CE, st);
+  SSDG_LAUNCH_CHECK();
+  int sgrid = sm_count() * 4;
+  const long long sneed = (P.N / 4 + 255) / 256;
+  if (sneed < sgrid) sgrid = (int)(sneed > 0 ? sneed : 1);
+  if (sgrid > 1024) sgrid = 1024;
+  select_kernel<<<sgrid, 256, 0, st>>>(P, 1);
+  select_kernel<<<sgrid, 256, 0, st>>>(P, 2);
+  final_kernel<<<sgrid, 256, 0, st>>>(P);
+  SSDG_LAUNCH_CHECK();
+  if (grad_cls) {
+    int ggrid = sm_count() * 8;
+    grad_kernel<<<ggrid, 256, 0, st>>>(P);
+    SSDG_LAUNCH_CHECK();
+  }
+  return SSDG_OK;
+}

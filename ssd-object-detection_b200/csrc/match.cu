@@ -1,0 +1,523 @@
+// Target assignment for a batch of images: IoU matching with the reference's greedy forced
+// assignment + threshold matching + offset encoding, one CTA per image (persistent grid).
+//
+// Reference semantics reproduced bit for bit (utils/bbox.py:44-101, models/ssd_model.py:211-224):
+//   * IoU in the reference's exact operation order and dtype mix (iou_corners, common.cuh).
+//   * Phase 1 (utils/bbox.py:62-68): T rounds of whole-matrix first-arg-max with row+column
+//     knock-out (knocked-out entries read as 0.0 and still take part in the arg-max).
+//   * Phase 2 (:71-79) == for every prior not taken in phase 1: first-arg-max ground truth over
+//     ALL rows, positive iff not (iou <= thresh).
+//   * Scatter (:84-90) in append order, later pairs overwrite; encode (:94-101).
+//
+// How the work is organised (per image, 32 priors = one warp tile, lane = prior):
+//   sweep    every warp walks its tiles; the ground-truth boxes that can overlap the tile's
+//            bounding box are found 32 at a time with one ballot (the rest have clamped
+//            intersections, provably <= the per-GT bound c_t < thresh, see gt_setup);
+//            for each surviving (tile, gt) the lanes evaluate the exact IoU, keep their
+//            column's running first-arg-max in registers (phase 2 needs nothing else) and
+//            filter against the row's running maximum in shared memory; the rare lanes that
+//            reach it append (gt, prior) to a log after a REDUX warp arg-max.
+//   resolve  the log is replayed to find each row's first arg-max column.
+//   greedy   warp 0 runs the T rounds on the cached row maxima; the CTA is only woken to
+//            rescan a row whose cached column was just taken by another row.
+//   scatter  phase-1 pairs overwrite the phase-2 outputs the sweep already stored.
+#include <math_constants.h>
+#include "common.cuh"
+
+namespace ssdg {
+
+constexpr int kMatchThreads = 512;
+constexpr int kMatchWarps = kMatchThreads / 32;
+constexpr int kLogCap = 32768;
+constexpr int kABits = 21;
+constexpr int kMaxGT = 2048;
+constexpr double kSlack = 1e-5;
+
+struct MatchParams {
+  const void* gt_boxes;
+  const float* gt_cls;
+  const int* gt_off;
+  const void* priors;
+  int B, A, max_gt, tm;  // tm = max_gt rounded up to 32
+  double thresh;
+  int* out_cls;
+  float* out_box;
+  float* out_loc;
+  uint8_t* out_mask;
+  int* out_match;
+  u32* ws_head;  // [0] next image, [1] status bits
+  u32* ws_log;   // per CTA kLogCap
+  u32* ws_elim;  // per CTA elim_words
+  int elim_words;
+};
+
+template <typename TG, typename TP>
+struct Promote {
+  typedef double type;
+};
+template <>
+struct Promote<float, float> {
+  typedef float type;
+};
+
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+  static __device__ __forceinline__ void load(const void* base, long long i, float& a, float& b, float& c,
+                                              float& d) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(base) + i);
+    a = v.x; b = v.y; c = v.z; d = v.w;
+  }
+};
+template <>
+struct Vec4<double> {
+  static __device__ __forceinline__ void load(const void* base, long long i, double& a, double& b, double& c,
+                                              double& d) {
+    const double2* p = reinterpret_cast<const double2*>(base) + 2 * i;
+    double2 u = __ldg(p), v = __ldg(p + 1);
+    a = u.x; b = u.y; c = v.x; d = v.y;
+  }
+};
+
+__device__ __forceinline__ float f_down(double v) { return __double2float_rd(v); }
+__device__ __forceinline__ float f_up(double v) { return __double2float_ru(v); }
+__device__ __forceinline__ bool finite4(double a, double b, double c, double d) {
+  return isfinite(a) && isfinite(b) && isfinite(c) && isfinite(d);
+}
+
+// apply_anchor_box for one row (utils/bbox.py:98-99), float64 arithmetic, float32 result
+// (the TensorSpec cast at models/ssd_model.py:222).
+template <typename TP>
+__device__ __forceinline__ float4 encode_row(float bx, float by, float bw, float bh, TP dx, TP dy, TP dw,
+                                             TP dh) {
+  double tx = ((double)bx - (double)dx) / (double)dw;
+  double ty = ((double)by - (double)dy) / (double)dh;
+  double rw = (double)fmaxf(bw, 1e-5f) / (double)max_nn(dw, (TP)1e-5);
+  double rh = (double)fmaxf(bh, 1e-5f) / (double)max_nn(dh, (TP)1e-5);
+  return make_float4((float)tx, (float)ty, (float)log(rw), (float)log(rh));
+}
+
+template <typename TG, typename TP>
+struct MatchSmem {
+  typedef typename Promote<TG, TP>::type R;
+  R *gx1, *gy1, *gx2, *gy2, *ga;     // ground-truth corners / area in the result dtype
+  float *cx1, *cy1, *cx2, *cy2;      // outward-rounded float cull box (+-inf when not cullable)
+  u64* rowkey;                       // running / cached row maximum (key64) over live columns
+  u64* cbkey;                        // key64 of the bound c_t on any culled pair (0: nothing culled)
+  int* rowcol;                       // first arg-max column of rowkey
+  int *pair_t, *pair_a, *rs_list;
+  uint8_t* dead;
+  u64* red_key;                      // [kMatchWarps]
+  int* red_idx;                      // [kMatchWarps]
+  int* ctl;                          // control words, see enum
+  __device__ void carve(unsigned char* base, int tm) {
+    size_t o = 0;
+    gx1 = (R*)(base + o); o += sizeof(R) * tm;
+    gy1 = (R*)(base + o); o += sizeof(R) * tm;
+    gx2 = (R*)(base + o); o += sizeof(R) * tm;
+    gy2 = (R*)(base + o); o += sizeof(R) * tm;
+    ga = (R*)(base + o); o += sizeof(R) * tm;
+    o = (o + 7) & ~(size_t)7;
+    rowkey = (u64*)(base + o); o += 8 * (size_t)tm;
+    cbkey = (u64*)(base + o); o += 8 * (size_t)tm;
+    red_key = (u64*)(base + o); o += 8 * kMatchWarps;
+    cx1 = (float*)(base + o); o += 4 * (size_t)tm;
+    cy1 = (float*)(base + o); o += 4 * (size_t)tm;
+    cx2 = (float*)(base + o); o += 4 * (size_t)tm;
+    cy2 = (float*)(base + o); o += 4 * (size_t)tm;
+    rowcol = (int*)(base + o); o += 4 * (size_t)tm;
+    pair_t = (int*)(base + o); o += 4 * (size_t)tm;
+    pair_a = (int*)(base + o); o += 4 * (size_t)tm;
+    rs_list = (int*)(base + o); o += 4 * (size_t)tm;
+    red_idx = (int*)(base + o); o += 4 * kMatchWarps;
+    ctl = (int*)(base + o); o += 4 * 16;
+    dead = (uint8_t*)(base + o);
+  }
+};
+static size_t match_smem_bytes(int tm) { return (size_t)tm * (5 * 8 + 16 + 16 + 16 + 1) + 12 * kMatchWarps + 64 + 64; }
+
+enum { C_IMG = 0, C_LOGN, C_NRS, C_DONE, C_ROUND, C_DEGEN, C_MINELIM, C_MINDEAD, C_OVERFLOW };
+
+template <typename TG, typename TP>
+__global__ void __launch_bounds__(kMatchThreads, 1) match_kernel(MatchParams P) {
+  typedef typename Promote<TG, TP>::type R;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  MatchSmem<TG, TP> S;
+  S.carve(smem_raw, P.tm);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int A = P.A;
+  const int ntiles = (A + 31) >> 5;
+  const R EPS = (R)1e-10;
+  u32* log = P.ws_log + (size_t)blockIdx.x * kLogCap;
+  u32* elim = P.ws_elim + (size_t)blockIdx.x * P.elim_words;
+  const u64 thr_key = key64((double)(R)P.thresh);
+
+  auto load_prior = [&](int a, Corners<R>& p, bool& safe, TP& dx, TP& dy, TP& dw, TP& dh) {
+    Vec4<TP>::load(P.priors, a, dx, dy, dw, dh);
+    Corners<TP> c = corners_of<TP>(dx, dy, dw, dh);
+    p.x1 = (R)c.x1; p.y1 = (R)c.y1; p.x2 = (R)c.x2; p.y2 = (R)c.y2; p.area = (R)c.area;
+    safe = finite4((double)p.x1, (double)p.y1, (double)p.x2, (double)p.y2) && (double)p.area >= 0.0 &&
+           isfinite((double)p.area);
+  };
+  auto load_gt = [&](int t) {
+    Corners<R> g;
+    g.x1 = S.gx1[t]; g.y1 = S.gy1[t]; g.x2 = S.gx2[t]; g.y2 = S.gy2[t]; g.area = S.ga[t];
+    return g;
+  };
+  auto elim_test = [&](int a) { return (elim[a >> 5] >> (a & 31)) & 1u; };
+
+  // CTA-wide exact rescan of row t over the live columns; result -> rowkey[t], rowcol[t].
+  auto rescan_row = [&](int t, bool use_cull) {
+    Corners<R> g = load_gt(t);
+    const float c1 = S.cx1[t], c2 = S.cy1[t], c3 = S.cx2[t], c4 = S.cy2[t];
+    u64 bk = 0;
+    int ba = 0x7fffffff;
+    for (int a = tid; a < A; a += kMatchThreads) {
+      if (elim_test(a)) continue;
+      Corners<R> p; bool safe; TP dx, dy, dw, dh;
+      load_prior(a, p, safe, dx, dy, dw, dh);
+      if (use_cull && safe) {
+        bool ov = !(c3 <= f_down((double)p.x1) || c1 >= f_up((double)p.x2) || c4 <= f_down((double)p.y1) ||
+                    c2 >= f_up((double)p.y2));
+        if (!ov) continue;
+      }
+      u64 k = key64((double)iou_corners<R>(g, p, EPS));
+      if (k > bk) { bk = k; ba = a; }
+    }
+    warp_argmax_u64(bk, ba);
+    if (lane == 0) { S.red_key[warp] = bk; S.red_idx[warp] = ba; }
+    __syncthreads();
+    if (warp == 0) {
+      u64 k = lane < kMatchWarps ? S.red_key[lane] : 0ull;
+      int i = lane < kMatchWarps ? S.red_idx[lane] : 0x7fffffff;
+      warp_argmax_u64(k, i);
+      if (lane == 0) { S.rowkey[t] = k; S.rowcol[t] = i; }
+    }
+    __syncthreads();
+  };
+  auto rescan_trusted = [&](int t) {
+    rescan_row(t, true);
+    if (S.rowcol[t] == 0x7fffffff || S.rowkey[t] <= S.cbkey[t]) rescan_row(t, false);
+  };
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) S.ctl[C_IMG] = (int)atomicAdd(&P.ws_head[0], 1u);
+    __syncthreads();
+    const int img = S.ctl[C_IMG];
+    if (img >= P.B) break;
+    const int g0 = P.gt_off[img];
+    int T = P.gt_off[img + 1] - g0;
+    if (T < 0) T = 0;
+    bool bad = false;
+    if (T > P.max_gt) { if (tid == 0) atomicOr(&P.ws_head[1], 1u); bad = true; }
+    if (T > A) { if (tid == 0) atomicOr(&P.ws_head[1], 2u); bad = true; }
+    if (bad) T = 0;  // outputs for the image are still fully written (all unmatched)
+    const size_t obase = (size_t)img * A;
+
+    // ---- per-image setup -------------------------------------------------------------------
+    for (int t = tid; t < T; t += kMatchThreads) {
+      TG cx, cy, w, h;
+      Vec4<TG>::load(P.gt_boxes, g0 + t, cx, cy, w, h);
+      Corners<TG> c = corners_of<TG>(cx, cy, w, h);
+      R x1 = (R)c.x1, y1 = (R)c.y1, x2 = (R)c.x2, y2 = (R)c.y2, ar = (R)c.area;
+      S.gx1[t] = x1; S.gy1[t] = y1; S.gx2[t] = x2; S.gy2[t] = y2; S.ga[t] = ar;
+      // c_t: an upper bound on the IoU of any pair with a clamped intersection extent
+      // (inter <= 1e-10 * E, denominator >= a1 + 1e-10 - inter when the prior's area >= 0).
+      double E = fmax(fmax((double)x2 - (double)x1, (double)y2 - (double)y1), 1e-10);
+      double a1 = (double)ar;
+      double imax = 1e-10 * E * (1.0 + kSlack);
+      bool ok = finite4((double)x1, (double)y1, (double)x2, (double)y2) && isfinite(a1) && a1 >= 0.0 &&
+                imax <= 0.5 * (a1 + 1e-10);
+      double cb = ok ? imax / (a1 + 1e-10 - imax) * (1.0 + kSlack) : CUDART_INF;
+      ok = ok && cb < (double)(R)P.thresh * (1.0 - kSlack);
+      S.cbkey[t] = ok ? key64(cb) : 0ull;
+      S.cx1[t] = ok ? f_down((double)x1) : -CUDART_INF_F;
+      S.cy1[t] = ok ? f_down((double)y1) : -CUDART_INF_F;
+      S.cx2[t] = ok ? f_up((double)x2) : CUDART_INF_F;
+      S.cy2[t] = ok ? f_up((double)y2) : CUDART_INF_F;
+      S.rowkey[t] = 0ull;
+      S.rowcol[t] = 0x7fffffff;
+      S.dead[t] = 0;
+    }
+    for (int w = tid; w < P.elim_words; w += kMatchThreads) elim[w] = 0u;
+    if (tid == 0) {
+      S.ctl[C_LOGN] = 0; S.ctl[C_NRS] = 0; S.ctl[C_DONE] = 0; S.ctl[C_ROUND] = 0; S.ctl[C_DEGEN] = 0;
+      S.ctl[C_MINELIM] = 0x7fffffff; S.ctl[C_MINDEAD] = 0x7fffffff; S.ctl[C_OVERFLOW] = 0;
+    }
+    __syncthreads();
+
+    // ---- sweep ---------------------------------------------------------------------------------
+    for (int tile = warp; tile < ntiles; tile += kMatchWarps) {
+      const int a = (tile << 5) + lane;
+      const bool valid = a < A;
+      Corners<R> p; bool safe = true;
+      TP dx = 0, dy = 0, dw = 1, dh = 1;
+      p.x1 = p.y1 = p.x2 = p.y2 = p.area = (R)0;
+      if (valid) load_prior(a, p, safe, dx, dy, dw, dh);
+      // tile bounding box, rounded outwards to float (REDUX on order-preserving keys)
+      float tx1 = unkey32(__reduce_min_sync(SSDG_FULL, valid && safe ? key32(f_down((double)p.x1)) : ~0u));
+      float ty1 = unkey32(__reduce_min_sync(SSDG_FULL, valid && safe ? key32(f_down((double)p.y1)) : ~0u));
+      float tx2 = unkey32(__reduce_max_sync(SSDG_FULL, valid && safe ? key32(f_up((double)p.x2)) : 0u));
+      float ty2 = unkey32(__reduce_max_sync(SSDG_FULL, valid && safe ? key32(f_up((double)p.y2)) : 0u));
+      if (!__all_sync(SSDG_FULL, safe)) { tx1 = ty1 = -CUDART_INF_F; tx2 = ty2 = CUDART_INF_F; }
+
+      u64 ckey = 0ull;
+      int ct = -1;
+      for (int t0 = 0; t0 < T; t0 += 32) {
+        const int tl = t0 + lane;
+        bool ov = false;
+        if (tl < T) ov = !(S.cx2[tl] <= tx1 || S.cx1[tl] >= tx2 || S.cy2[tl] <= ty1 || S.cy1[tl] >= ty2);
+        u32 m = __ballot_sync(SSDG_FULL, ov);
+        while (m) {
+          const int t = t0 + __ffs(m) - 1;
+          m &= m - 1;
+          Corners<R> g = load_gt(t);
+          u64 key = valid ? key64((double)iou_corners<R>(g, p, EPS)) : 0ull;
+          if (key > ckey) { ckey = key; ct = t; }
+          const u64 rk = *reinterpret_cast<volatile u64*>(&S.rowkey[t]);
+          const bool pass = valid && key >= rk;
+          if (__any_sync(SSDG_FULL, pass)) {
+            const u64 wmax = warp_max_u64(pass ? key : 0ull);
+            const bool top = pass && key == wmax;
+            const u32 tmask = __ballot_sync(SSDG_FULL, top);
+            const int leader = __ffs(tmask) - 1;
+            int base = 0;
+            if (lane == leader) {
+              base = atomicAdd(&S.ctl[C_LOGN], __popc(tmask));
+              atomicMax(&S.rowkey[t], wmax);
+            }
+            base = __shfl_sync(SSDG_FULL, base, leader);
+            if (top) {
+              int pos = base + __popc(tmask & ((1u << lane) - 1u));
+              if (pos < kLogCap) log[pos] = ((u32)t << kABits) | (u32)a;
+              else S.ctl[C_OVERFLOW] = 1;
+            }
+          }
+        }
+      }
+      // phase-2 result for this prior (phase-1 priors are overwritten after the greedy rounds)
+      if (valid) {
+        const bool pos = ckey > thr_key;
+        float bx = 0.f, by = 0.f, bw = 0.f, bh = 0.f;
+        int lab = 0;
+        if (pos) {
+          TG gx, gy, gw, gh;
+          Vec4<TG>::load(P.gt_boxes, g0 + ct, gx, gy, gw, gh);
+          bx = (float)gx; by = (float)gy; bw = (float)gw; bh = (float)gh;
+          lab = (int)__ldg(P.gt_cls + g0 + ct);
+        }
+        if (P.out_cls) P.out_cls[obase + a] = lab;
+        if (P.out_mask) P.out_mask[obase + a] = pos ? 1 : 0;
+        if (P.out_match) P.out_match[obase + a] = pos ? ct : -1;
+        if (P.out_box) reinterpret_cast<float4*>(P.out_box)[obase + a] = make_float4(bx, by, bw, bh);
+        if (P.out_loc) reinterpret_cast<float4*>(P.out_loc)[obase + a] = encode_row<TP>(bx, by, bw, bh, dx, dy, dw, dh);
+      }
+    }
+    __syncthreads();
+    if (T == 0) continue;
+
+    // ---- resolve the row arg-max columns from the log ---------------------------------------------
+    {
+      const bool overflow = S.ctl[C_OVERFLOW] != 0;
+      const int n = min(S.ctl[C_LOGN], kLogCap);
+      if (!overflow) {
+        for (int e = tid; e < n; e += kMatchThreads) {
+          const u32 v = log[e];
+          const int t = (int)(v >> kABits), a = (int)(v & ((1u << kABits) - 1u));
+          Corners<R> p; bool safe; TP dx, dy, dw, dh;
+          load_prior(a, p, safe, dx, dy, dw, dh);
+          Corners<R> g = load_gt(t);
+          if (key64((double)iou_corners<R>(g, p, EPS)) == S.rowkey[t]) atomicMin(&S.rowcol[t], a);
+        }
+      }
+      __syncthreads();
+      // rows whose cached maximum cannot be trusted get an exact, un-culled rescan
+      for (int t = tid; t < T; t += kMatchThreads) {
+        if (overflow || S.rowcol[t] == 0x7fffffff || S.rowkey[t] <= S.cbkey[t])
+          S.rs_list[atomicAdd(&S.ctl[C_NRS], 1)] = t;
+      }
+      if (overflow && tid == 0) atomicOr(&P.ws_head[1], 4u);
+      __syncthreads();
+      const int nrs = S.ctl[C_NRS];
+      for (int i = 0; i < nrs; ++i) rescan_row(S.rs_list[i], false);
+      if (tid == 0) S.ctl[C_NRS] = 0;
+      __syncthreads();
+    }
+
+    // ---- greedy rounds (utils/bbox.py:62-68) --------------------------------------------------------
+    for (;;) {
+      if (warp == 0) {
+        int round = S.ctl[C_ROUND];
+        int nrs = 0;
+        while (round < T) {
+          u64 bk = 0ull;
+          int bt = 0x7fffffff;
+          for (int t = lane; t < T; t += 32) {
+            if (!S.dead[t]) {
+              u64 k = S.rowkey[t];
+              if (k > bk) { bk = k; bt = t; }
+            }
+          }
+          warp_argmax_u64(bk, bt);
+          int wt, wa;
+          if (bk > SSDG_KEY_ZERO || round == 0) {
+            wt = bt;
+            wa = S.rowcol[bt];
+          } else {
+            // Knocked-out entries (0.0) tie with or beat every live entry: full rule, first flat index.
+            if (lane == 0) {
+              u64 best = 0ull;
+              long long bflat = 0x7fffffffffffffffll;
+              const int me = S.ctl[C_MINELIM];
+              for (int t = 0; t < T; ++t) {
+                u64 k; long long f;
+                if (S.dead[t]) { k = SSDG_KEY_ZERO; f = (long long)t * A; }
+                else {
+                  k = S.rowkey[t]; f = (long long)t * A + S.rowcol[t];
+                  if (k > best || (k == best && f < bflat)) { best = k; bflat = f; }
+                  k = SSDG_KEY_ZERO; f = (long long)t * A + me;
+                }
+                if (k > best || (k == best && f < bflat)) { best = k; bflat = f; }
+              }
+              S.red_idx[0] = (int)(bflat / A);
+              S.red_idx[1] = (int)(bflat % A);
+              S.ctl[C_DEGEN] = 1;
+            }
+            __syncwarp();
+            wt = S.red_idx[0];
+            wa = S.red_idx[1];
+          }
+          const bool fresh = !elim_test(wa);
+          __syncwarp();
+          if (lane == 0) {
+            S.pair_t[round] = wt;
+            S.pair_a[round] = wa;
+            S.dead[wt] = 1;
+            elim[wa >> 5] |= 1u << (wa & 31);
+            if (wa < S.ctl[C_MINELIM]) S.ctl[C_MINELIM] = wa;
+          }
+          __syncwarp();
+          ++round;
+          if (fresh && round < T) {
+            for (int t0 = 0; t0 < T; t0 += 32) {
+              const int t = t0 + lane;
+              const bool need = t < T && !S.dead[t] && S.rowcol[t] == wa;
+              const u32 nm = __ballot_sync(SSDG_FULL, need);
+              if (need) S.rs_list[nrs + __popc(nm & ((1u << lane) - 1u))] = t;
+              nrs += __popc(nm);
+            }
+          }
+          if (nrs > 0) break;
+        }
+        if (lane == 0) { S.ctl[C_ROUND] = round; S.ctl[C_NRS] = nrs; S.ctl[C_DONE] = round >= T; }
+      }
+      __syncthreads();
+      const int nrs = S.ctl[C_NRS];
+      const bool done = S.ctl[C_DONE] != 0;
+      if (done && nrs == 0) break;
+      for (int i = 0; i < nrs; ++i) rescan_trusted(S.rs_list[i]);
+      if (tid == 0) S.ctl[C_NRS] = 0;
+      __syncthreads();
+      if (done) break;
+    }
+
+    // ---- scatter the phase-1 pairs (utils/bbox.py:87-90; later pairs win) ----------------------------
+    const bool degen = S.ctl[C_DEGEN] != 0;
+    for (int k = tid; k < T; k += kMatchThreads) {
+      const int t = S.pair_t[k], a = S.pair_a[k];
+      bool last = true;
+      if (degen)
+        for (int k2 = k + 1; k2 < T; ++k2)
+          if (S.pair_a[k2] == a) { last = false; break; }
+      if (!last) continue;
+      TG gx, gy, gw, gh;
+      Vec4<TG>::load(P.gt_boxes, g0 + t, gx, gy, gw, gh);
+      const float bx = (float)gx, by = (float)gy, bw = (float)gw, bh = (float)gh;
+      if (P.out_cls) P.out_cls[obase + a] = (int)__ldg(P.gt_cls + g0 + t);
+      if (P.out_mask) P.out_mask[obase + a] = 1;
+      if (P.out_match) P.out_match[obase + a] = t;
+      if (P.out_box) reinterpret_cast<float4*>(P.out_box)[obase + a] = make_float4(bx, by, bw, bh);
+      if (P.out_loc) {
+        TP dx, dy, dw, dh;
+        Vec4<TP>::load(P.priors, a, dx, dy, dw, dh);
+        reinterpret_cast<float4*>(P.out_loc)[obase + a] = encode_row<TP>(bx, by, bw, bh, dx, dy, dw, dh);
+      }
+    }
+  }
+}
+
+template <typename TG, typename TP>
+static int launch_match(const MatchParams& P, int grid, size_t smem, cudaStream_t st) {
+  if (smem > 48 * 1024)
+    SSDG_CUDA_TRY(cudaFuncSetAttribute(match_kernel<TG, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prof_begin(SSDG_PROF_MATCH, st);
+  match_kernel<TG, TP><<<grid, kMatchThreads, smem, st>>>(P);
+  prof_end(SSDG_PROF_MATCH, st);
+  SSDG_LAUNCH_CHECK();
+  return SSDG_OK;
+}
+
+static int match_grid(int batch) {
+  int g = sm_count();
+  return batch < g ? batch : g;
+}
+
+}  // namespace ssdg
+
+using namespace ssdg;
+
+extern "C" size_t ssdg_match_workspace_bytes(int32_t batch, int32_t n_priors, int32_t max_gt) {
+  (void)max_gt;
+  if (batch <= 0 || n_priors <= 0) return 0;
+  size_t ctas = 256;  // >= any SM count this library targets; the grid never exceeds it
+  size_t elim_words = ((size_t)n_priors + 31) / 32;
+  return 256 + ctas * (size_t)kLogCap * 4 + align_up(ctas * elim_words * 4, 256);
+}
+
+extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const float* gt_cls,
+                                 const int32_t* gt_offsets, const void* priors, int32_t prior_dtype,
+                                 int32_t batch, int32_t n_priors, int32_t max_gt, double thresh,
+                                 int32_t* out_cls, float* out_box, float* out_loc, uint8_t* out_mask,
+                                 int32_t* out_match, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!gt_boxes || !gt_cls || !gt_offsets || !priors || batch <= 0 || n_priors <= 0 || max_gt < 0) return SSDG_ERR_ARG;
+  if ((gt_dtype != SSDG_F32 && gt_dtype != SSDG_F64) || (prior_dtype != SSDG_F32 && prior_dtype != SSDG_F64))
+    return SSDG_ERR_ARG;
+  if (!(thresh > 0.0)) return SSDG_ERR_THRESH;
+  if (n_priors >= (1 << kABits) || max_gt > kMaxGT) return SSDG_ERR_LIMIT;
+  if (max_gt > n_priors) max_gt = n_priors;  // images with more GT than priors raise status bit 1
+  if (((uintptr_t)gt_boxes | (uintptr_t)priors | (uintptr_t)out_box | (uintptr_t)out_loc) & 15) return SSDG_ERR_ALIGN;
+  if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < ssdg_match_workspace_bytes(batch, n_priors, max_gt))
+    return SSDG_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = match_grid(batch);
+  if (grid > 256) grid = 256;
+  MatchParams P;
+  P.gt_boxes = gt_boxes; P.gt_cls = gt_cls; P.gt_off = gt_offsets; P.priors = priors;
+  P.B = batch; P.A = n_priors; P.max_gt = max_gt; P.tm = ((max_gt + 31) / 32) * 32;
+  if (P.tm == 0) P.tm = 32;
+  P.thresh = thresh;
+  P.out_cls = out_cls; P.out_box = out_box; P.out_loc = out_loc; P.out_mask = out_mask; P.out_match = out_match;
+  P.elim_words = (n_priors + 31) / 32;
+  unsigned char* w = (unsigned char*)workspace;
+  P.ws_head = (u32*)w;
+  P.ws_log = (u32*)(w + 256);
+  P.ws_elim = (u32*)(w + 256 + (size_t)256 * kLogCap * 4);
+  SSDG_CUDA_TRY(cudaMemsetAsync(P.ws_head, 0, 256, st));
+  size_t smem = match_smem_bytes(P.tm);
+  if ((int)smem > max_smem_optin()) return SSDG_ERR_LIMIT;
+  if (gt_dtype == SSDG_F32 && prior_dtype == SSDG_F64) return launch_match<float, double>(P, grid, smem, st);
+  if (gt_dtype == SSDG_F32 && prior_dtype == SSDG_F32) return launch_match<float, float>(P, grid, smem, st);
+  if (gt_dtype == SSDG_F64 && prior_dtype == SSDG_F64) return launch_match<double, double>(P, grid, smem, st);
+  return launch_match<double, float>(P, grid, smem, st);
+}
+
+extern "C" int ssdg_match_status(const void* workspace, int32_t* status, void* stream) {
+  if (!workspace || !status) return SSDG_ERR_ARG;
+  u32 head[2];
+  SSDG_CUDA_TRY(cudaMemcpyAsync(head, workspace, sizeof(head), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  SSDG_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  *status = (int32_t)head[1];
+  return SSDG_OK;
+}

@@ -1,0 +1,107 @@
+"""ctypes binding of libssdgeom.so (include/ssdgeom.h).  There is no fallback: if the library
+is missing or CUDA is unavailable, calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libssdgeom.so")
+
+OK = 0
+ERR_ARG, ERR_TOO_MANY_GT, ERR_THRESH, ERR_SHAPE, ERR_NO_POSITIVE = -1, -2, -3, -4, -5
+ERR_TOPK_RANGE, ERR_WORKSPACE, ERR_ALIGN, ERR_LIMIT, ERR_POS_NEG_OVERLAP = -6, -7, -8, -9, -10
+F32, F64 = 0, 1
+LOSS_RESULT_LEN = 16
+PROF_MATCH, PROF_CE, PROF_FILTER, PROF_NMS = 0, 1, 2, 3
+
+_vp, _i32, _i64, _f32, _f64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_size_t
+_pi32, _pf64 = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+
+# name -> (restype, argtypes); every symbol include/ssdgeom.h declares
+PROTOTYPES = {
+    "ssdg_status_string": (C.c_char_p, [C.c_int]),
+    "ssdg_version": (C.c_int, []),
+    "ssdg_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "ssdg_set_device": (C.c_int, [C.c_int]),
+    "ssdg_device_alloc": (C.c_int, [C.POINTER(_vp), _sz]),
+    "ssdg_device_free": (C.c_int, [_vp]),
+    "ssdg_host_alloc": (C.c_int, [C.POINTER(_vp), _sz]),
+    "ssdg_host_free": (C.c_int, [_vp]),
+    "ssdg_memcpy_h2d": (C.c_int, [_vp, _vp, _sz, _vp]),
+    "ssdg_memcpy_d2h": (C.c_int, [_vp, _vp, _sz, _vp]),
+    "ssdg_memset": (C.c_int, [_vp, C.c_int, _sz, _vp]),
+    "ssdg_stream_create": (C.c_int, [C.POINTER(_vp)]),
+    "ssdg_stream_destroy": (C.c_int, [_vp]),
+    "ssdg_stream_sync": (C.c_int, [_vp]),
+    "ssdg_event_create": (C.c_int, [C.POINTER(_vp)]),
+    "ssdg_event_destroy": (C.c_int, [_vp]),
+    "ssdg_event_record": (C.c_int, [_vp, _vp]),
+    "ssdg_stream_wait_event": (C.c_int, [_vp, _vp]),
+    "ssdg_event_elapsed_ms": (C.c_int, [_vp, _vp, C.POINTER(_f32)]),
+    "ssdg_profile_enable": (C.c_int, [C.c_int]),
+    "ssdg_profile_last_ms": (C.c_int, [C.c_int, C.POINTER(_f32)]),
+    "ssdg_prior_count": (_i64, [_pi32, _pi32, _pi32, _i32]),
+    "ssdg_prior_boxes": (C.c_int, [_pi32, _pi32, _pf64, _pi32, _pf64, _i32, _f64, _vp, _i64, _vp]),
+    "ssdg_match_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "ssdg_match_encode": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f64,
+                                    _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ssdg_match_status": (C.c_int, [_vp, _pi32, _vp]),
+    "ssdg_encode": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _i32, _vp]),
+    "ssdg_decode": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _f64, _vp, _vp]),
+    "ssdg_iou_pairs": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _vp]),
+    "ssdg_loss_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "ssdg_multibox_loss": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
+                                     _vp, _sz, _vp]),
+    "ssdg_detect_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
+    "ssdg_detect": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp, _vp,
+                              _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ssdg_nms": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
+}
+
+_lib = None
+
+
+class SsdgeomError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the library with prototypes attached."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise SsdgeomError(
+                "libssdgeom.so is not built (%s). Run `python ssd-object-detection_b200/build_native.py` "
+                "or __graft_entry__.build(); there is no CPU fallback." % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def status_string(status: int) -> str:
+    return lib().ssdg_status_string(int(status)).decode()
+
+
+def check(status: int, what: str = ""):
+    """Map a status code to the exception type the reference would raise: the reference's
+    asserts (utils/bbox.py:50-51, models/ssd_model.py:347-351,375) are AssertionError;
+    everything else is ValueError (argument) or SsdgeomError (CUDA)."""
+    status = int(status)
+    if status == OK:
+        return
+    msg = "%s%s" % (what + ": " if what else "", status_string(status))
+    if status in (ERR_TOO_MANY_GT, ERR_THRESH, ERR_SHAPE, ERR_POS_NEG_OVERLAP):
+        raise AssertionError(msg)
+    if status < 0:
+        raise ValueError(msg)
+    raise SsdgeomError("CUDA error %d: %s" % (status, msg))
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    lib().ssdg_device_count(C.byref(n))
+    return n.value

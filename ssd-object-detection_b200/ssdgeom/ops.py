@@ -1,0 +1,243 @@
+"""Thin, allocation-explicit Python wrappers over the C ABI (include/ssdgeom.h).  Everything
+here works on device memory (``device.DeviceArray`` or any ``__cuda_array_interface__`` object)
+and is asynchronous on the given stream.  The reference-named drop-ins live in
+``ssdgeom.utils.bbox`` and ``ssdgeom.models.ssd_model``."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from . import device as D
+
+_DT = {np.dtype(np.float32): N.F32, np.dtype(np.float64): N.F64}
+
+
+def _code(dtype) -> int:
+    try:
+        return _DT[np.dtype(dtype)]
+    except KeyError:
+        raise TypeError("boxes must be float32 or float64, got %s" % dtype)
+
+
+class WorkspacePool:
+    """Grow-only device scratch, one buffer per kernel family so families can overlap on
+    different streams."""
+
+    def __init__(self):
+        self._buf = {}
+
+    def get(self, kind: str, nbytes: int) -> D.DeviceArray:
+        cur = self._buf.get(kind)
+        if cur is None or cur.nbytes < nbytes:
+            cur = D.empty((int(nbytes) + 255) // 256 * 256, np.uint8)
+            self._buf[kind] = cur
+        return cur
+
+
+POOL = WorkspacePool()
+
+
+def _p(x):
+    return None if x is None else x.ptr
+
+
+# ---- A1 ------------------------------------------------------------------------------------------
+def prior_boxes(size_list, s_k_refer, aspect_ratio, input_size=300, stream=None) -> D.DeviceArray:
+    """models/ssd_model.py:173-194 with the tables lifted to arguments; float64 [A,4] on the device."""
+    n = len(size_list)
+    if len(s_k_refer) != n + 1 or len(aspect_ratio) != n:
+        raise ValueError("need len(s_k_refer) == len(size_list)+1 and one ratio list per level")
+    fh = (C.c_int32 * n)(*[int(s[0]) for s in size_list])
+    fw = (C.c_int32 * n)(*[int(s[1]) for s in size_list])
+    sk = (C.c_double * (n + 1))(*[float(v) for v in s_k_refer])
+    offs = [0]
+    flat = []
+    for r in aspect_ratio:
+        flat += [float(v) for v in r]
+        offs.append(len(flat))
+    ro = (C.c_int32 * (n + 1))(*offs)
+    rr = (C.c_double * max(len(flat), 1))(*flat)
+    lib = N.lib()
+    count = lib.ssdg_prior_count(fh, fw, ro, n)
+    if count <= 0:
+        N.check(int(count) if count < 0 else N.ERR_ARG, "prior_count")
+    out = D.empty((count, 4), np.float64)
+    N.check(lib.ssdg_prior_boxes(fh, fw, sk, ro, rr, n, float(input_size), out.ptr, count, D.stream_handle(stream)),
+            "prior_boxes")
+    return out
+
+
+# ---- A3 + A4 + A5 ----------------------------------------------------------------------------------
+def match_encode(gt_boxes, gt_cls, gt_offsets, priors, batch: int, max_gt: int, thresh: float = 0.5,
+                 want=("cls", "loc", "mask"), out=None, stream=None) -> dict:
+    """Batched match_bbox + apply_anchor_box (utils/bbox.py:44-101, models/ssd_model.py:211-224).
+    ``want`` selects outputs among cls, box, loc, mask, match; ``out`` may carry preallocated arrays."""
+    gt_boxes, priors = D.as_device(gt_boxes), D.as_device(priors)
+    gt_cls = D.as_device(gt_cls, np.float32)
+    gt_offsets = D.as_device(gt_offsets, np.int32)
+    a = int(priors.shape[0])
+    out = dict(out or {})
+    spec = {"cls": ((batch, a), np.int32), "box": ((batch, a, 4), np.float32), "loc": ((batch, a, 4), np.float32),
+            "mask": ((batch, a), np.uint8), "match": ((batch, a), np.int32)}
+    for k in want:
+        if k not in out:
+            out[k] = D.empty(*spec[k])
+    lib = N.lib()
+    nbytes = lib.ssdg_match_workspace_bytes(batch, a, max_gt)
+    ws = POOL.get("match", nbytes)
+    N.check(lib.ssdg_match_encode(gt_boxes.ptr, _code(gt_boxes.dtype), gt_cls.ptr, gt_offsets.ptr, priors.ptr,
+                                  _code(priors.dtype), batch, a, int(max_gt), float(thresh),
+                                  _p(out.get("cls")), _p(out.get("box")), _p(out.get("loc")), _p(out.get("mask")),
+                                  _p(out.get("match")), ws.ptr, ws.nbytes, D.stream_handle(stream)), "match_encode")
+    out["_keep"] = (gt_boxes, gt_cls, gt_offsets, priors, ws)
+    return out
+
+
+def match_status(stream=None) -> int:
+    st = C.c_int32(0)
+    ws = POOL.get("match", 256)
+    N.check(N.lib().ssdg_match_status(ws.ptr, C.byref(st), D.stream_handle(stream)), "match_status")
+    return st.value
+
+
+def encode(boxes, priors, out_dtype=np.float32, stream=None) -> D.DeviceArray:
+    boxes, priors = D.as_device(boxes), D.as_device(priors)
+    a = int(priors.shape[0])
+    n = boxes.size // 4
+    if n % a:
+        raise AssertionError("boxes and priors disagree in shape")  # utils/bbox.py:95
+    out = D.empty(boxes.shape, out_dtype)
+    N.check(N.lib().ssdg_encode(boxes.ptr, _code(boxes.dtype), priors.ptr, _code(priors.dtype), n // a, a, out.ptr,
+                                _code(out_dtype), D.stream_handle(stream)), "encode")
+    out._keep = (boxes, priors)
+    return out
+
+
+def decode(loc, priors, scale=300.0, stream=None) -> D.DeviceArray:
+    loc, priors = D.as_device(loc, np.float32), D.as_device(priors)
+    a = int(priors.shape[0])
+    n = loc.size // 4
+    if n % a:
+        raise AssertionError("loc and priors disagree in shape")
+    out = D.empty(loc.shape, np.float32)
+    N.check(N.lib().ssdg_decode(loc.ptr, priors.ptr, _code(priors.dtype), n // a, a, float(scale), out.ptr,
+                                D.stream_handle(stream)), "decode")
+    out._keep = (loc, priors)
+    return out
+
+
+def iou_pairs(boxes_1, boxes_2, use_eps_clamp: bool, stream=None) -> D.DeviceArray:
+    b1, b2 = D.as_device(boxes_1), D.as_device(boxes_2)
+    n = b1.size // 4
+    if b2.size // 4 != n:
+        raise ValueError("paired IoU needs equally many rows")
+    odt = np.float32 if (b1.dtype == np.float32 and b2.dtype == np.float32) else np.float64
+    out = D.empty((n,), odt)
+    N.check(N.lib().ssdg_iou_pairs(b1.ptr, _code(b1.dtype), b2.ptr, _code(b2.dtype), n, int(bool(use_eps_clamp)),
+                                   out.ptr, D.stream_handle(stream)), "iou_pairs")
+    out._keep = (b1, b2)
+    return out
+
+
+# ---- A6 ----------------------------------------------------------------------------------------------
+def multibox_loss(gt_cls, gt_box, gt_mask, pred_box, pred_cls, neg_ratio: int = 3, want_neg_mask=False,
+                  want_neg_ce=False, want_grad=False, out=None, stream=None, ws_kind="loss") -> dict:
+    """models/ssd_model.py:341-396.  Returns {'result': float64[16] device block, ...}; see
+    include/ssdgeom.h for the block layout."""
+    gt_cls = D.as_device(gt_cls, np.int32)
+    gt_box = D.as_device(gt_box, np.float32)
+    gt_mask = D.as_device(gt_mask, np.uint8)
+    pred_box = D.as_device(pred_box, np.float32)
+    pred_cls = D.as_device(pred_cls, np.float32)
+    if len(pred_cls.shape) != 3:
+        raise AssertionError("pred_cls must be [B,A,C]")
+    b, a, c = pred_cls.shape
+    # models/ssd_model.py:347-351
+    if not (gt_cls.size == b * a and gt_mask.size == b * a and gt_box.size == b * a * 4 and pred_box.size == b * a * 4):
+        raise AssertionError("y_true / y_pred disagree in shape")
+    out = dict(out or {})
+    if "result" not in out:
+        out["result"] = D.empty((N.LOSS_RESULT_LEN,), np.float64)
+    if want_neg_mask and "neg_mask" not in out:
+        out["neg_mask"] = D.empty((b, a), np.uint8)
+    if want_neg_ce and "neg_ce" not in out:
+        out["neg_ce"] = D.empty((b, a), np.float32)
+    if want_grad:
+        out.setdefault("grad_box", D.empty((b, a, 4), np.float32))
+        out.setdefault("grad_cls", D.empty((b, a, c), np.float32))
+    lib = N.lib()
+    ws = POOL.get(ws_kind, lib.ssdg_loss_workspace_bytes(b, a, c))
+    N.check(lib.ssdg_multibox_loss(gt_cls.ptr, gt_box.ptr, gt_mask.ptr, pred_box.ptr, pred_cls.ptr, b, a, c,
+                                   int(neg_ratio), out["result"].ptr, _p(out.get("neg_mask")), _p(out.get("neg_ce")),
+                                   _p(out.get("grad_box")), _p(out.get("grad_cls")), ws.ptr, ws.nbytes,
+                                   D.stream_handle(stream)), "multibox_loss")
+    out["_keep"] = (gt_cls, gt_box, gt_mask, pred_box, pred_cls, ws)
+    return out
+
+
+def loss_result_to_host(result: D.DeviceArray, stream=None) -> dict:
+    """One synchronising read of the result block; raises like the reference on the device-side
+    guards (num_pos == 0 -> IndexError at models/ssd_model.py:369; k out of range -> top_k error)."""
+    r = result.to_host(stream)
+    status = int(r[7])
+    if status == N.ERR_NO_POSITIVE:
+        raise IndexError("no positive prior in the batch: hard-negative top-k is empty (models/ssd_model.py:369)")
+    if status == N.ERR_TOPK_RANGE:
+        raise ValueError("3*num_pos exceeds the number of priors in the batch (tf.math.top_k, models/ssd_model.py:368)")
+    N.check(status, "multibox_loss")
+    return {"total": r[0], "cls loss pos": r[1], "cls loss neg": r[2], "loc loss": r[3], "num_pos": int(r[4]),
+            "num_neg": int(r[5]), "kth": r[6], "sum_pos_ce": r[8], "sum_neg_ce": r[9], "sum_l1": r[10]}
+
+
+# ---- A7 + A8 + A9 ---------------------------------------------------------------------------------------
+def detect(pred_cls, pred_box, priors, score_thresh=0.01, top_k=200, iou_thresh=0.45, want_scores=False,
+           want_boxes=False, want_probs=False, head_thresh=None, out=None, stream=None) -> dict:
+    pred_cls = D.as_device(pred_cls, np.float32)
+    pred_box = D.as_device(pred_box, np.float32)
+    priors = D.as_device(priors)
+    b, a, c = pred_cls.shape
+    if pred_box.size != b * a * 4 or priors.shape[0] != a:
+        raise AssertionError("pred_cls / pred_box / priors disagree in shape")
+    out = dict(out or {})
+    out.setdefault("kept", D.empty((b, c - 1, top_k), np.int32))
+    out.setdefault("count", D.empty((b, c - 1), np.int32))
+    if want_scores:
+        out.setdefault("kept_score", D.empty((b, c - 1, top_k), np.float32))
+    if want_boxes:
+        out.setdefault("boxes", D.empty((b, a, 4), np.float32))
+    if want_probs:
+        out.setdefault("probs", D.empty((b, a, c), np.float32))
+    if head_thresh is not None:
+        out.setdefault("head_score", D.empty((b, a), np.float32))
+        out.setdefault("head_cls", D.empty((b, a), np.int32))
+        out.setdefault("head_mask", D.empty((b, a), np.uint8))
+    lib = N.lib()
+    ws = POOL.get("detect", lib.ssdg_detect_workspace_bytes(b, a, c, top_k))
+    N.check(lib.ssdg_detect(pred_cls.ptr, pred_box.ptr, priors.ptr, _code(priors.dtype), b, a, c, float(score_thresh),
+                            int(top_k), float(iou_thresh), out["kept"].ptr, out["count"].ptr, _p(out.get("kept_score")),
+                            _p(out.get("boxes")), _p(out.get("probs")),
+                            float(head_thresh if head_thresh is not None else 0.0), _p(out.get("head_score")),
+                            _p(out.get("head_cls")), _p(out.get("head_mask")), ws.ptr, ws.nbytes,
+                            D.stream_handle(stream)), "detect")
+    out["_keep"] = (pred_cls, pred_box, priors, ws)
+    return out
+
+
+def nms(probs, boxes, score_thresh=0.01, top_k=200, iou_thresh=0.45, want_scores=False, stream=None) -> dict:
+    probs = D.as_device(probs, np.float32)
+    boxes = D.as_device(boxes, np.float32)
+    b, a, c = probs.shape
+    if boxes.size != b * a * 4:
+        raise AssertionError("probs / boxes disagree in shape")
+    out = {"kept": D.empty((b, c - 1, top_k), np.int32), "count": D.empty((b, c - 1), np.int32)}
+    if want_scores:
+        out["kept_score"] = D.empty((b, c - 1, top_k), np.float32)
+    lib = N.lib()
+    ws = POOL.get("detect", lib.ssdg_detect_workspace_bytes(b, a, c, top_k))
+    N.check(lib.ssdg_nms(probs.ptr, boxes.ptr, b, a, c, float(score_thresh), int(top_k), float(iou_thresh),
+                         out["kept"].ptr, out["count"].ptr, _p(out.get("kept_score")), ws.ptr, ws.nbytes,
+                         D.stream_handle(stream)), "nms")
+    out["_keep"] = (probs, boxes, ws)
+    return out

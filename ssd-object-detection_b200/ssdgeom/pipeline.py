@@ -1,0 +1,89 @@
+"""The chained hot path (target assignment -> multibox loss, and decode -> per-class NMS) with
+preallocated buffers and explicit streams: the call a data-parallel trainer/evaluator makes per
+batch.  The two branches only share the predictions, so they run on separate streams: the
+matcher is ALU-bound and the loss/filter passes are HBM-bound, so they overlap."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _native as N
+from . import device as D
+from . import ops
+from .models.ssd_model import SSD300
+
+
+class HotPath:
+    def __init__(self, table=None, batch=256, max_gt=100, classes=81, thresh=0.5, neg_ratio=3,
+                 score_thresh=0.01, top_k=200, iou_thresh=0.45, total_gt=None):
+        table = SSD300 if table is None else table
+        self.batch, self.max_gt, self.classes = int(batch), int(max_gt), int(classes)
+        self.thresh, self.neg_ratio = float(thresh), int(neg_ratio)
+        self.score_thresh, self.top_k, self.iou_thresh = float(score_thresh), int(top_k), float(iou_thresh)
+        self.priors = ops.prior_boxes(table["sizes"], table["s_k_refer"], table["aspect_ratio"], table["input_size"])
+        self.A = a = int(self.priors.shape[0])
+        b, c = self.batch, self.classes
+        n_gt = int(total_gt if total_gt is not None else b * self.max_gt)
+        self.gt_boxes = D.empty((n_gt, 4), np.float32)
+        self.gt_cls = D.empty((n_gt,), np.float32)
+        self.gt_off = D.empty((b + 1,), np.int32)
+        self.pred_cls = D.empty((b, a, c), np.float32)
+        self.pred_box = D.empty((b, a, 4), np.float32)
+        self.tgt = {"cls": D.empty((b, a), np.int32), "loc": D.empty((b, a, 4), np.float32),
+                    "mask": D.empty((b, a), np.uint8)}
+        self.loss = {"result": D.empty((N.LOSS_RESULT_LEN,), np.float64)}
+        self.det = {"kept": D.empty((b, c - 1, self.top_k), np.int32), "count": D.empty((b, c - 1), np.int32)}
+        self.s_main, self.s_a, self.s_d = D.Stream(), D.Stream(), D.Stream()
+        self.ev_begin, self.ev_a, self.ev_d = D.Event(), D.Event(), D.Event()
+        self.kernel_launches_per_step = 7   # match | ce, select x2, final | filter, nms
+        self.h2d_bytes = (self.gt_boxes.nbytes + self.gt_cls.nbytes + self.gt_off.nbytes + self.pred_cls.nbytes +
+                          self.pred_box.nbytes)
+        self.d2h_bytes = self.loss["result"].nbytes + self.det["kept"].nbytes + self.det["count"].nbytes
+
+    # ---- stages (asynchronous on the given stream) ---------------------------------------------------
+    def assign(self, stream):
+        ops.match_encode(self.gt_boxes, self.gt_cls, self.gt_off, self.priors, self.batch, self.max_gt, self.thresh,
+                         want=(), out=self.tgt, stream=stream)
+
+    def loss_stage(self, stream):
+        ops.multibox_loss(self.tgt["cls"], self.tgt["loc"], self.tgt["mask"], self.pred_box, self.pred_cls,
+                          self.neg_ratio, out=self.loss, stream=stream)
+
+    def detect_stage(self, stream):
+        ops.detect(self.pred_cls, self.pred_box, self.priors, self.score_thresh, self.top_k, self.iou_thresh,
+                   out=self.det, stream=stream)
+
+    def step(self):
+        """One pass of the chain over the resident batch; work is ordered on ``s_main``."""
+        self.ev_begin.record(self.s_main)
+        D.stream_wait_event(self.s_a, self.ev_begin)
+        D.stream_wait_event(self.s_d, self.ev_begin)
+        self.assign(self.s_a)
+        self.loss_stage(self.s_a)
+        self.detect_stage(self.s_d)
+        self.ev_a.record(self.s_a)
+        self.ev_d.record(self.s_d)
+        D.stream_wait_event(self.s_main, self.ev_a)
+        D.stream_wait_event(self.s_main, self.ev_d)
+
+    # ---- host-facing -------------------------------------------------------------------------------------
+    def upload(self, gt_boxes, gt_cls, gt_off, pred_cls, pred_box, stream=None):
+        """Host (ideally pinned) -> device copies of one batch, asynchronous on ``stream`` (s_main)."""
+        st = self.s_main if stream is None else stream
+        lib = N.lib()
+        for dst, src in ((self.gt_boxes, gt_boxes), (self.gt_cls, gt_cls), (self.gt_off, gt_off),
+                         (self.pred_box, pred_box), (self.pred_cls, pred_cls)):
+            assert src.nbytes == dst.nbytes and src.dtype == dst.dtype and src.flags["C_CONTIGUOUS"]
+            N.check(lib.ssdg_memcpy_h2d(dst.ptr, src.ctypes.data, dst.nbytes, D.stream_handle(st)), "h2d")
+
+    def download(self, out_result, out_kept, out_count, stream=None):
+        st = self.s_main if stream is None else stream
+        lib = N.lib()
+        for src, dst in ((self.loss["result"], out_result), (self.det["kept"], out_kept), (self.det["count"], out_count)):
+            N.check(lib.ssdg_memcpy_d2h(dst.ctypes.data, src.ptr, src.nbytes, D.stream_handle(st)), "d2h")
+
+    def step_host(self, gt_boxes, gt_cls, gt_off, pred_cls, pred_box, out_result, out_kept, out_count):
+        """End to end: host inputs in, host results out (synchronises)."""
+        self.upload(gt_boxes, gt_cls, gt_off, pred_cls, pred_box)
+        self.step()
+        self.download(out_result, out_kept, out_count)
+        self.s_main.sync()
