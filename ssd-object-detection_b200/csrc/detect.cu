@@ -76,40 +76,81 @@ __device__ __forceinline__ float4 decode_row(float4 t, const void* priors, int a
   return o;
 }
 
-// One prior: row in shared memory (may be overwritten with the probabilities).
+// One warp tile (32 priors, lane r owns row r in shared memory; the rows may be overwritten with the
+// probabilities).  Candidate emission is warp-cooperative: a ballot per class gives the tile's
+// candidate mask, the lanes then reserve list space for all classes at once (one atomic per
+// (tile, class), issued side by side so their latencies overlap) and finally scatter their entries.
 template <typename TP>
-__device__ __forceinline__ void filter_one_prior(const DetectParams& P, long long n, int b, int a, float* row) {
-  const int C = P.C;
-  float m0 = -CUDART_INF_F, m1 = m0, m2 = m0, m3 = m0;
-  int c = 0;
-  for (; c + 4 <= C; c += 4) {
-    m0 = fmaxf(m0, row[c]); m1 = fmaxf(m1, row[c + 1]); m2 = fmaxf(m2, row[c + 2]); m3 = fmaxf(m3, row[c + 3]);
+__device__ __forceinline__ void filter_tile(const DetectParams& P, long long n, int b, int a, bool valid, float* row,
+                                            u32* wmask, u32* wbase, int lane) {
+  const int C = P.C, nfg = P.C - 1;
+  float m = 0.f, s = 1.f;
+  if (valid) {
+    float m0 = -CUDART_INF_F, m1 = m0, m2 = m0, m3 = m0;
+    int c = 0;
+    for (; c + 4 <= C; c += 4) {
+      m0 = fmaxf(m0, row[c]); m1 = fmaxf(m1, row[c + 1]); m2 = fmaxf(m2, row[c + 2]); m3 = fmaxf(m3, row[c + 3]);
+    }
+    for (; c < C; ++c) m0 = fmaxf(m0, row[c]);
+    m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    c = 0;
+    for (; c + 4 <= C; c += 4) {
+      s0 += __expf(row[c] - m); s1 += __expf(row[c + 1] - m); s2 += __expf(row[c + 2] - m); s3 += __expf(row[c + 3] - m);
+    }
+    for (; c < C; ++c) s0 += __expf(row[c] - m);
+    s = (s0 + s1) + (s2 + s3);
   }
-  for (; c < C; ++c) m0 = fmaxf(m0, row[c]);
-  const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  c = 0;
-  for (; c + 4 <= C; c += 4) {
-    s0 += __expf(row[c] - m); s1 += __expf(row[c + 1] - m); s2 += __expf(row[c + 2] - m); s3 += __expf(row[c + 3] - m);
-  }
-  for (; c < C; ++c) s0 += __expf(row[c] - m);
-  const float s = (s0 + s1) + (s2 + s3);
   // p_c > thresh  <=>  x_c - m > log(thresh * s); pre-filter in logit space with a margin, then the
   // exact score  exp(x_c - m) / s  decides.
   const float cut = (P.score_thresh > 0.f) ? __logf(P.score_thresh * s) - 1e-3f : -CUDART_INF_F;
-  for (c = 0; c < C - 1; ++c) {
-    const float d = row[c] - m;
-    if (d > cut) {
-      const float score = __fdiv_rn(__expf(d), s);
-      if (score > P.score_thresh) emit_candidate(P, b, a, c, score);
+  for (int c = 0; c < nfg; ++c) {
+    bool p = false;
+    if (valid) {
+      const float d = row[c] - m;
+      if (d > cut) p = __fdiv_rn(__expf(d), s) > P.score_thresh;
+    }
+    const u32 mc = __ballot_sync(SSDG_FULL, p);
+    if (lane == 0) wmask[c] = mc;
+  }
+  __syncwarp();
+  const int b0 = __shfl_sync(SSDG_FULL, b, 0);
+  const u32 other = __ballot_sync(SSDG_FULL, valid && b > b0 + 1);
+  if (other) {
+    // a tile spanning more than two images (fewer than 32 priors per image): plain per-candidate path
+    if (valid)
+      for (int c = 0; c < nfg; ++c)
+        if ((wmask[c] >> lane) & 1u) emit_candidate(P, b, a, c, __fdiv_rn(__expf(row[c] - m), s));
+  } else {
+    for (int which = 0; which < 2; ++which) {
+      const u32 sel = __ballot_sync(SSDG_FULL, valid && b == b0 + which);
+      if (!sel) continue;
+      const size_t lbase = (size_t)(b0 + which) * nfg;
+      for (int c = lane; c < nfg; c += 32) {
+        const int cnt = __popc(wmask[c] & sel);
+        wbase[c] = cnt ? atomicAdd(&P.ccount[lbase + c], (u32)cnt) : 0u;
+      }
+      __syncwarp();
+      const u32 lt = (1u << lane) - 1u;
+      for (int c = 0; c < nfg; ++c) {
+        const u32 mc = wmask[c] & sel;
+        if (!mc) continue;
+        if ((mc >> lane) & 1u) {
+          const float score = __fdiv_rn(__expf(row[c] - m), s);
+          const u32 pos = wbase[c] + (u32)__popc(mc & lt);
+          if (pos < (u32)P.A) P.cand[(lbase + c) * P.A + pos] = ((u64)key32(score) << 32) | (u64)(~(u32)a);
+        }
+      }
+      __syncwarp();
     }
   }
+  if (!valid) return;
   if (P.head_score || P.head_cls || P.head_mask) {
     // models/ssd_model.py:481-488: max foreground probability, arg-max over all classes (first max)
     float best = row[0];
     int arg = 0;
     float fg = -CUDART_INF_F;
-    for (c = 0; c < C; ++c) {
+    for (int c = 0; c < C; ++c) {
       const float v = row[c];
       if (v > best) { best = v; arg = c; }
       if (c < C - 1) fg = fmaxf(fg, v);
@@ -125,7 +166,7 @@ __device__ __forceinline__ void filter_one_prior(const DetectParams& P, long lon
     reinterpret_cast<float4*>(P.boxes)[n] = decode_row<TP>(t, P.priors, a);
   }
   if (P.probs)
-    for (c = 0; c < C; ++c) row[c] = __fdiv_rn(__expf(row[c] - m), s);
+    for (int c = 0; c < C; ++c) row[c] = __fdiv_rn(__expf(row[c] - m), s);
 }
 
 template <typename TP>
@@ -136,12 +177,15 @@ __global__ void __launch_bounds__(kFThreads, 1) filter_kernel(DetectParams P, in
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* bufs = reinterpret_cast<float*>(smem_raw);
   u64* bars = reinterpret_cast<u64*>(smem_raw + (size_t)warps_per_cta * kFStages * tile_bytes);
+  u32* scratch = reinterpret_cast<u32*>(bars + kFWarps * kFStages);   // [warps][2][C]
   if (tid == 0) {
     for (int i = 0; i < warps_per_cta * kFStages; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
   }
   __syncthreads();
   if (warp >= warps_per_cta) return;
+  u32* wmask = scratch + (size_t)warp * 2 * C;
+  u32* wbase = wmask + C;
   const long long full_tiles = P.N >> 5;
   const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
   const long long stride = (long long)gridDim.x * warps_per_cta;
@@ -165,7 +209,7 @@ __global__ void __launch_bounds__(kFThreads, 1) filter_kernel(DetectParams P, in
     float* tile = mybuf + (size_t)s * 32 * C;
     const long long n = (t << 5) + lane;
     const int b = (int)(n / A), a = (int)(n - (long long)b * A);
-    filter_one_prior<TP>(P, n, b, a, tile + (size_t)lane * C);
+    filter_tile<TP>(P, n, b, a, true, tile + (size_t)lane * C, wmask, wbase, lane);
     __syncwarp();
     if (P.probs) {  // the tile layout in shared memory equals the layout in global memory
       float4* dst = reinterpret_cast<float4*>(P.probs + (size_t)t * 32 * C);
@@ -184,11 +228,10 @@ __global__ void __launch_bounds__(kFThreads, 1) filter_kernel(DetectParams P, in
     const float* g = P.pred_cls + (size_t)full_tiles * 32 * C;
     for (int i = lane; i < tail * C; i += 32) mybuf[i] = g[i];
     __syncwarp();
-    if (lane < tail) {
-      const long long n = (full_tiles << 5) + lane;
-      const int b = (int)(n / A), a = (int)(n - (long long)b * A);
-      filter_one_prior<TP>(P, n, b, a, mybuf + (size_t)lane * C);
-    }
+    const bool valid = lane < tail;
+    const long long n = (full_tiles << 5) + (valid ? lane : 0);
+    const int b = (int)(n / A), a = (int)(n - (long long)b * A);
+    filter_tile<TP>(P, n, b, a, valid, mybuf + (size_t)(valid ? lane : 0) * C, wmask, wbase, lane);
     __syncwarp();
     if (P.probs)
       for (int i = lane; i < tail * C; i += 32) P.probs[(size_t)full_tiles * 32 * C + i] = mybuf[i];
@@ -226,7 +269,7 @@ __device__ __forceinline__ void bitonic_sort_desc(u64* keys, int n, int tid, int
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       __syncthreads();
       for (int i = tid; i < (n >> 1); i += nthreads) {
-        const int lo = ((i / stride) * (stride << 1)) + (i % stride);
+        const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
         const int hi = lo + stride;
         const bool desc = ((lo & size) == 0);
         const u64 a = keys[lo], b = keys[hi];
@@ -244,7 +287,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
   u64* keys = reinterpret_cast<u64*>(smem_raw);                 // [sortn]
   float4* crn = reinterpret_cast<float4*>(keys + sortn);        // [sortn] x1,y1,x2,y2
   float* area = reinterpret_cast<float*>(crn + sortn);          // [sortn]
-  u32* sup = reinterpret_cast<u32*>(area + sortn);              // [sortn][W] lower triangle
+  u32* sup = reinterpret_cast<u32*>(area + 2 * sortn);          // [sortn][W] lower triangle (after area, qa)
   u32* keptw = sup + (size_t)sortn * W;                         // [W]
   u32* remw = keptw + W;                                        // [W]
   u32* hist = remw + W;                                         // [256]
@@ -296,47 +339,92 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
     __syncthreads();
     n = min(sel_fill, sortn);
   }
-  bitonic_sort_desc(keys, sortn, tid, kNmsThreads);
+  int sn = 32;
+  while (sn < n) sn <<= 1;           // n <= sortn here; the keys beyond n are 0 and sort to the end
+  bitonic_sort_desc(keys, sn, tid, kNmsThreads);
   const int m = min(n, P.top_k);
 
-  // gather decoded boxes; corners in the formula's own float32 operations (utils/bbox.py:13-21)
+  // gather decoded boxes; corners in the formula's own float32 operations (utils/bbox.py:13-21).
+  // qa = q*(area + 0.5e-10), q = thr/(1+thr):  iou > thr  <=>  inter > qa_i + qa_j  in exact arithmetic
+  // (denominator positive); boxes that can never overlap anything (w <= 0, h <= 0, non-finite) get
+  // qa = +inf so the fast test rejects them exactly like the formula does (their intersection is 0).
+  const float thr = P.iou_thresh;
+  const bool fast_ok = thr > 0.f && thr < 1e6f;
+  const float q = fast_ok ? thr / (1.f + thr) : 0.f;
+  float* qa = area + sortn;   // [sortn]
   for (int i = tid; i < m; i += kNmsThreads) {
     const int a = (int)(~(u32)keys[i]);
     const float4 bx = __ldg(reinterpret_cast<const float4*>(P.boxes) + (size_t)b * P.A + a);
     const float hw = __fmul_rn(bx.z, 0.5f), hh = __fmul_rn(bx.w, 0.5f);
-    crn[i] = make_float4(__fsub_rn(bx.x, hw), __fsub_rn(bx.y, hh), __fadd_rn(bx.x, hw), __fadd_rn(bx.y, hh));
-    area[i] = __fmul_rn(bx.z, bx.w);
+    const float4 cr = make_float4(__fsub_rn(bx.x, hw), __fsub_rn(bx.y, hh), __fadd_rn(bx.x, hw), __fadd_rn(bx.y, hh));
+    const float ar = __fmul_rn(bx.z, bx.w);
+    crn[i] = cr;
+    area[i] = ar;
+    const bool sane = bx.z > 0.f && bx.w > 0.f && isfinite(cr.x) && isfinite(cr.y) && isfinite(cr.z) &&
+                      isfinite(cr.w) && isfinite(ar);
+    qa[i] = sane ? q * (ar + 0.5e-10f) : CUDART_INF_F;
   }
   for (int i = tid; i < W; i += kNmsThreads) { keptw[i] = 0u; remw[i] = 0u; }
   __syncthreads();
 
-  // lower-triangle suppression bits: sup[i][w] bit l  <=>  iou(box_{32w+l}, box_i) > thresh, 32w+l < i
-  const float thr = P.iou_thresh;
-  const float thr_lo = thr * 0.999f, thr_hi = thr * 1.001f;
-  for (int i = warp; i < m; i += kNmsThreads / 32) {
-    const float4 bi = crn[i];
-    const float ai = area[i];
-    for (int w = 0; (w << 5) < i; ++w) {
+  // lower-triangle suppression bits: sup[i][w] bit l  <=>  iou(box_{32w+l}, box_i) > thresh, 32w+l < i.
+  // Two rows per warp iteration share the loads of the column boxes.
+  for (int ip = warp; 2 * ip < m; ip += kNmsThreads / 32) {
+    const int i0 = 2 * ip, i1 = i0 + 1;
+    const bool has1 = i1 < m;
+    const float4 b0 = crn[i0], b1 = crn[has1 ? i1 : i0];
+    const float q0 = qa[i0], q1 = qa[has1 ? i1 : i0];
+    const int last = has1 ? i1 : i0;
+    for (int w = 0; (w << 5) < last; ++w) {
       const int j = (w << 5) + lane;
-      bool s = false;
-      if (j < i) {
+      bool s0 = false, s1 = false, amb0 = false, amb1 = false;
+      if (j < last) {
         const float4 bj = crn[j];
-        const float ex = fmaxf(0.f, __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
-        const float ey = fmaxf(0.f, __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
-        const float inter = __fmul_rn(ex, ey);
-        if (inter > 0.f) {
-          const float den = __fadd_rn(__fsub_rn(__fadd_rn(area[j], ai), inter), 1e-10f);
-          if (den > 0.f && thr > 0.f && inter < thr_lo * den) s = false;
-          else if (den > 0.f && thr > 0.f && inter > thr_hi * den) s = true;
-          else s = __fdiv_rn(inter, den) > thr;
-        } else {
-          // inter == 0 (or NaN): 0/den > thr only for a negative threshold with a positive denominator
-          const float den = __fadd_rn(__fsub_rn(__fadd_rn(area[j], ai), inter), 1e-10f);
-          s = __fdiv_rn(inter, den) > thr;
+        const float qj = qa[j];
+        {
+          const float ex = fmaxf(0.f, fminf(b0.z, bj.z) - fmaxf(b0.x, bj.x));
+          const float ey = fmaxf(0.f, fminf(b0.w, bj.w) - fmaxf(b0.y, bj.y));
+          const float inter = ex * ey, r = q0 + qj;
+          s0 = inter > r * 1.0001f;
+          amb0 = !s0 && !(inter < r * 0.9999f);
+        }
+        {
+          const float ex = fmaxf(0.f, fminf(b1.z, bj.z) - fmaxf(b1.x, bj.x));
+          const float ey = fmaxf(0.f, fminf(b1.w, bj.w) - fmaxf(b1.y, bj.y));
+          const float inter = ex * ey, r = q1 + qj;
+          s1 = inter > r * 1.0001f;
+          amb1 = !s1 && !(inter < r * 0.9999f);
+        }
+        if (!fast_ok) { amb0 = true; amb1 = true; }
+        if (j >= i0) { s0 = false; amb0 = false; }
+        if (!has1) { s1 = false; amb1 = false; }
+      }
+      if (__any_sync(SSDG_FULL, amb0 || amb1)) {
+        // inside the margin (or no fast test): the formula itself, IEEE float32, no contraction
+        if (amb0 || amb1) {
+          const float4 bj = crn[j];
+          const float aj = area[j];
+          if (amb0) {
+            const float ex = fmaxf(0.f, __fsub_rn(fminf(b0.z, bj.z), fmaxf(b0.x, bj.x)));
+            const float ey = fmaxf(0.f, __fsub_rn(fminf(b0.w, bj.w), fmaxf(b0.y, bj.y)));
+            const float inter = __fmul_rn(ex, ey);
+            const float den = __fadd_rn(__fsub_rn(__fadd_rn(aj, area[i0]), inter), 1e-10f);
+            s0 = __fdiv_rn(inter, den) > thr;
+          }
+          if (amb1) {
+            const float ex = fmaxf(0.f, __fsub_rn(fminf(b1.z, bj.z), fmaxf(b1.x, bj.x)));
+            const float ey = fmaxf(0.f, __fsub_rn(fminf(b1.w, bj.w), fmaxf(b1.y, bj.y)));
+            const float inter = __fmul_rn(ex, ey);
+            const float den = __fadd_rn(__fsub_rn(__fadd_rn(aj, area[i1]), inter), 1e-10f);
+            s1 = __fdiv_rn(inter, den) > thr;
+          }
         }
       }
-      const u32 bits = __ballot_sync(SSDG_FULL, s);
-      if (lane == 0) sup[(size_t)i * W + w] = bits;
+      const u32 bits0 = __ballot_sync(SSDG_FULL, s0), bits1 = __ballot_sync(SSDG_FULL, s1);
+      if (lane == 0) {
+        if ((w << 5) < i0) sup[(size_t)i0 * W + w] = bits0;
+        if (has1) sup[(size_t)i1 * W + w] = bits1;
+      }
     }
   }
   __syncthreads();
@@ -381,7 +469,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
 }
 
 static int f_warps_for(int C) {
-  const size_t budget = 200 * 1024;
+  const size_t budget = 200 * 1024 - (size_t)kFWarps * 2 * C * 4;
   int w = (int)(budget / ((size_t)kFStages * 32 * C * 4));
   return w > kFWarps ? kFWarps : w;
 }
@@ -392,7 +480,7 @@ static int next_pow2(int v) {
 }
 static size_t nms_smem_bytes(int sortn) {
   const int W = sortn / 32;
-  return (size_t)sortn * (8 + 16 + 4) + (size_t)sortn * W * 4 + 2 * W * 4 + 256 * 4 + 64;
+  return (size_t)sortn * (8 + 16 + 4 + 4) + (size_t)sortn * W * 4 + 2 * W * 4 + 256 * 4 + 64;
 }
 
 struct DetectWs {
@@ -469,7 +557,8 @@ extern "C" int ssdg_detect(const float* pred_cls, const float* pred_box, const v
   P.ccount = ws.ccount; P.cand = ws.cand; P.boxes = out_boxes ? out_boxes : ws.boxes; P.probs = out_probs;
   P.head_thresh = head_thresh; P.head_score = head_score; P.head_cls = head_cls; P.head_mask = head_mask;
   SSDG_CUDA_TRY(cudaMemsetAsync(ws.ccount, 0, (size_t)batch * (n_classes - 1) * 4, st));
-  const size_t smem = (size_t)warps * kFStages * 32 * n_classes * 4 + kFWarps * kFStages * 8 + 128;
+  const size_t smem = (size_t)warps * kFStages * 32 * n_classes * 4 + kFWarps * kFStages * 8 +
+                      (size_t)kFWarps * 2 * n_classes * 4 + 128;
   int grid = sm_count();
   const long long tiles = (P.N + 31) / 32;
   const long long need = (tiles + warps - 1) / warps;

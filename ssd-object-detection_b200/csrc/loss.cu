@@ -231,12 +231,13 @@ __device__ int scan_level(const u32* __restrict__ ghist, int nbins, long long& k
 
 __device__ void derive_state(const LossParams& P, int levels_done, SelectState& st, u32* sh, int tid, int nthreads,
                              int* sh_bin, long long* sh_above, double* sh_np) {
-  if (tid == 0) {
+  if (tid < 32) {
+    // counts are integers < 2^53: the sum is exact in any order
     double np = 0;
     const int n = (int)P.ws->nparts[0];
-    for (int i = 0; i < n; ++i) np += P.ws->part[i][2];
-    *sh_np = np;
-    *sh_bin = 0; *sh_above = 0;
+    for (int i = tid; i < n; i += 32) np += P.ws->part[i][2];
+    np = warp_sum(np);
+    if (tid == 0) { *sh_np = np; *sh_bin = 0; *sh_above = 0; }
   }
   __syncthreads();
   st.num_pos = *sh_np;
@@ -330,18 +331,29 @@ __global__ void __launch_bounds__(256) final_kernel(LossParams P) {
     is_last = atomicAdd(&P.ws->ticket[0], 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (!is_last || tid != 0) return;
+  if (!is_last) return;
   __threadfence();
-  // deterministic final reduction, fixed order
+  // deterministic final reduction: fixed assignment of partials to threads, fixed tree
   double s_pos = 0, s_l1 = 0, s_neg = 0;
   unsigned long long n_neg = 0, n_ovl = 0;
   const int np = (int)P.ws->nparts[0];
-  for (int i = 0; i < np; ++i) { s_pos += P.ws->part[i][0]; s_l1 += P.ws->part[i][1]; }
-  for (int i = 0; i < (int)gridDim.x; ++i) {
+  for (int i = tid; i < np; i += blockDim.x) { s_pos += P.ws->part[i][0]; s_l1 += P.ws->part[i][1]; }
+  for (int i = tid; i < (int)gridDim.x; i += blockDim.x) {
     s_neg += ((volatile double*)P.ws->fpart[i])[0];
     n_neg += ((volatile u32*)P.ws->fcount[i])[0];
     n_ovl += ((volatile u32*)P.ws->fcount[i])[1];
   }
+  __shared__ double fin[5][8];
+  s_pos = warp_sum(s_pos); s_l1 = warp_sum(s_l1); s_neg = warp_sum(s_neg);
+  double d_neg = warp_sum((double)n_neg), d_ovl = warp_sum((double)n_ovl);
+  if (lane == 0) { fin[0][warp] = s_pos; fin[1][warp] = s_l1; fin[2][warp] = s_neg; fin[3][warp] = d_neg; fin[4][warp] = d_ovl; }
+  __syncthreads();
+  if (tid != 0) return;
+  s_pos = s_l1 = s_neg = d_neg = d_ovl = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+    s_pos += fin[0][w]; s_l1 += fin[1][w]; s_neg += fin[2][w]; d_neg += fin[3][w]; d_ovl += fin[4][w];
+  }
+  n_neg = (unsigned long long)d_neg; n_ovl = (unsigned long long)d_ovl;
   double* r = P.result;
   int status = st.status;
   if (!status && n_ovl) status = SSDG_ERR_POS_NEG_OVERLAP;  // models/ssd_model.py:375 (positives mined as negatives)

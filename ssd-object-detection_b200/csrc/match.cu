@@ -26,9 +26,17 @@
 
 namespace ssdg {
 
-constexpr int kMatchThreads = 512;
+#ifndef SSDG_MATCH_THREADS
+#define SSDG_MATCH_THREADS 512
+#endif
+#ifndef SSDG_MATCH_CTAS_PER_SM
+#define SSDG_MATCH_CTAS_PER_SM 2
+#endif
+constexpr int kMatchThreads = SSDG_MATCH_THREADS;
 constexpr int kMatchWarps = kMatchThreads / 32;
-constexpr int kLogCap = 32768;
+constexpr int kMatchCtasPerSm = SSDG_MATCH_CTAS_PER_SM;
+constexpr int kMatchMaxCtas = 1024;
+constexpr int kLogCap = 16384;
 constexpr int kABits = 21;
 constexpr int kMaxGT = 2048;
 constexpr double kSlack = 1e-5;
@@ -103,6 +111,7 @@ struct MatchSmem {
   typedef typename Promote<TG, TP>::type R;
   R *gx1, *gy1, *gx2, *gy2, *ga;     // ground-truth corners / area in the result dtype
   float *cx1, *cy1, *cx2, *cy2;      // outward-rounded float cull box (+-inf when not cullable)
+  float2* glo;                       // .x: float lower bound of the GT area, .y: of the running row maximum
   u64* rowkey;                       // running / cached row maximum (key64) over live columns
   u64* cbkey;                        // key64 of the bound c_t on any culled pair (0: nothing culled)
   int* rowcol;                       // first arg-max column of rowkey
@@ -122,6 +131,7 @@ struct MatchSmem {
     rowkey = (u64*)(base + o); o += 8 * (size_t)tm;
     cbkey = (u64*)(base + o); o += 8 * (size_t)tm;
     red_key = (u64*)(base + o); o += 8 * kMatchWarps;
+    glo = (float2*)(base + o); o += 8 * (size_t)tm;
     cx1 = (float*)(base + o); o += 4 * (size_t)tm;
     cy1 = (float*)(base + o); o += 4 * (size_t)tm;
     cx2 = (float*)(base + o); o += 4 * (size_t)tm;
@@ -135,12 +145,12 @@ struct MatchSmem {
     dead = (uint8_t*)(base + o);
   }
 };
-static size_t match_smem_bytes(int tm) { return (size_t)tm * (5 * 8 + 16 + 16 + 16 + 1) + 12 * kMatchWarps + 64 + 64; }
+static size_t match_smem_bytes(int tm) { return (size_t)tm * (5 * 8 + 16 + 8 + 16 + 16 + 1) + 12 * kMatchWarps + 64 + 64; }
 
 enum { C_IMG = 0, C_LOGN, C_NRS, C_DONE, C_ROUND, C_DEGEN, C_MINELIM, C_MINDEAD, C_OVERFLOW };
 
 template <typename TG, typename TP>
-__global__ void __launch_bounds__(kMatchThreads, 1) match_kernel(MatchParams P) {
+__global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(MatchParams P) {
   typedef typename Promote<TG, TP>::type R;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   MatchSmem<TG, TP> S;
@@ -152,6 +162,7 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_kernel(MatchParams P) 
   u32* log = P.ws_log + (size_t)blockIdx.x * kLogCap;
   u32* elim = P.ws_elim + (size_t)blockIdx.x * P.elim_words;
   const u64 thr_key = key64((double)(R)P.thresh);
+  const float thr_lo = f_down((double)(R)P.thresh);
 
   auto load_prior = [&](int a, Corners<R>& p, bool& safe, TP& dx, TP& dy, TP& dw, TP& dh) {
     Vec4<TP>::load(P.priors, a, dx, dy, dw, dh);
@@ -237,6 +248,7 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_kernel(MatchParams P) 
       S.cy1[t] = ok ? f_down((double)y1) : -CUDART_INF_F;
       S.cx2[t] = ok ? f_up((double)x2) : CUDART_INF_F;
       S.cy2[t] = ok ? f_up((double)y2) : CUDART_INF_F;
+      S.glo[t] = make_float2(ok ? f_down(a1) : -CUDART_INF_F, 0.f);
       S.rowkey[t] = 0ull;
       S.rowcol[t] = 0x7fffffff;
       S.dead[t] = 0;
@@ -249,18 +261,23 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_kernel(MatchParams P) 
     __syncthreads();
 
     // ---- sweep ---------------------------------------------------------------------------------
-    for (int tile = warp; tile < ntiles; tile += kMatchWarps) {
+    // Tiles are walked from the last (largest priors of an SSD pyramid: few, and the ones that set a
+    // ground truth's row maximum early) to the first, so the float pre-filter below has a useful bound
+    // by the time the many small priors are visited.  The result does not depend on the order.
+    for (int tile = ntiles - 1 - warp; tile >= 0; tile -= kMatchWarps) {
       const int a = (tile << 5) + lane;
       const bool valid = a < A;
       Corners<R> p; bool safe = true;
       TP dx = 0, dy = 0, dw = 1, dh = 1;
       p.x1 = p.y1 = p.x2 = p.y2 = p.area = (R)0;
       if (valid) load_prior(a, p, safe, dx, dy, dw, dh);
-      // tile bounding box, rounded outwards to float (REDUX on order-preserving keys)
-      float tx1 = unkey32(__reduce_min_sync(SSDG_FULL, valid && safe ? key32(f_down((double)p.x1)) : ~0u));
-      float ty1 = unkey32(__reduce_min_sync(SSDG_FULL, valid && safe ? key32(f_down((double)p.y1)) : ~0u));
-      float tx2 = unkey32(__reduce_max_sync(SSDG_FULL, valid && safe ? key32(f_up((double)p.x2)) : 0u));
-      float ty2 = unkey32(__reduce_max_sync(SSDG_FULL, valid && safe ? key32(f_up((double)p.y2)) : 0u));
+      // outward-rounded float copy of the prior and the tile bounding box (REDUX on order-preserving keys)
+      const float ax1 = f_down((double)p.x1), ay1 = f_down((double)p.y1);
+      const float ax2 = f_up((double)p.x2), ay2 = f_up((double)p.y2), aalo = f_down((double)p.area);
+      float tx1 = unkey32(__reduce_min_sync(SSDG_FULL, valid && safe ? key32(ax1) : ~0u));
+      float ty1 = unkey32(__reduce_min_sync(SSDG_FULL, valid && safe ? key32(ay1) : ~0u));
+      float tx2 = unkey32(__reduce_max_sync(SSDG_FULL, valid && safe ? key32(ax2) : 0u));
+      float ty2 = unkey32(__reduce_max_sync(SSDG_FULL, valid && safe ? key32(ay2) : 0u));
       if (!__all_sync(SSDG_FULL, safe)) { tx1 = ty1 = -CUDART_INF_F; tx2 = ty2 = CUDART_INF_F; }
 
       u64 ckey = 0ull;
@@ -273,6 +290,25 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_kernel(MatchParams P) 
         while (m) {
           const int t = t0 + __ffs(m) - 1;
           m &= m - 1;
+          // Float pre-filter: I_ub / D_lb bounds the IoU the exact path would compute from above
+          // (outward-rounded corners, directed rounding).  A pair below min(thresh, running row
+          // maximum) can be neither a positive (phase 2) nor the row's arg-max (phase 1).
+          bool need = valid;
+          if (valid && safe) {
+            const float ex = fmaxf(__fsub_ru(fminf(S.cx2[t], ax2), fmaxf(S.cx1[t], ax1)), 1.0001e-10f);
+            const float ey = fmaxf(__fsub_ru(fminf(S.cy2[t], ay2), fmaxf(S.cy1[t], ay1)), 1.0001e-10f);
+            const float iub = __fmul_ru(ex, ey);
+            float2 gl;   // one 8-byte volatile load: {area lower bound, running row-max lower bound}
+            {
+              const u64 raw = *reinterpret_cast<volatile u64*>(&S.glo[t]);
+              gl.x = __uint_as_float((u32)raw);
+              gl.y = __uint_as_float((u32)(raw >> 32));
+            }
+            const float dlb = __fadd_rd(__fsub_rd(__fadd_rd(gl.x, aalo), iub), 0.9999e-10f);
+            const float bound = fminf(thr_lo, gl.y);
+            need = !(dlb > 0.f && iub * 1.0001f < bound * dlb);
+          }
+          if (!__any_sync(SSDG_FULL, need)) continue;
           Corners<R> g = load_gt(t);
           u64 key = valid ? key64((double)iou_corners<R>(g, p, EPS)) : 0ull;
           if (key > ckey) { ckey = key; ct = t; }
@@ -287,6 +323,8 @@ __global__ void __launch_bounds__(kMatchThreads, 1) match_kernel(MatchParams P) 
             if (lane == leader) {
               base = atomicAdd(&S.ctl[C_LOGN], __popc(tmask));
               atomicMax(&S.rowkey[t], wmax);
+              const float lo = fmaxf(f_down(unkey64(wmax)), 0.f);
+              atomicMax(reinterpret_cast<int*>(&S.glo[t].y), __float_as_int(lo));
             }
             base = __shfl_sync(SSDG_FULL, base, leader);
             if (top) {
@@ -460,7 +498,8 @@ static int launch_match(const MatchParams& P, int grid, size_t smem, cudaStream_
 }
 
 static int match_grid(int batch) {
-  int g = sm_count();
+  int g = sm_count() * kMatchCtasPerSm;
+  if (g > kMatchMaxCtas) g = kMatchMaxCtas;
   return batch < g ? batch : g;
 }
 
@@ -471,7 +510,7 @@ using namespace ssdg;
 extern "C" size_t ssdg_match_workspace_bytes(int32_t batch, int32_t n_priors, int32_t max_gt) {
   (void)max_gt;
   if (batch <= 0 || n_priors <= 0) return 0;
-  size_t ctas = 256;  // >= any SM count this library targets; the grid never exceeds it
+  size_t ctas = kMatchMaxCtas;  // the grid never exceeds it
   size_t elim_words = ((size_t)n_priors + 31) / 32;
   return 256 + ctas * (size_t)kLogCap * 4 + align_up(ctas * elim_words * 4, 256);
 }
@@ -492,7 +531,6 @@ extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const f
     return SSDG_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   int grid = match_grid(batch);
-  if (grid > 256) grid = 256;
   MatchParams P;
   P.gt_boxes = gt_boxes; P.gt_cls = gt_cls; P.gt_off = gt_offsets; P.priors = priors;
   P.B = batch; P.A = n_priors; P.max_gt = max_gt; P.tm = ((max_gt + 31) / 32) * 32;
@@ -503,7 +541,7 @@ extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const f
   unsigned char* w = (unsigned char*)workspace;
   P.ws_head = (u32*)w;
   P.ws_log = (u32*)(w + 256);
-  P.ws_elim = (u32*)(w + 256 + (size_t)256 * kLogCap * 4);
+  P.ws_elim = (u32*)(w + 256 + (size_t)kMatchMaxCtas * kLogCap * 4);
   SSDG_CUDA_TRY(cudaMemsetAsync(P.ws_head, 0, 256, st));
   size_t smem = match_smem_bytes(P.tm);
   if ((int)smem > max_smem_optin()) return SSDG_ERR_LIMIT;

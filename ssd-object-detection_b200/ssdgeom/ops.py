@@ -165,8 +165,10 @@ def multibox_loss(gt_cls, gt_box, gt_mask, pred_box, pred_cls, neg_ratio: int = 
     if want_neg_ce and "neg_ce" not in out:
         out["neg_ce"] = D.empty((b, a), np.float32)
     if want_grad:
-        out.setdefault("grad_box", D.empty((b, a, 4), np.float32))
-        out.setdefault("grad_cls", D.empty((b, a, c), np.float32))
+        if "grad_box" not in out:
+            out["grad_box"] = D.empty((b, a, 4), np.float32)
+        if "grad_cls" not in out:
+            out["grad_cls"] = D.empty((b, a, c), np.float32)
     lib = N.lib()
     ws = POOL.get(ws_kind, lib.ssdg_loss_workspace_bytes(b, a, c))
     N.check(lib.ssdg_multibox_loss(gt_cls.ptr, gt_box.ptr, gt_mask.ptr, pred_box.ptr, pred_cls.ptr, b, a, c,
@@ -201,18 +203,23 @@ def detect(pred_cls, pred_box, priors, score_thresh=0.01, top_k=200, iou_thresh=
     if pred_box.size != b * a * 4 or priors.shape[0] != a:
         raise AssertionError("pred_cls / pred_box / priors disagree in shape")
     out = dict(out or {})
-    out.setdefault("kept", D.empty((b, c - 1, top_k), np.int32))
-    out.setdefault("count", D.empty((b, c - 1), np.int32))
+
+    def need(key, shape, dtype):
+        if key not in out:            # never dict.setdefault here: it would allocate (and free) eagerly
+            out[key] = D.empty(shape, dtype)
+
+    need("kept", (b, c - 1, top_k), np.int32)
+    need("count", (b, c - 1), np.int32)
     if want_scores:
-        out.setdefault("kept_score", D.empty((b, c - 1, top_k), np.float32))
+        need("kept_score", (b, c - 1, top_k), np.float32)
     if want_boxes:
-        out.setdefault("boxes", D.empty((b, a, 4), np.float32))
+        need("boxes", (b, a, 4), np.float32)
     if want_probs:
-        out.setdefault("probs", D.empty((b, a, c), np.float32))
+        need("probs", (b, a, c), np.float32)
     if head_thresh is not None:
-        out.setdefault("head_score", D.empty((b, a), np.float32))
-        out.setdefault("head_cls", D.empty((b, a), np.int32))
-        out.setdefault("head_mask", D.empty((b, a), np.uint8))
+        need("head_score", (b, a), np.float32)
+        need("head_cls", (b, a), np.int32)
+        need("head_mask", (b, a), np.uint8)
     lib = N.lib()
     ws = POOL.get("detect", lib.ssdg_detect_workspace_bytes(b, a, c, top_k))
     N.check(lib.ssdg_detect(pred_cls.ptr, pred_box.ptr, priors.ptr, _code(priors.dtype), b, a, c, float(score_thresh),
