@@ -9,18 +9,22 @@
 //     ALL rows, positive iff not (iou <= thresh).
 //   * Scatter (:84-90) in append order, later pairs overwrite; encode (:94-101).
 //
-// How the work is organised (per image, 32 priors = one warp tile, lane = prior):
-//   sweep    every warp walks its tiles; the ground-truth boxes that can overlap the tile's
-//            bounding box are found 32 at a time with one ballot (the rest have clamped
-//            intersections, provably <= the per-GT bound c_t < thresh, see gt_setup);
-//            for each surviving (tile, gt) the lanes evaluate the exact IoU, keep their
-//            column's running first-arg-max in registers (phase 2 needs nothing else) and
-//            filter against the row's running maximum in shared memory; the rare lanes that
-//            reach it append (gt, prior) to a log after a REDUX warp arg-max.
-//   resolve  the log is replayed to find each row's first arg-max column.
-//   greedy   warp 0 runs the T rounds on the cached row maxima; the CTA is only woken to
-//            rescan a row whose cached column was just taken by another row.
-//   scatter  phase-1 pairs overwrite the phase-2 outputs the sweep already stored.
+// How the work is organised (32 priors = one warp tile, lane = prior):
+//   tile_stats  once per launch: outward-rounded float bounding box, max width/height and min area
+//               of every tile of priors (shared by all images).
+//   sweep       every warp walks its tiles from the last (largest priors of an SSD pyramid, which
+//               establish the row maxima early) to the first.  32 ground-truth rows at a time are
+//               tested against the tile with a conservative float upper bound of the IoU any prior
+//               of the tile can reach (one ballot); surviving (tile, row) pairs repeat the bound per
+//               lane, and only pairs that can still be a positive (> thresh) or the row's arg-max
+//               (>= running row maximum) reach the exact float64 evaluation.  Lanes keep their
+//               column's running first-arg-max in registers (all phase 2 needs); lanes that reach
+//               the running row maximum are logged after a REDUX warp arg-max.
+//   resolve     the log is replayed to find each row's first arg-max column.
+//   greedy      warp 0 runs the T rounds on the cached row maxima; rows whose cached column was just
+//               taken by another row are re-swept together (same code, restricted to those rows and
+//               to live columns).
+//   scatter     phase-1 pairs overwrite the phase-2 outputs the sweep already stored.
 #include <math_constants.h>
 #include "common.cuh"
 
@@ -39,7 +43,13 @@ constexpr int kMatchMaxCtas = 1024;
 constexpr int kLogCap = 16384;
 constexpr int kABits = 21;
 constexpr int kMaxGT = 2048;
-constexpr double kSlack = 1e-5;
+
+struct TileStat {
+  float x1, y1, x2, y2;   // bounding box of the tile's priors, rounded outwards
+  float wmax, hmax;       // largest corner-derived width / height (rounded up)
+  float amin;             // smallest area (rounded down)
+  u32 safe;               // 1: every prior of the tile is finite
+};
 
 struct MatchParams {
   const void* gt_boxes;
@@ -53,9 +63,10 @@ struct MatchParams {
   float* out_loc;
   uint8_t* out_mask;
   int* out_match;
-  u32* ws_head;  // [0] next image, [1] status bits
-  u32* ws_log;   // per CTA kLogCap
-  u32* ws_elim;  // per CTA elim_words
+  u32* ws_head;          // [0] next image, [1] status bits
+  u32* ws_log;           // per CTA kLogCap
+  u32* ws_elim;          // per CTA elim_words
+  const TileStat* tiles; // [ceil(A/32)]
   int elim_words;
 };
 
@@ -106,14 +117,65 @@ __device__ __forceinline__ float4 encode_row(float bx, float by, float bw, float
   return make_float4((float)tx, (float)ty, (float)log(rw), (float)log(rh));
 }
 
+// Conservative float upper bound of the IoU the exact path would compute, as a cross-multiplied
+// comparison:  returns true unless  iou < bound  is certain.  (x1,y1,x2,y2) / (ex_cap, ey_cap) bound the
+// intersection extents from above, a_lo bounds the areas from below; directed rounding throughout.
+// Any NaN makes the comparison fail, i.e. the pair is kept for the exact evaluation.
+__device__ __forceinline__ bool may_reach(float gx1, float gy1, float gx2, float gy2, float ga_lo, float px1,
+                                          float py1, float px2, float py2, float ex_cap, float ey_cap, float pa_lo,
+                                          float bound) {
+  float ex = fmaxf(__fsub_ru(fminf(gx2, px2), fmaxf(gx1, px1)), 1.0001e-10f);
+  float ey = fmaxf(__fsub_ru(fminf(gy2, py2), fmaxf(gy1, py1)), 1.0001e-10f);
+  ex = fminf(ex, ex_cap);
+  ey = fminf(ey, ey_cap);
+  const float iub = __fmul_ru(ex, ey);
+  const float dlb = __fadd_rd(__fsub_rd(__fadd_rd(ga_lo, pa_lo), iub), 0.9999e-10f);
+  return !(dlb > 0.f && iub * 1.0001f < bound * dlb);
+}
+
+// ---- per-tile statistics of the priors (once per launch) ------------------------------------------------
+template <typename TP>
+__global__ void __launch_bounds__(256) tile_stats_kernel(const void* __restrict__ priors, int A, TileStat* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int tile = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int ntiles = (A + 31) >> 5;
+  if (tile >= ntiles) return;
+  const int a = (tile << 5) + lane;
+  const bool valid = a < A;
+  u32 kx1 = ~0u, ky1 = ~0u, kx2 = 0u, ky2 = 0u, kw = 0u, kh = 0u, ka = ~0u;
+  bool safe = true;
+  if (valid) {
+    TP cx, cy, w, h;
+    Vec4<TP>::load(priors, a, cx, cy, w, h);
+    Corners<TP> c = corners_of<TP>(cx, cy, w, h);
+    safe = finite4((double)c.x1, (double)c.y1, (double)c.x2, (double)c.y2) && isfinite((double)c.area);
+    if (safe) {
+      const float x1 = f_down((double)c.x1), y1 = f_down((double)c.y1);
+      const float x2 = f_up((double)c.x2), y2 = f_up((double)c.y2);
+      kx1 = key32(x1); ky1 = key32(y1); kx2 = key32(x2); ky2 = key32(y2);
+      kw = key32(__fsub_ru(x2, x1)); kh = key32(__fsub_ru(y2, y1));
+      ka = key32(f_down((double)c.area));
+    }
+  }
+  TileStat st;
+  st.x1 = unkey32(__reduce_min_sync(SSDG_FULL, kx1));
+  st.y1 = unkey32(__reduce_min_sync(SSDG_FULL, ky1));
+  st.x2 = unkey32(__reduce_max_sync(SSDG_FULL, kx2));
+  st.y2 = unkey32(__reduce_max_sync(SSDG_FULL, ky2));
+  st.wmax = fmaxf(unkey32(__reduce_max_sync(SSDG_FULL, kw)), 1.0001e-10f);
+  st.hmax = fmaxf(unkey32(__reduce_max_sync(SSDG_FULL, kh)), 1.0001e-10f);
+  st.amin = unkey32(__reduce_min_sync(SSDG_FULL, ka));
+  st.safe = __all_sync(SSDG_FULL, safe) ? 1u : 0u;
+  if (lane == 0) out[tile] = st;
+}
+
 template <typename TG, typename TP>
 struct MatchSmem {
   typedef typename Promote<TG, TP>::type R;
   R *gx1, *gy1, *gx2, *gy2, *ga;     // ground-truth corners / area in the result dtype
-  float *cx1, *cy1, *cx2, *cy2;      // outward-rounded float cull box (+-inf when not cullable)
-  float2* glo;                       // .x: float lower bound of the GT area, .y: of the running row maximum
+  float4* cbox;                      // outward-rounded float box of the ground truth
+  float2* glo;                       // .x float lower bound of the area (NaN: never cull), .y of the running row maximum
   u64* rowkey;                       // running / cached row maximum (key64) over live columns
-  u64* cbkey;                        // key64 of the bound c_t on any culled pair (0: nothing culled)
   int* rowcol;                       // first arg-max column of rowkey
   int *pair_t, *pair_a, *rs_list;
   uint8_t* dead;
@@ -127,15 +189,11 @@ struct MatchSmem {
     gx2 = (R*)(base + o); o += sizeof(R) * tm;
     gy2 = (R*)(base + o); o += sizeof(R) * tm;
     ga = (R*)(base + o); o += sizeof(R) * tm;
-    o = (o + 7) & ~(size_t)7;
+    o = (o + 15) & ~(size_t)15;
+    cbox = (float4*)(base + o); o += 16 * (size_t)tm;
     rowkey = (u64*)(base + o); o += 8 * (size_t)tm;
-    cbkey = (u64*)(base + o); o += 8 * (size_t)tm;
-    red_key = (u64*)(base + o); o += 8 * kMatchWarps;
     glo = (float2*)(base + o); o += 8 * (size_t)tm;
-    cx1 = (float*)(base + o); o += 4 * (size_t)tm;
-    cy1 = (float*)(base + o); o += 4 * (size_t)tm;
-    cx2 = (float*)(base + o); o += 4 * (size_t)tm;
-    cy2 = (float*)(base + o); o += 4 * (size_t)tm;
+    red_key = (u64*)(base + o); o += 8 * kMatchWarps;
     rowcol = (int*)(base + o); o += 4 * (size_t)tm;
     pair_t = (int*)(base + o); o += 4 * (size_t)tm;
     pair_a = (int*)(base + o); o += 4 * (size_t)tm;
@@ -145,9 +203,9 @@ struct MatchSmem {
     dead = (uint8_t*)(base + o);
   }
 };
-static size_t match_smem_bytes(int tm) { return (size_t)tm * (5 * 8 + 16 + 8 + 16 + 16 + 1) + 12 * kMatchWarps + 64 + 64; }
+static size_t match_smem_bytes(int tm) { return (size_t)tm * (5 * 8 + 16 + 8 + 8 + 16 + 1) + 12 * kMatchWarps + 64 + 80; }
 
-enum { C_IMG = 0, C_LOGN, C_NRS, C_DONE, C_ROUND, C_DEGEN, C_MINELIM, C_MINDEAD, C_OVERFLOW };
+enum { C_IMG = 0, C_LOGN, C_NRS, C_DONE, C_ROUND, C_DEGEN, C_MINELIM, C_OVERFLOW };
 
 template <typename TG, typename TP>
 __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(MatchParams P) {
@@ -168,8 +226,7 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
     Vec4<TP>::load(P.priors, a, dx, dy, dw, dh);
     Corners<TP> c = corners_of<TP>(dx, dy, dw, dh);
     p.x1 = (R)c.x1; p.y1 = (R)c.y1; p.x2 = (R)c.x2; p.y2 = (R)c.y2; p.area = (R)c.area;
-    safe = finite4((double)p.x1, (double)p.y1, (double)p.x2, (double)p.y2) && (double)p.area >= 0.0 &&
-           isfinite((double)p.area);
+    safe = finite4((double)p.x1, (double)p.y1, (double)p.x2, (double)p.y2) && isfinite((double)p.area);
   };
   auto load_gt = [&](int t) {
     Corners<R> g;
@@ -177,22 +234,20 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
     return g;
   };
   auto elim_test = [&](int a) { return (elim[a >> 5] >> (a & 31)) & 1u; };
+  auto load_glo = [&](int t) {   // one 8-byte volatile load
+    const u64 raw = *reinterpret_cast<volatile u64*>(&S.glo[t]);
+    return make_float2(__uint_as_float((u32)raw), __uint_as_float((u32)(raw >> 32)));
+  };
 
-  // CTA-wide exact rescan of row t over the live columns; result -> rowkey[t], rowcol[t].
-  auto rescan_row = [&](int t, bool use_cull) {
+  // Exhaustive exact scan of row t over the live columns (fallback when the log overflowed).
+  auto scan_row_exact = [&](int t) {
     Corners<R> g = load_gt(t);
-    const float c1 = S.cx1[t], c2 = S.cy1[t], c3 = S.cx2[t], c4 = S.cy2[t];
     u64 bk = 0;
     int ba = 0x7fffffff;
     for (int a = tid; a < A; a += kMatchThreads) {
       if (elim_test(a)) continue;
       Corners<R> p; bool safe; TP dx, dy, dw, dh;
       load_prior(a, p, safe, dx, dy, dw, dh);
-      if (use_cull && safe) {
-        bool ov = !(c3 <= f_down((double)p.x1) || c1 >= f_up((double)p.x2) || c4 <= f_down((double)p.y1) ||
-                    c2 >= f_up((double)p.y2));
-        if (!ov) continue;
-      }
       u64 k = key64((double)iou_corners<R>(g, p, EPS));
       if (k > bk) { bk = k; ba = a; }
     }
@@ -206,10 +261,6 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
       if (lane == 0) { S.rowkey[t] = k; S.rowcol[t] = i; }
     }
     __syncthreads();
-  };
-  auto rescan_trusted = [&](int t) {
-    rescan_row(t, true);
-    if (S.rowcol[t] == 0x7fffffff || S.rowkey[t] <= S.cbkey[t]) rescan_row(t, false);
   };
 
   for (;;) {
@@ -234,21 +285,9 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
       Corners<TG> c = corners_of<TG>(cx, cy, w, h);
       R x1 = (R)c.x1, y1 = (R)c.y1, x2 = (R)c.x2, y2 = (R)c.y2, ar = (R)c.area;
       S.gx1[t] = x1; S.gy1[t] = y1; S.gx2[t] = x2; S.gy2[t] = y2; S.ga[t] = ar;
-      // c_t: an upper bound on the IoU of any pair with a clamped intersection extent
-      // (inter <= 1e-10 * E, denominator >= a1 + 1e-10 - inter when the prior's area >= 0).
-      double E = fmax(fmax((double)x2 - (double)x1, (double)y2 - (double)y1), 1e-10);
-      double a1 = (double)ar;
-      double imax = 1e-10 * E * (1.0 + kSlack);
-      bool ok = finite4((double)x1, (double)y1, (double)x2, (double)y2) && isfinite(a1) && a1 >= 0.0 &&
-                imax <= 0.5 * (a1 + 1e-10);
-      double cb = ok ? imax / (a1 + 1e-10 - imax) * (1.0 + kSlack) : CUDART_INF;
-      ok = ok && cb < (double)(R)P.thresh * (1.0 - kSlack);
-      S.cbkey[t] = ok ? key64(cb) : 0ull;
-      S.cx1[t] = ok ? f_down((double)x1) : -CUDART_INF_F;
-      S.cy1[t] = ok ? f_down((double)y1) : -CUDART_INF_F;
-      S.cx2[t] = ok ? f_up((double)x2) : CUDART_INF_F;
-      S.cy2[t] = ok ? f_up((double)y2) : CUDART_INF_F;
-      S.glo[t] = make_float2(ok ? f_down(a1) : -CUDART_INF_F, 0.f);
+      const bool ok = finite4((double)x1, (double)y1, (double)x2, (double)y2) && isfinite((double)ar);
+      S.cbox[t] = make_float4(f_down((double)x1), f_down((double)y1), f_up((double)x2), f_up((double)y2));
+      S.glo[t] = make_float2(ok ? f_down((double)ar) : CUDART_NAN_F, 0.f);
       S.rowkey[t] = 0ull;
       S.rowcol[t] = 0x7fffffff;
       S.dead[t] = 0;
@@ -256,111 +295,108 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
     for (int w = tid; w < P.elim_words; w += kMatchThreads) elim[w] = 0u;
     if (tid == 0) {
       S.ctl[C_LOGN] = 0; S.ctl[C_NRS] = 0; S.ctl[C_DONE] = 0; S.ctl[C_ROUND] = 0; S.ctl[C_DEGEN] = 0;
-      S.ctl[C_MINELIM] = 0x7fffffff; S.ctl[C_MINDEAD] = 0x7fffffff; S.ctl[C_OVERFLOW] = 0;
+      S.ctl[C_MINELIM] = 0x7fffffff; S.ctl[C_OVERFLOW] = 0;
     }
     __syncthreads();
 
-    // ---- sweep ---------------------------------------------------------------------------------
-    // Tiles are walked from the last (largest priors of an SSD pyramid: few, and the ones that set a
-    // ground truth's row maximum early) to the first, so the float pre-filter below has a useful bound
-    // by the time the many small priors are visited.  The result does not depend on the order.
-    for (int tile = ntiles - 1 - warp; tile >= 0; tile -= kMatchWarps) {
-      const int a = (tile << 5) + lane;
-      const bool valid = a < A;
-      Corners<R> p; bool safe = true;
-      TP dx = 0, dy = 0, dw = 1, dh = 1;
-      p.x1 = p.y1 = p.x2 = p.y2 = p.area = (R)0;
-      if (valid) load_prior(a, p, safe, dx, dy, dw, dh);
-      // outward-rounded float copy of the prior and the tile bounding box (REDUX on order-preserving keys)
-      const float ax1 = f_down((double)p.x1), ay1 = f_down((double)p.y1);
-      const float ax2 = f_up((double)p.x2), ay2 = f_up((double)p.y2), aalo = f_down((double)p.area);
-      float tx1 = unkey32(__reduce_min_sync(SSDG_FULL, valid && safe ? key32(ax1) : ~0u));
-      float ty1 = unkey32(__reduce_min_sync(SSDG_FULL, valid && safe ? key32(ay1) : ~0u));
-      float tx2 = unkey32(__reduce_max_sync(SSDG_FULL, valid && safe ? key32(ax2) : 0u));
-      float ty2 = unkey32(__reduce_max_sync(SSDG_FULL, valid && safe ? key32(ay2) : 0u));
-      if (!__all_sync(SSDG_FULL, safe)) { tx1 = ty1 = -CUDART_INF_F; tx2 = ty2 = CUDART_INF_F; }
-
-      u64 ckey = 0ull;
-      int ct = -1;
-      for (int t0 = 0; t0 < T; t0 += 32) {
-        const int tl = t0 + lane;
-        bool ov = false;
-        if (tl < T) ov = !(S.cx2[tl] <= tx1 || S.cx1[tl] >= tx2 || S.cy2[tl] <= ty1 || S.cy1[tl] >= ty2);
-        u32 m = __ballot_sync(SSDG_FULL, ov);
-        while (m) {
-          const int t = t0 + __ffs(m) - 1;
-          m &= m - 1;
-          // Float pre-filter: I_ub / D_lb bounds the IoU the exact path would compute from above
-          // (outward-rounded corners, directed rounding).  A pair below min(thresh, running row
-          // maximum) can be neither a positive (phase 2) nor the row's arg-max (phase 1).
-          bool need = valid;
-          if (valid && safe) {
-            const float ex = fmaxf(__fsub_ru(fminf(S.cx2[t], ax2), fmaxf(S.cx1[t], ax1)), 1.0001e-10f);
-            const float ey = fmaxf(__fsub_ru(fminf(S.cy2[t], ay2), fmaxf(S.cy1[t], ay1)), 1.0001e-10f);
-            const float iub = __fmul_ru(ex, ey);
-            float2 gl;   // one 8-byte volatile load: {area lower bound, running row-max lower bound}
-            {
-              const u64 raw = *reinterpret_cast<volatile u64*>(&S.glo[t]);
-              gl.x = __uint_as_float((u32)raw);
-              gl.y = __uint_as_float((u32)(raw >> 32));
-            }
-            const float dlb = __fadd_rd(__fsub_rd(__fadd_rd(gl.x, aalo), iub), 0.9999e-10f);
-            const float bound = fminf(thr_lo, gl.y);
-            need = !(dlb > 0.f && iub * 1.0001f < bound * dlb);
+    // ---- sweep: all rows (first pass, also emits the phase-2 outputs) or the rows in rs_list ----------
+    auto sweep = [&](const bool subset) {
+      const int nrow = subset ? S.ctl[C_NRS] : T;
+      for (int tile = ntiles - 1 - warp; tile >= 0; tile -= kMatchWarps) {
+        const TileStat ts = P.tiles[tile];
+        const int a = (tile << 5) + lane;
+        bool valid = a < A;
+        bool loaded = false, safe = true;
+        Corners<R> p;
+        TP dx = 0, dy = 0, dw = 1, dh = 1;
+        float ax1 = 0.f, ay1 = 0.f, ax2 = 0.f, ay2 = 0.f, aw = 0.f, ah = 0.f, aalo = 0.f;
+        p.x1 = p.y1 = p.x2 = p.y2 = p.area = (R)0;
+        auto load_lane = [&]() {
+          if (subset && valid && elim_test(a)) valid = false;
+          if (valid) {
+            load_prior(a, p, safe, dx, dy, dw, dh);
+            ax1 = f_down((double)p.x1); ay1 = f_down((double)p.y1);
+            ax2 = f_up((double)p.x2); ay2 = f_up((double)p.y2);
+            aw = fmaxf(__fsub_ru(ax2, ax1), 1.0001e-10f); ah = fmaxf(__fsub_ru(ay2, ay1), 1.0001e-10f);
+            aalo = f_down((double)p.area);
           }
-          if (!__any_sync(SSDG_FULL, need)) continue;
-          Corners<R> g = load_gt(t);
-          u64 key = valid ? key64((double)iou_corners<R>(g, p, EPS)) : 0ull;
-          if (key > ckey) { ckey = key; ct = t; }
-          const u64 rk = *reinterpret_cast<volatile u64*>(&S.rowkey[t]);
-          const bool pass = valid && key >= rk;
-          if (__any_sync(SSDG_FULL, pass)) {
-            const u64 wmax = warp_max_u64(pass ? key : 0ull);
-            const bool top = pass && key == wmax;
-            const u32 tmask = __ballot_sync(SSDG_FULL, top);
-            const int leader = __ffs(tmask) - 1;
-            int base = 0;
-            if (lane == leader) {
-              base = atomicAdd(&S.ctl[C_LOGN], __popc(tmask));
-              atomicMax(&S.rowkey[t], wmax);
-              const float lo = fmaxf(f_down(unkey64(wmax)), 0.f);
-              atomicMax(reinterpret_cast<int*>(&S.glo[t].y), __float_as_int(lo));
+          loaded = true;
+        };
+        if (!subset) load_lane();
+        u64 ckey = 0ull;
+        int ct = -1;
+        for (int k0 = 0; k0 < nrow; k0 += 32) {
+          const int k = k0 + lane;
+          bool reach = false;
+          if (k < nrow) {
+            const int t = subset ? S.rs_list[k] : k;
+            const float4 gb = S.cbox[t];
+            const float2 gl = load_glo(t);
+            reach = !ts.safe || may_reach(gb.x, gb.y, gb.z, gb.w, gl.x, ts.x1, ts.y1, ts.x2, ts.y2, ts.wmax, ts.hmax,
+                                          ts.amin, fminf(thr_lo, gl.y));
+          }
+          u32 m = __ballot_sync(SSDG_FULL, reach);
+          if (m && !loaded) load_lane();
+          while (m) {
+            const int kk = k0 + __ffs(m) - 1;
+            m &= m - 1;
+            const int t = subset ? S.rs_list[kk] : kk;
+            bool need = valid;
+            if (valid && safe) {
+              const float4 gb = S.cbox[t];
+              const float2 gl = load_glo(t);
+              need = may_reach(gb.x, gb.y, gb.z, gb.w, gl.x, ax1, ay1, ax2, ay2, aw, ah, aalo, fminf(thr_lo, gl.y));
             }
-            base = __shfl_sync(SSDG_FULL, base, leader);
-            if (top) {
-              int pos = base + __popc(tmask & ((1u << lane) - 1u));
-              if (pos < kLogCap) log[pos] = ((u32)t << kABits) | (u32)a;
-              else S.ctl[C_OVERFLOW] = 1;
+            if (!__any_sync(SSDG_FULL, need)) continue;
+            Corners<R> g = load_gt(t);
+            u64 key = valid ? key64((double)iou_corners<R>(g, p, EPS)) : 0ull;
+            if (key > ckey) { ckey = key; ct = t; }
+            const u64 rk = *reinterpret_cast<volatile u64*>(&S.rowkey[t]);
+            const bool pass = valid && key >= rk;
+            if (__any_sync(SSDG_FULL, pass)) {
+              const u64 wmax = warp_max_u64(pass ? key : 0ull);
+              const bool top = pass && key == wmax;
+              const u32 tmask = __ballot_sync(SSDG_FULL, top);
+              const int leader = __ffs(tmask) - 1;
+              int base = 0;
+              if (lane == leader) {
+                base = atomicAdd(&S.ctl[C_LOGN], __popc(tmask));
+                atomicMax(&S.rowkey[t], wmax);
+                const float lo = fmaxf(f_down(unkey64(wmax)), 0.f);
+                atomicMax(reinterpret_cast<int*>(&S.glo[t].y), __float_as_int(lo));
+              }
+              base = __shfl_sync(SSDG_FULL, base, leader);
+              if (top) {
+                int pos = base + __popc(tmask & ((1u << lane) - 1u));
+                if (pos < kLogCap) log[pos] = ((u32)t << kABits) | (u32)a;
+                else S.ctl[C_OVERFLOW] = 1;
+              }
             }
           }
         }
-      }
-      // phase-2 result for this prior (phase-1 priors are overwritten after the greedy rounds)
-      if (valid) {
-        const bool pos = ckey > thr_key;
-        float bx = 0.f, by = 0.f, bw = 0.f, bh = 0.f;
-        int lab = 0;
-        if (pos) {
-          TG gx, gy, gw, gh;
-          Vec4<TG>::load(P.gt_boxes, g0 + ct, gx, gy, gw, gh);
-          bx = (float)gx; by = (float)gy; bw = (float)gw; bh = (float)gh;
-          lab = (int)__ldg(P.gt_cls + g0 + ct);
+        // phase-2 result for this prior (phase-1 priors are overwritten after the greedy rounds)
+        if (!subset && valid) {
+          const bool pos = ckey > thr_key;
+          float bx = 0.f, by = 0.f, bw = 0.f, bh = 0.f;
+          int lab = 0;
+          if (pos) {
+            TG gx, gy, gw, gh;
+            Vec4<TG>::load(P.gt_boxes, g0 + ct, gx, gy, gw, gh);
+            bx = (float)gx; by = (float)gy; bw = (float)gw; bh = (float)gh;
+            lab = (int)__ldg(P.gt_cls + g0 + ct);
+          }
+          if (P.out_cls) P.out_cls[obase + a] = lab;
+          if (P.out_mask) P.out_mask[obase + a] = pos ? 1 : 0;
+          if (P.out_match) P.out_match[obase + a] = pos ? ct : -1;
+          if (P.out_box) reinterpret_cast<float4*>(P.out_box)[obase + a] = make_float4(bx, by, bw, bh);
+          if (P.out_loc) reinterpret_cast<float4*>(P.out_loc)[obase + a] = encode_row<TP>(bx, by, bw, bh, dx, dy, dw, dh);
         }
-        if (P.out_cls) P.out_cls[obase + a] = lab;
-        if (P.out_mask) P.out_mask[obase + a] = pos ? 1 : 0;
-        if (P.out_match) P.out_match[obase + a] = pos ? ct : -1;
-        if (P.out_box) reinterpret_cast<float4*>(P.out_box)[obase + a] = make_float4(bx, by, bw, bh);
-        if (P.out_loc) reinterpret_cast<float4*>(P.out_loc)[obase + a] = encode_row<TP>(bx, by, bw, bh, dx, dy, dw, dh);
       }
-    }
-    __syncthreads();
-    if (T == 0) continue;
-
-    // ---- resolve the row arg-max columns from the log ---------------------------------------------
-    {
+      __syncthreads();
+      // resolve the row arg-max columns from the log (the smallest logged column that attains the maximum)
       const bool overflow = S.ctl[C_OVERFLOW] != 0;
-      const int n = min(S.ctl[C_LOGN], kLogCap);
       if (!overflow) {
+        const int n = S.ctl[C_LOGN];
         for (int e = tid; e < n; e += kMatchThreads) {
           const u32 v = log[e];
           const int t = (int)(v >> kABits), a = (int)(v & ((1u << kABits) - 1u));
@@ -369,20 +405,17 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
           Corners<R> g = load_gt(t);
           if (key64((double)iou_corners<R>(g, p, EPS)) == S.rowkey[t]) atomicMin(&S.rowcol[t], a);
         }
+        __syncthreads();
+      } else {
+        if (tid == 0) atomicOr(&P.ws_head[1], 4u);
+        for (int k = 0; k < nrow; ++k) scan_row_exact(subset ? S.rs_list[k] : k);
       }
+      if (tid == 0) { S.ctl[C_LOGN] = 0; S.ctl[C_OVERFLOW] = 0; }
       __syncthreads();
-      // rows whose cached maximum cannot be trusted get an exact, un-culled rescan
-      for (int t = tid; t < T; t += kMatchThreads) {
-        if (overflow || S.rowcol[t] == 0x7fffffff || S.rowkey[t] <= S.cbkey[t])
-          S.rs_list[atomicAdd(&S.ctl[C_NRS], 1)] = t;
-      }
-      if (overflow && tid == 0) atomicOr(&P.ws_head[1], 4u);
-      __syncthreads();
-      const int nrs = S.ctl[C_NRS];
-      for (int i = 0; i < nrs; ++i) rescan_row(S.rs_list[i], false);
-      if (tid == 0) S.ctl[C_NRS] = 0;
-      __syncthreads();
-    }
+    };
+
+    sweep(false);
+    if (T == 0) continue;
 
     // ---- greedy rounds (utils/bbox.py:62-68) --------------------------------------------------------
     for (;;) {
@@ -443,7 +476,12 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
               const int t = t0 + lane;
               const bool need = t < T && !S.dead[t] && S.rowcol[t] == wa;
               const u32 nm = __ballot_sync(SSDG_FULL, need);
-              if (need) S.rs_list[nrs + __popc(nm & ((1u << lane) - 1u))] = t;
+              if (need) {
+                S.rs_list[nrs + __popc(nm & ((1u << lane) - 1u))] = t;
+                S.rowkey[t] = 0ull;
+                S.rowcol[t] = 0x7fffffff;
+                S.glo[t].y = 0.f;
+              }
               nrs += __popc(nm);
             }
           }
@@ -455,7 +493,7 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
       const int nrs = S.ctl[C_NRS];
       const bool done = S.ctl[C_DONE] != 0;
       if (done && nrs == 0) break;
-      for (int i = 0; i < nrs; ++i) rescan_trusted(S.rs_list[i]);
+      if (nrs > 0) sweep(true);
       if (tid == 0) S.ctl[C_NRS] = 0;
       __syncthreads();
       if (done) break;
@@ -488,6 +526,9 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
 
 template <typename TG, typename TP>
 static int launch_match(const MatchParams& P, int grid, size_t smem, cudaStream_t st) {
+  const int ntiles = (P.A + 31) / 32;
+  tile_stats_kernel<TP><<<(ntiles * 32 + 255) / 256, 256, 0, st>>>(P.priors, P.A, const_cast<TileStat*>(P.tiles));
+  SSDG_LAUNCH_CHECK();
   if (smem > 48 * 1024)
     SSDG_CUDA_TRY(cudaFuncSetAttribute(match_kernel<TG, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(SSDG_PROF_MATCH, st);
@@ -503,6 +544,26 @@ static int match_grid(int batch) {
   return batch < g ? batch : g;
 }
 
+struct MatchWs {
+  u32* head;
+  u32* log;
+  u32* elim;
+  TileStat* tiles;
+};
+static size_t match_ws_layout(int n_priors, MatchWs* out, unsigned char* base) {
+  size_t o = 0;
+  const size_t elim_words = ((size_t)n_priors + 31) / 32;
+  if (out) out->head = (u32*)(base + o);
+  o += 256;
+  if (out) out->log = (u32*)(base + o);
+  o += (size_t)kMatchMaxCtas * kLogCap * 4;
+  if (out) out->elim = (u32*)(base + o);
+  o += align_up((size_t)kMatchMaxCtas * elim_words * 4, 256);
+  if (out) out->tiles = (TileStat*)(base + o);
+  o += align_up(elim_words * sizeof(TileStat), 256);
+  return o;
+}
+
 }  // namespace ssdg
 
 using namespace ssdg;
@@ -510,9 +571,7 @@ using namespace ssdg;
 extern "C" size_t ssdg_match_workspace_bytes(int32_t batch, int32_t n_priors, int32_t max_gt) {
   (void)max_gt;
   if (batch <= 0 || n_priors <= 0) return 0;
-  size_t ctas = kMatchMaxCtas;  // the grid never exceeds it
-  size_t elim_words = ((size_t)n_priors + 31) / 32;
-  return 256 + ctas * (size_t)kLogCap * 4 + align_up(ctas * elim_words * 4, 256);
+  return match_ws_layout(n_priors, nullptr, nullptr);
 }
 
 extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const float* gt_cls,
@@ -530,7 +589,9 @@ extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const f
   if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < ssdg_match_workspace_bytes(batch, n_priors, max_gt))
     return SSDG_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  int grid = match_grid(batch);
+  const int grid = match_grid(batch);
+  MatchWs ws;
+  match_ws_layout(n_priors, &ws, (unsigned char*)workspace);
   MatchParams P;
   P.gt_boxes = gt_boxes; P.gt_cls = gt_cls; P.gt_off = gt_offsets; P.priors = priors;
   P.B = batch; P.A = n_priors; P.max_gt = max_gt; P.tm = ((max_gt + 31) / 32) * 32;
@@ -538,10 +599,7 @@ extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const f
   P.thresh = thresh;
   P.out_cls = out_cls; P.out_box = out_box; P.out_loc = out_loc; P.out_mask = out_mask; P.out_match = out_match;
   P.elim_words = (n_priors + 31) / 32;
-  unsigned char* w = (unsigned char*)workspace;
-  P.ws_head = (u32*)w;
-  P.ws_log = (u32*)(w + 256);
-  P.ws_elim = (u32*)(w + 256 + (size_t)kMatchMaxCtas * kLogCap * 4);
+  P.ws_head = ws.head; P.ws_log = ws.log; P.ws_elim = ws.elim; P.tiles = ws.tiles;
   SSDG_CUDA_TRY(cudaMemsetAsync(P.ws_head, 0, 256, st));
   size_t smem = match_smem_bytes(P.tm);
   if ((int)smem > max_smem_optin()) return SSDG_ERR_LIMIT;
