@@ -2,30 +2,31 @@
 // per-class score-threshold / top-k / greedy NMS the reference lacks (spec: oracle/ssd_oracle.py
 // nms_per_class, IoU formula utils/bbox.py:13-25 in float32).
 //
-//   filter_kernel  one streaming pass over the logits [B,A,C].  Tiles are 32 priors of ONE image
-//                  (image-aligned), each warp owns a ring of tiles filled by 1-D bulk TMA
-//                  (cp.async.bulk + mbarrier); lane r owns row r in shared memory (stride C words:
-//                  conflict-free for odd C).  Candidates (p > score_thresh) are found with one ballot
-//                  per class; a warp prefix scan over the classes gives every class its slot range
-//                  in the tile's private segment of the candidate buffer, so there is NO atomic and
-//                  no contention: the tile writes  cand[tile][class-major]  and one packed
-//                  (offset,count) word per class into  meta[image][class][tile].
-//   nms_kernel     one CTA per (image, class): coalesced read + block scan of the class's meta row,
-//                  gather of the candidates, exact top-k by (score desc, prior asc) -- radix select when
-//                  the list is longer than the sort width, then a bitonic sort whose short strides are
-//                  warp-local -- the lower-triangle suppression bit matrix built by 32x32 tasks in
-//                  registers (division-free margin test, the exact IEEE formula only inside the margin),
+//   filter_kernel  one streaming pass over the logits [B,A,C].  Tiles are 32 priors of ONE image; each
+//                  of the 16 warps of a CTA owns one shared-memory tile filled by 1-D bulk TMA
+//                  (cp.async.bulk + mbarrier); lane r owns row r (stride C words: conflict-free for odd
+//                  C).  exp(x - max) is written back into the row while summing, with a one-bit-per-class
+//                  pre-filter; the exact scores exp(x-max)*(1/sum) > score_thresh of the few surviving
+//                  classes are then appended, lane after lane (one warp scan), to the tile's private
+//                  segment of the candidate buffer.  No atomics, one count word per tile.
+//   bucket_kernel  one CTA per image: counting sort of the image's candidates by class (shared-memory
+//                  histogram, scan, scatter) into contiguous per-class lists.
+//   nms_kernel     one CTA per (image, class): exact top-k by (score desc, prior asc) -- radix select when
+//                  the list is longer than the sort width, then a bitonic sort (register shuffles for the
+//                  short strides) -- the lower-triangle suppression bit matrix built by 32x32 tasks in
+//                  registers (cheap float test with a margin, the exact IEEE formula for the survivors),
 //                  and a parallel fixed-point resolution of "kept(i) <=> no kept j < i suppresses i".
 #include <math_constants.h>
 #include "common.cuh"
 
 namespace ssdg {
 
-constexpr int kFThreads = 256;
+constexpr int kFThreads = 512;
 constexpr int kFWarps = kFThreads / 32;
-constexpr int kFStages = 2;
 constexpr int kNmsThreads = 256;
 constexpr int kNmsWarps = kNmsThreads / 32;
+constexpr int kBucketThreads = 512;
+constexpr int kABitsD = 21;     // prior index bits in a staged candidate (A < 2^21, C <= 2048)
 
 struct DetectParams {
   const float* pred_cls;   // logits (filter) or probabilities (kProbs)
@@ -34,8 +35,11 @@ struct DetectParams {
   int B, A, C, tpi;        // tpi: tiles per image
   int tma_ok;              // every tile start / size is 16-byte aligned
   float score_thresh;
-  u32* meta;               // [B][C-1][tpi]  (offset << 8) | count
-  u64* cand;               // [B*tpi][32*(C-1)]
+  u32* tile_cnt;           // [B*tpi] candidates of the tile
+  u64* seg;                // [B*tpi][32*(C-1)] (score key << 32) | (class << 21) | prior
+  u32* cls_cnt;            // [B][C-1]
+  u32* cls_off;            // [B][C-1] start of the class list inside the image's sorted buffer
+  u64* sorted;             // [B][tpi*32*(C-1)] (score key << 32) | ~prior, class-major
   float* boxes;            // [B*A,4] decoded
   float* probs;            // optional [B*A,C]
   float head_thresh;
@@ -57,6 +61,8 @@ __device__ __forceinline__ void tma_load_hint(void* smem_dst, const void* gsrc, 
       : "memory");
 }
 
+// models/ssd_model.py:466-467 with scale 1: the reference evaluates np.exp on its float32 offsets, the
+// products with the (float64) priors in float64, and stores float32.
 template <typename TP>
 __device__ __forceinline__ float4 decode_row(float4 t, const void* priors, int a) {
   double dx, dy, dw, dh;
@@ -71,112 +77,112 @@ __device__ __forceinline__ float4 decode_row(float4 t, const void* priors, int a
   float4 o;
   o.x = (float)((double)t.x * dw + dx);
   o.y = (float)((double)t.y * dh + dy);
-  o.z = (float)(exp((double)t.z) * dw);
-  o.w = (float)(exp((double)t.w) * dh);
+  o.z = (float)((double)expf(t.z) * dw);
+  o.w = (float)((double)expf(t.w) * dh);
   return o;
 }
 
-// One warp tile: `rows` priors of image b starting at prior 32*j; lane r owns row r (rows may be
-// overwritten with the probabilities).  kProbs: the rows already hold probabilities.
+// One warp tile: `rows` priors of image b starting at prior 32*j; lane r owns row r.  After the call
+// the rows hold exp(x - max) (or the probabilities when P.probs is set).  kProbs: the rows already hold
+// probabilities.  Scores are  p_c = exp(x_c - max) * (1 / sum)  in float32.
 template <typename TP, bool kProbs>
-__device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j, int rows, float* tile, u32* wmask,
-                                            u32* wbase, int lane) {
+__device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j, int rows, float* tile, int lane) {
   const int C = P.C, nfg = P.C - 1;
   const bool valid = lane < rows;
   const int a = j * 32 + lane;
   const long long n = (long long)b * P.A + a;
   float* row = tile + (size_t)(valid ? lane : 0) * C;
-  float m = 0.f, s = 1.f;
-  if (!kProbs && valid) {
-    float m0 = -CUDART_INF_F, m1 = m0, m2 = m0, m3 = m0;
-    int c = 0;
-    for (; c + 4 <= C; c += 4) {
-      m0 = fmaxf(m0, row[c]); m1 = fmaxf(m1, row[c + 1]); m2 = fmaxf(m2, row[c + 2]); m3 = fmaxf(m3, row[c + 3]);
-    }
-    for (; c < C; ++c) m0 = fmaxf(m0, row[c]);
-    m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    c = 0;
-    for (; c + 4 <= C; c += 4) {
-      s0 += __expf(row[c] - m); s1 += __expf(row[c + 1] - m); s2 += __expf(row[c + 2] - m); s3 += __expf(row[c + 3] - m);
-    }
-    for (; c < C; ++c) s0 += __expf(row[c] - m);
-    s = (s0 + s1) + (s2 + s3);
-  }
-  // p_c > thresh  <=>  x_c - m > log(thresh * s): pre-filter in logit space with a margin, then the
-  // exact score  exp(x_c - m) / s  decides.
-  const float cut = (P.score_thresh > 0.f) ? __logf(P.score_thresh * s) - 1e-3f : -CUDART_INF_F;
-  for (int c = 0; c < nfg; ++c) {
-    bool p = false;
-    if (valid) {
-      if (kProbs) {
-        p = row[c] > P.score_thresh;
-      } else {
-        const float d = row[c] - m;
-        if (d > cut) p = __fdiv_rn(__expf(d), s) > P.score_thresh;
+  const float thr = P.score_thresh;
+  float4 tbox = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!kProbs && valid && P.boxes) tbox = __ldg(reinterpret_cast<const float4*>(P.pred_box) + n);  // early: hide latency
+  float m = 0.f, inv_s = 1.f;
+  // a class can only be a candidate if exp(x_c - max) > thresh (the sum is >= 1): one bit per class
+  // (first 96 classes in registers; more classes fall back to re-testing every class)
+  const float pre = kProbs ? thr : thr * 0.999f;
+  u32 bits0 = 0u, bits1 = 0u, bits2 = 0u;
+  if (valid) {
+    if (!kProbs) {
+      float m0 = -CUDART_INF_F, m1 = m0, m2 = m0, m3 = m0;
+      int c = 0;
+      for (; c + 4 <= C; c += 4) {
+        m0 = fmaxf(m0, row[c]); m1 = fmaxf(m1, row[c + 1]); m2 = fmaxf(m2, row[c + 2]); m3 = fmaxf(m3, row[c + 3]);
       }
+      for (; c < C; ++c) m0 = fmaxf(m0, row[c]);
+      m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      float s0 = 0.f, s1 = 0.f;
+      c = 0;
+      for (; c + 2 <= C; c += 2) {
+        const float e0 = __expf(row[c] - m), e1 = __expf(row[c + 1] - m);
+        row[c] = e0; row[c + 1] = e1;
+        s0 += e0; s1 += e1;
+      }
+      for (; c < C; ++c) { const float e0 = __expf(row[c] - m); row[c] = e0; s0 += e0; }
+      inv_s = __frcp_rn(s0 + s1);
     }
-    const u32 mc = __ballot_sync(SSDG_FULL, p);
-    if (lane == 0) wmask[c] = mc;
+    const int lim = min(nfg, 96);
+    for (int c = 0; c < lim; ++c) {
+      const u32 hit = row[c] > pre ? 1u : 0u;
+      if (c < 32) bits0 |= hit << c; else if (c < 64) bits1 |= hit << (c - 32); else bits2 |= hit << (c - 64);
+    }
   }
-  __syncwarp();
-  // slot ranges: exclusive prefix sum of the per-class counts, classes in ascending order
-  {
-    u32* mrow = P.meta + (size_t)b * nfg * P.tpi + j;
-    int running = 0;
-    for (int c0 = 0; c0 < nfg; c0 += 32) {
-      const int c = c0 + lane;
-      const int cnt = c < nfg ? __popc(wmask[c]) : 0;
-      int incl = cnt;
+  // exact test of the pre-filtered classes; count, scan, append
+  auto exact = [&](u32 bits, int c0) {
+    u32 keep = 0u;
+    while (bits) {
+      const int cc = __ffs(bits) - 1;
+      bits &= bits - 1;
+      if ((kProbs ? row[c0 + cc] : row[c0 + cc] * inv_s) > thr) keep |= 1u << cc;
+    }
+    return keep;
+  };
+  bits0 = exact(bits0, 0); bits1 = exact(bits1, 32); bits2 = exact(bits2, 64);
+  int extra = 0;   // classes beyond 96: counted here, emitted below
+  if (valid)
+    for (int c = 96; c < nfg; ++c) extra += ((kProbs ? row[c] : row[c] * inv_s) > thr) ? 1 : 0;
+  const int mine = __popc(bits0) + __popc(bits1) + __popc(bits2) + extra;
+  int incl = mine;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(SSDG_FULL, incl, o);
-        if (lane >= o) incl += v;
-      }
-      const int off = running + incl - cnt;
-      if (c < nfg) {
-        wbase[c] = (u32)off;
-        mrow[(size_t)c * P.tpi] = ((u32)off << 8) | (u32)cnt;
-      }
-      running += __shfl_sync(SSDG_FULL, incl, 31);
-    }
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(SSDG_FULL, incl, o);
+    if (lane >= o) incl += v;
   }
-  __syncwarp();
-  {
-    u64* seg = P.cand + ((size_t)b * P.tpi + j) * (size_t)(32 * nfg);
-    const u32 lt = (1u << lane) - 1u;
-    for (int c = 0; c < nfg; ++c) {
-      const u32 mc = wmask[c];
-      if (!mc) continue;
-      if ((mc >> lane) & 1u) {
-        const float score = kProbs ? row[c] : __fdiv_rn(__expf(row[c] - m), s);
-        seg[wbase[c] + (u32)__popc(mc & lt)] = ((u64)key32(score) << 32) | (u64)(~(u32)a);
-      }
+  const size_t tix = (size_t)b * P.tpi + j;
+  if (lane == 31) P.tile_cnt[tix] = (u32)incl;
+  u64* dst = P.seg + tix * (size_t)(32 * nfg) + (incl - mine);
+  auto emit = [&](u32 bits, int c0) {
+    while (bits) {
+      const int c = c0 + __ffs(bits) - 1;
+      bits &= bits - 1;
+      const float score = kProbs ? row[c] : row[c] * inv_s;
+      *dst++ = ((u64)key32(score) << 32) | (u64)(((u32)c << kABitsD) | (u32)a);
     }
-  }
+  };
+  emit(bits0, 0); emit(bits1, 32); emit(bits2, 64);
+  if (valid)
+    for (int c = 96; c < nfg; ++c) {
+      const float score = kProbs ? row[c] : row[c] * inv_s;
+      if (score > thr) *dst++ = ((u64)key32(score) << 32) | (u64)(((u32)c << kABitsD) | (u32)a);
+    }
   if (kProbs || !valid) return;
   if (P.head_score || P.head_cls || P.head_mask) {
     // models/ssd_model.py:481-488: max foreground probability, arg-max over all classes (first max)
     float best = row[0];
     int arg = 0;
-    float fg = -CUDART_INF_F;
+    float fg = 0.f;
     for (int c = 0; c < C; ++c) {
       const float v = row[c];
       if (v > best) { best = v; arg = c; }
       if (c < C - 1) fg = fmaxf(fg, v);
     }
-    const float score = __fdiv_rn(__expf(fg - m), s);
-    const float pbg = __fdiv_rn(__expf(row[C - 1] - m), s);
+    const float score = fg * inv_s;
+    const float pbg = row[C - 1] * inv_s;
     if (P.head_score) P.head_score[n] = score;
     if (P.head_cls) P.head_cls[n] = arg;
     if (P.head_mask) P.head_mask[n] = (score > P.head_thresh && !(pbg > P.head_thresh)) ? 1 : 0;
   }
-  if (P.boxes) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(P.pred_box) + n);
-    reinterpret_cast<float4*>(P.boxes)[n] = decode_row<TP>(t, P.priors, a);
-  }
+  if (P.boxes) reinterpret_cast<float4*>(P.boxes)[n] = decode_row<TP>(tbox, P.priors, a);
   if (P.probs)
-    for (int c = 0; c < C; ++c) row[c] = __fdiv_rn(__expf(row[c] - m), s);
+    for (int c = 0; c < C; ++c) row[c] *= inv_s;
 }
 
 template <typename TP, bool kProbs>
@@ -186,21 +192,18 @@ __global__ void __launch_bounds__(kFThreads, 1) filter_kernel(DetectParams P, in
   const size_t tile_floats = (size_t)32 * C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* bufs = reinterpret_cast<float*>(smem_raw);
-  u64* bars = reinterpret_cast<u64*>(smem_raw + (size_t)warps_per_cta * kFStages * tile_floats * 4);
-  u32* scratch = reinterpret_cast<u32*>(bars + kFWarps * kFStages);   // [warps][2][C]
+  u64* bars = reinterpret_cast<u64*>(smem_raw + (size_t)warps_per_cta * tile_floats * 4);
   if (tid == 0) {
-    for (int i = 0; i < warps_per_cta * kFStages; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < warps_per_cta; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
   }
   __syncthreads();
   if (warp >= warps_per_cta) return;
-  u32* wmask = scratch + (size_t)warp * 2 * C;
-  u32* wbase = wmask + C;
   const long long ntiles = (long long)P.B * tpi;
   const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
   const long long stride = (long long)gridDim.x * warps_per_cta;
-  float* mybuf = bufs + (size_t)warp * kFStages * tile_floats;
-  u64* mybar = bars + warp * kFStages;
+  float* tile = bufs + (size_t)warp * tile_floats;
+  u64* mybar = bars + warp;
   const u64 pol = evict_first_policy();
 
   auto tile_rows = [&](long long t) { const int j = (int)(t % tpi); return min(32, A - j * 32); };
@@ -209,48 +212,94 @@ __global__ void __launch_bounds__(kFThreads, 1) filter_kernel(DetectParams P, in
     const int j = (int)(t - b * tpi);
     return P.pred_cls + ((size_t)b * A + (size_t)j * 32) * C;
   };
-  auto issue = [&](long long t, int s) {  // lane 0 only
+  auto issue = [&](long long t) {  // lane 0 only
     const u32 bytes = (u32)tile_rows(t) * (u32)C * 4u;
-    mbar_arrive_expect_tx(&mybar[s], bytes);
-    tma_load_hint(mybuf + (size_t)s * tile_floats, tile_src(t), bytes, &mybar[s], pol);
+    mbar_arrive_expect_tx(mybar, bytes);
+    tma_load_hint(tile, tile_src(t), bytes, mybar, pol);
   };
-
-  if (P.tma_ok && lane == 0)
-    for (int s = 0; s < kFStages; ++s) {
-      const long long t = gw + (long long)s * stride;
-      if (t < ntiles) issue(t, s);
-    }
+  // One tile in flight per warp; the other 15 warps of the CTA hide its latency.
+  if (P.tma_ok && lane == 0 && gw < ntiles) issue(gw);
   int k = 0;
   for (long long t = gw; t < ntiles; t += stride, ++k) {
-    const int s = k % kFStages;
-    float* tile = mybuf + (size_t)s * tile_floats;
     const int rows = tile_rows(t);
     const int b = (int)(t / tpi), j = (int)(t - (long long)b * tpi);
     if (P.tma_ok) {
-      mbar_wait(&mybar[s], (u32)((k / kFStages) & 1));
+      mbar_wait(mybar, (u32)(k & 1));
     } else {  // unaligned shapes: plain cooperative copy
       const float* g = tile_src(t);
       for (int i = lane; i < rows * C; i += 32) tile[i] = g[i];
       __syncwarp();
     }
-    filter_tile<TP, kProbs>(P, b, j, rows, tile, wmask, wbase, lane);
+    filter_tile<TP, kProbs>(P, b, j, rows, tile, lane);
     __syncwarp();
     if (!kProbs && P.probs) {  // the tile layout in shared memory equals the layout in global memory
       float* dst = P.probs + ((size_t)b * A + (size_t)j * 32) * C;
       for (int i = lane; i < rows * C; i += 32) __stcs(&dst[i], tile[i]);
       __syncwarp();
     }
-    const long long tn = t + (long long)kFStages * stride;
-    if (P.tma_ok && lane == 0 && tn < ntiles) issue(tn, s);
+    const long long tn = t + stride;
+    if (P.tma_ok && lane == 0 && tn < ntiles) issue(tn);
+  }
+}
+
+// Counting sort of one image's candidates by class.
+__global__ void __launch_bounds__(kBucketThreads) bucket_kernel(DetectParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int nfg = P.C - 1, tpi = P.tpi, b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  u32* hist = reinterpret_cast<u32*>(smem_raw);   // [nfg]
+  u32* off = hist + nfg;                          // [nfg]
+  for (int c = tid; c < nfg; c += kBucketThreads) hist[c] = 0u;
+  __syncthreads();
+  const u32* tcnt = P.tile_cnt + (size_t)b * tpi;
+  const u64* seg = P.seg + (size_t)b * tpi * (size_t)(32 * nfg);
+  for (int j = warp; j < tpi; j += kBucketThreads / 32) {
+    const int cnt = (int)tcnt[j];
+    const u64* s = seg + (size_t)j * (32 * nfg);
+    for (int e = lane; e < cnt; e += 32) atomicAdd(&hist[(u32)s[e] >> kABitsD], 1u);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    u32 running = 0u;
+    for (int c0 = 0; c0 < nfg; c0 += 32) {
+      const int c = c0 + lane;
+      const u32 cnt = c < nfg ? hist[c] : 0u;
+      u32 incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 v = __shfl_up_sync(SSDG_FULL, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (c < nfg) {
+        off[c] = running + incl - cnt;
+        P.cls_cnt[(size_t)b * nfg + c] = cnt;
+        P.cls_off[(size_t)b * nfg + c] = running + incl - cnt;
+      }
+      running += __shfl_sync(SSDG_FULL, incl, 31);
+    }
+  }
+  __syncthreads();
+  u64* out = P.sorted + (size_t)b * tpi * (size_t)(32 * nfg);
+  for (int j = warp; j < tpi; j += kBucketThreads / 32) {
+    const int cnt = (int)tcnt[j];
+    const u64* s = seg + (size_t)j * (32 * nfg);
+    for (int e = lane; e < cnt; e += 32) {
+      const u64 v = s[e];
+      const u32 low = (u32)v;
+      const u32 pos = atomicAdd(&off[low >> kABitsD], 1u);
+      out[pos] = (v & 0xffffffff00000000ull) | (u64)(~(low & ((1u << kABitsD) - 1u)));
+    }
   }
 }
 
 // ---- per-(image, class) NMS ---------------------------------------------------------------------------
 struct NmsParams {
-  const u32* meta;
-  const u64* cand;
+  const u32* cls_cnt;
+  const u32* cls_off;
+  const u64* sorted;
+  size_t img_stride;   // candidates capacity per image in `sorted`
   const float* boxes;  // [B,A,4]
-  int A, n_fg, tpi, top_k, sortn;  // sortn: power of two >= max(top_k, 32)
+  int A, n_fg, top_k, sortn;  // sortn: power of two >= max(top_k, 32)
   float iou_thresh;
   int* out_kept;
   int* out_count;
@@ -292,41 +341,18 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
   u32* keptw = sup + (size_t)sortn * WP;                        // [W]
   u32* remw = keptw + W;                                        // [W]
   u32* hist = remw + W;                                         // [256]
-  int* wsum = reinterpret_cast<int*>(hist + 256);               // [kNmsWarps]
   __shared__ u64 sel_prefix;
   __shared__ int sel_k, sel_fill;
 
   const size_t list = blockIdx.x;
   const int b = (int)(list / P.n_fg);
-  const int tpi = P.tpi;
-  const u32* mrow = P.meta + list * (size_t)tpi;
-  const u64* cbase = P.cand + (size_t)b * tpi * (size_t)(32 * P.n_fg);
+  int n = (int)P.cls_cnt[list];
+  const u64* cl = P.sorted + (size_t)b * P.img_stride + P.cls_off[list];
 
-  // candidates of this class: per-tile (offset, count) -> exclusive scan -> total
-  int mine = 0;
-  for (int j = tid; j < tpi; j += kNmsThreads) mine += (int)(mrow[j] & 255u);
-  int incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(SSDG_FULL, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) wsum[warp] = incl;
   for (int i = tid; i < sortn; i += kNmsThreads) keys[i] = 0ull;
   __syncthreads();
-  int before = incl - mine, n = 0;
-  for (int w = 0; w < kNmsWarps; ++w) {
-    if (w < warp) before += wsum[w];
-    n += wsum[w];
-  }
-
   if (n <= sortn) {
-    int dst = before;
-    for (int j = tid; j < tpi; j += kNmsThreads) {
-      const u32 mv = mrow[j];
-      const u64* src = cbase + (size_t)j * (32 * P.n_fg) + (mv >> 8);
-      for (int e = 0; e < (int)(mv & 255u); ++e) keys[dst++] = src[e];
-    }
+    for (int i = tid; i < n; i += kNmsThreads) keys[i] = cl[i];
   } else {
     // Radix select of the top_k-th largest composite key (keys are unique), 8 bits per pass.
     if (tid == 0) { sel_prefix = 0ull; sel_k = P.top_k; sel_fill = 0; }
@@ -336,13 +362,9 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
       __syncthreads();
       const u64 pre = sel_prefix;
       const u64 hmask = shift == 56 ? 0ull : (~0ull << (shift + 8));
-      for (int j = tid; j < tpi; j += kNmsThreads) {
-        const u32 mv = mrow[j];
-        const u64* src = cbase + (size_t)j * (32 * P.n_fg) + (mv >> 8);
-        for (int e = 0; e < (int)(mv & 255u); ++e) {
-          const u64 v = src[e];
-          if ((v & hmask) == pre) atomicAdd(&hist[(u32)(v >> shift) & 255u], 1u);
-        }
+      for (int i = tid; i < n; i += kNmsThreads) {
+        const u64 v = cl[i];
+        if ((v & hmask) == pre) atomicAdd(&hist[(u32)(v >> shift) & 255u], 1u);
       }
       __syncthreads();
       if (tid == 0) {
@@ -357,15 +379,11 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
       __syncthreads();
     }
     const u64 kth = sel_prefix;
-    for (int j = tid; j < tpi; j += kNmsThreads) {
-      const u32 mv = mrow[j];
-      const u64* src = cbase + (size_t)j * (32 * P.n_fg) + (mv >> 8);
-      for (int e = 0; e < (int)(mv & 255u); ++e) {
-        const u64 v = src[e];
-        if (v >= kth) {
-          const int p = atomicAdd(&sel_fill, 1);
-          if (p < sortn) keys[p] = v;
-        }
+    for (int i = tid; i < n; i += kNmsThreads) {
+      const u64 v = cl[i];
+      if (v >= kth) {
+        const int p = atomicAdd(&sel_fill, 1);
+        if (p < sortn) keys[p] = v;
       }
     }
     __syncthreads();
@@ -373,7 +391,33 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
   }
   int sn = 32;
   while (sn < n) sn <<= 1;           // n <= sortn here; the keys beyond n are 0 and sort to the end
-  bitonic_sort_desc(keys, sn, tid);
+  if (sn <= kNmsThreads) {
+    // one key per thread: short strides by shuffle, strides >= 32 through shared memory
+    __syncthreads();
+    u64 key = keys[tid < sortn ? tid : 0];
+    if (tid >= sn) key = 0ull;
+    for (int size = 2; size <= sn; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        u64 other;
+        if (stride < 32) {
+          other = __shfl_xor_sync(SSDG_FULL, key, stride);
+        } else {
+          __syncthreads();
+          if (tid < sortn) keys[tid] = key;
+          __syncthreads();
+          other = keys[(tid ^ stride) < sortn ? (tid ^ stride) : 0];
+        }
+        const bool take_max = ((tid & stride) == 0) == ((tid & size) == 0);
+        const bool gt = key > other;
+        key = (gt == take_max) ? key : other;
+      }
+    }
+    __syncthreads();
+    if (tid < sn) keys[tid] = key;
+    __syncthreads();
+  } else {
+    bitonic_sort_desc(keys, sn, tid);
+  }
   const int m = min(n, P.top_k);
   const int mpad = (m + 31) & ~31;
 
@@ -415,28 +459,25 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
     const int i = (g << 5) + lane;
     const float4 bi = crn[i];
     const float2 qi = q2[i];
-    u32 bits = 0u, amb = 0u;
-#pragma unroll 8
+    // every pair that can exceed the threshold passes the cheap float test (1e-4 relative margin,
+    // float rounding is ~1e-7); the rare survivors are decided by the formula itself
+    u32 maybe = 0u;
+    const float qi_lo = qi.y;
+#pragma unroll
     for (int jj = 0; jj < 32; ++jj) {
       const int j = (w << 5) + jj;
       const float4 bj = crn[j];
-      const float2 qj = q2[j];
       const float ex = fminf(bi.z, bj.z) - fmaxf(bi.x, bj.x);
       const float ey = fminf(bi.w, bj.w) - fmaxf(bi.y, bj.y);
-      const float inter = ex * ey;
-      const bool over = ex > 0.f && ey > 0.f;
-      const bool s = over && inter > qi.x + qj.x;
-      const bool am = over && !s && !(inter < qi.y + qj.y);
-      bits |= (s ? 1u : 0u) << jj;
-      amb |= (am ? 1u : 0u) << jj;
+      if (ex > 0.f && ex * ey >= qi_lo + q2[j].y) maybe |= 1u << jj;
     }
-    if (!fast_ok) amb = 0xffffffffu;
-    if (w == g) { const u32 lower = (1u << lane) - 1u; bits &= lower; amb &= lower; }
-    if (i >= m) { bits = 0u; amb = 0u; }
-    // inside the margin (or no fast test): the formula itself, IEEE float32, no contraction
-    while (amb) {
-      const int jj = __ffs(amb) - 1;
-      amb &= amb - 1;
+    if (!fast_ok) maybe = 0xffffffffu;
+    if (w == g) maybe &= (1u << lane) - 1u;
+    if (i >= m) maybe = 0u;
+    u32 bits = 0u;
+    while (maybe) {   // IEEE float32, no contraction (utils/bbox.py:13-25)
+      const int jj = __ffs(maybe) - 1;
+      maybe &= maybe - 1;
       const int j = (w << 5) + jj;
       if (j >= m) continue;
       const float4 bj = crn[j];
@@ -444,7 +485,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
       const float ey = fmaxf(0.f, __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
       const float inter = __fmul_rn(ex, ey);
       const float den = __fadd_rn(__fsub_rn(__fadd_rn(area[j], area[i]), inter), 1e-10f);
-      if (__fdiv_rn(inter, den) > thr) bits |= 1u << jj; else bits &= ~(1u << jj);
+      if (__fdiv_rn(inter, den) > thr) bits |= 1u << jj;
     }
     sup[(size_t)i * WP + w] = bits;
   }
@@ -490,8 +531,8 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
 }
 
 static int f_warps_for(int C) {
-  const size_t budget = 200 * 1024 - (size_t)kFWarps * 2 * C * 4;
-  int w = (int)(budget / ((size_t)kFStages * 32 * C * 4));
+  const size_t budget = 220 * 1024;
+  int w = (int)(budget / ((size_t)32 * C * 4 + 8));
   return w > kFWarps ? kFWarps : w;
 }
 static int next_pow2(int v) {
@@ -501,21 +542,27 @@ static int next_pow2(int v) {
 }
 static size_t nms_smem_bytes(int sortn) {
   const int W = sortn / 32, WP = W | 1;
-  return (size_t)sortn * (8 + 16 + 8 + 4) + (size_t)sortn * WP * 4 + 2 * W * 4 + 256 * 4 + kNmsWarps * 4 + 128;
+  return (size_t)sortn * (8 + 16 + 8 + 4) + (size_t)sortn * WP * 4 + 2 * W * 4 + 256 * 4 + 128;
 }
 
 struct DetectWs {
-  u32* meta;
-  u64* cand;
+  u32 *tile_cnt, *cls_cnt, *cls_off;
+  u64 *seg, *sorted;
   float* boxes;
 };
 static size_t detect_ws_layout(long long batch, int A, int C, DetectWs* out, unsigned char* base) {
   size_t o = 0;
   const size_t tpi = ((size_t)A + 31) / 32;
   const size_t nfg = (size_t)C - 1;
-  if (out) out->meta = (u32*)(base + o);
-  o += align_up((size_t)batch * nfg * tpi * 4, 256);
-  if (out) out->cand = (u64*)(base + o);
+  if (out) out->tile_cnt = (u32*)(base + o);
+  o += align_up((size_t)batch * tpi * 4, 256);
+  if (out) out->cls_cnt = (u32*)(base + o);
+  o += align_up((size_t)batch * nfg * 4, 256);
+  if (out) out->cls_off = (u32*)(base + o);
+  o += align_up((size_t)batch * nfg * 4, 256);
+  if (out) out->seg = (u64*)(base + o);
+  o += align_up((size_t)batch * tpi * 32 * nfg * 8, 256);
+  if (out) out->sorted = (u64*)(base + o);
   o += align_up((size_t)batch * tpi * 32 * nfg * 8, 256);
   if (out) out->boxes = (float*)(base + o);
   o += align_up((size_t)batch * A * 16, 256);
@@ -526,7 +573,7 @@ template <bool kProbs>
 static int run_filter(DetectParams& P, int prior_dtype, cudaStream_t st) {
   const int warps = f_warps_for(P.C);
   if (warps < 1) return SSDG_ERR_LIMIT;
-  const size_t smem = (size_t)warps * kFStages * 32 * P.C * 4 + kFWarps * kFStages * 8 + (size_t)kFWarps * 2 * P.C * 4 + 128;
+  const size_t smem = (size_t)warps * 32 * P.C * 4 + kFWarps * 8 + 128;
   int grid = sm_count();
   const long long tiles = (long long)P.B * P.tpi;
   const long long need = (tiles + warps - 1) / warps;
@@ -542,13 +589,17 @@ static int run_filter(DetectParams& P, int prior_dtype, cudaStream_t st) {
   }
   prof_end(SSDG_PROF_FILTER, st);
   SSDG_LAUNCH_CHECK();
+  bucket_kernel<<<P.B, kBucketThreads, (size_t)2 * (P.C - 1) * 4, st>>>(P);
+  SSDG_LAUNCH_CHECK();
   return SSDG_OK;
 }
 
 static int run_nms(const DetectWs& ws, const float* boxes, long long batch, int A, int C, int top_k, float iou_thresh,
                    int* out_kept, int* out_count, float* out_score, cudaStream_t st) {
   NmsParams Q;
-  Q.meta = ws.meta; Q.cand = ws.cand; Q.boxes = boxes; Q.A = A; Q.n_fg = C - 1; Q.tpi = (A + 31) / 32; Q.top_k = top_k;
+  Q.cls_cnt = ws.cls_cnt; Q.cls_off = ws.cls_off; Q.sorted = ws.sorted;
+  Q.img_stride = (size_t)((A + 31) / 32) * 32 * (size_t)(C - 1);
+  Q.boxes = boxes; Q.A = A; Q.n_fg = C - 1; Q.top_k = top_k;
   Q.sortn = next_pow2(top_k); Q.iou_thresh = iou_thresh;
   Q.out_kept = out_kept; Q.out_count = out_count; Q.out_score = out_score;
   const size_t smem = nms_smem_bytes(Q.sortn);
@@ -562,6 +613,11 @@ static int run_nms(const DetectWs& ws, const float* boxes, long long batch, int 
   prof_end(SSDG_PROF_NMS, st);
   SSDG_LAUNCH_CHECK();
   return SSDG_OK;
+}
+
+static void fill_params(DetectParams& P, const DetectWs& ws, long long batch, int A, int C) {
+  P.B = (int)batch; P.A = A; P.C = C; P.tpi = (A + 31) / 32;
+  P.tile_cnt = ws.tile_cnt; P.seg = ws.seg; P.cls_cnt = ws.cls_cnt; P.cls_off = ws.cls_off; P.sorted = ws.sorted;
 }
 
 }  // namespace ssdg
@@ -583,7 +639,7 @@ extern "C" int ssdg_detect(const float* pred_cls, const float* pred_box, const v
   if (!pred_cls || !pred_box || !priors || !out_kept || !out_count) return SSDG_ERR_ARG;
   if (batch <= 0 || n_priors <= 0 || n_classes < 2 || top_k <= 0) return SSDG_ERR_ARG;
   if (prior_dtype != SSDG_F32 && prior_dtype != SSDG_F64) return SSDG_ERR_ARG;
-  if (top_k > 1024 || batch > 0x7fffffff / 64) return SSDG_ERR_LIMIT;
+  if (top_k > 1024 || batch > 0x7fffffff / 64 || n_priors >= (1 << kABitsD) || n_classes > 2048) return SSDG_ERR_LIMIT;
   if (((uintptr_t)pred_box | (uintptr_t)priors | (uintptr_t)out_boxes) & 15) return SSDG_ERR_ALIGN;
   if (((uintptr_t)pred_cls | (uintptr_t)out_probs) & 3) return SSDG_ERR_ALIGN;
   if (!workspace || ((uintptr_t)workspace & 255) ||
@@ -593,9 +649,9 @@ extern "C" int ssdg_detect(const float* pred_cls, const float* pred_box, const v
   DetectWs ws;
   detect_ws_layout(batch, n_priors, n_classes, &ws, (unsigned char*)workspace);
   DetectParams P;
-  P.pred_cls = pred_cls; P.pred_box = pred_box; P.priors = priors;
-  P.B = (int)batch; P.A = n_priors; P.C = n_classes; P.tpi = (n_priors + 31) / 32; P.score_thresh = score_thresh;
-  P.meta = ws.meta; P.cand = ws.cand; P.boxes = out_boxes ? out_boxes : ws.boxes; P.probs = out_probs;
+  fill_params(P, ws, batch, n_priors, n_classes);
+  P.pred_cls = pred_cls; P.pred_box = pred_box; P.priors = priors; P.score_thresh = score_thresh;
+  P.boxes = out_boxes ? out_boxes : ws.boxes; P.probs = out_probs;
   P.head_thresh = head_thresh; P.head_score = head_score; P.head_cls = head_cls; P.head_mask = head_mask;
   int rc = run_filter<false>(P, prior_dtype, st);
   if (rc) return rc;
@@ -607,7 +663,7 @@ extern "C" int ssdg_nms(const float* probs, const float* boxes, int64_t batch, i
                         float* out_kept_score, void* workspace, size_t workspace_bytes, void* stream) {
   if (!probs || !boxes || !out_kept || !out_count) return SSDG_ERR_ARG;
   if (batch <= 0 || n_priors <= 0 || n_classes < 2 || top_k <= 0) return SSDG_ERR_ARG;
-  if (top_k > 1024 || batch > 0x7fffffff / 64) return SSDG_ERR_LIMIT;
+  if (top_k > 1024 || batch > 0x7fffffff / 64 || n_priors >= (1 << kABitsD) || n_classes > 2048) return SSDG_ERR_LIMIT;
   if ((uintptr_t)boxes & 15) return SSDG_ERR_ALIGN;
   if ((uintptr_t)probs & 3) return SSDG_ERR_ALIGN;
   if (!workspace || ((uintptr_t)workspace & 255) ||
@@ -617,9 +673,9 @@ extern "C" int ssdg_nms(const float* probs, const float* boxes, int64_t batch, i
   DetectWs ws;
   detect_ws_layout(batch, n_priors, n_classes, &ws, (unsigned char*)workspace);
   DetectParams P;
-  P.pred_cls = probs; P.pred_box = nullptr; P.priors = nullptr;
-  P.B = (int)batch; P.A = n_priors; P.C = n_classes; P.tpi = (n_priors + 31) / 32; P.score_thresh = score_thresh;
-  P.meta = ws.meta; P.cand = ws.cand; P.boxes = nullptr; P.probs = nullptr;
+  fill_params(P, ws, batch, n_priors, n_classes);
+  P.pred_cls = probs; P.pred_box = nullptr; P.priors = nullptr; P.score_thresh = score_thresh;
+  P.boxes = nullptr; P.probs = nullptr;
   P.head_thresh = 0.f; P.head_score = nullptr; P.head_cls = nullptr; P.head_mask = nullptr;
   int rc = run_filter<true>(P, SSDG_F32, st);
   if (rc) return rc;

@@ -302,8 +302,26 @@ __global__ void __launch_bounds__(256) final_kernel(LossParams P) {
   const u32 kth = st.prefix;
   double sum = 0;
   u32 cnt = 0, ovl = 0;
+  const long long gtid = (long long)blockIdx.x * blockDim.x + tid, gstride = (long long)gridDim.x * blockDim.x;
+  const bool vec = (((uintptr_t)P.gt_mask | (uintptr_t)P.neg_mask) & 3) == 0;
   if (!st.status) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < P.N; i += (long long)gridDim.x * blockDim.x) {
+    long long done = 0;
+    if (vec) {   // four priors per thread per iteration: independent 16-byte / 4-byte loads in flight
+      const long long n4 = P.N >> 2;
+      const float4* v4 = reinterpret_cast<const float4*>(P.neg_ce);
+      const uchar4* m4 = reinterpret_cast<const uchar4*>(P.gt_mask);
+      for (long long i = gtid; i < n4; i += gstride) {
+        const float4 v = v4[i];
+        const uchar4 mk = m4[i];
+        const bool n0 = key32(v.x) >= kth, n1 = key32(v.y) >= kth, n2 = key32(v.z) >= kth, n3 = key32(v.w) >= kth;
+        sum += (double)((n0 ? v.x : 0.f) + (n1 ? v.y : 0.f)) + (double)((n2 ? v.z : 0.f) + (n3 ? v.w : 0.f));
+        cnt += (u32)n0 + (u32)n1 + (u32)n2 + (u32)n3;
+        ovl += (u32)(n0 && mk.x) + (u32)(n1 && mk.y) + (u32)(n2 && mk.z) + (u32)(n3 && mk.w);
+        if (P.neg_mask) reinterpret_cast<uchar4*>(P.neg_mask)[i] = make_uchar4(n0, n1, n2, n3);
+      }
+      done = n4 << 2;
+    }
+    for (long long i = done + gtid; i < P.N; i += gstride) {
       const float v = P.neg_ce[i];
       const bool neg = key32(v) >= kth;
       if (neg) {
@@ -314,7 +332,7 @@ __global__ void __launch_bounds__(256) final_kernel(LossParams P) {
       if (P.neg_mask) P.neg_mask[i] = neg ? 1 : 0;
     }
   } else if (P.neg_mask) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < P.N; i += (long long)gridDim.x * blockDim.x) P.neg_mask[i] = 0;
+    for (long long i = gtid; i < P.N; i += gstride) P.neg_mask[i] = 0;
   }
   sum = warp_sum(sum);
   cnt = __reduce_add_sync(SSDG_FULL, cnt);

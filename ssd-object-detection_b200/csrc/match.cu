@@ -68,6 +68,7 @@ struct MatchParams {
   u32* ws_elim;          // per CTA elim_words
   const TileStat* tiles; // [ceil(A/32)]
   int elim_words;
+  int elim_in_smem;      // the knocked-out-column bitmap fits in shared memory
 };
 
 template <typename TG, typename TP>
@@ -200,10 +201,17 @@ struct MatchSmem {
     rs_list = (int*)(base + o); o += 4 * (size_t)tm;
     red_idx = (int*)(base + o); o += 4 * kMatchWarps;
     ctl = (int*)(base + o); o += 4 * 16;
-    dead = (uint8_t*)(base + o);
+    dead = (uint8_t*)(base + o); o += (size_t)tm;
+    o = (o + 15) & ~(size_t)15;
+    elim_s = (u32*)(base + o);
   }
+  u32* elim_s;                       // [elim_words] when it fits, else the bitmap lives in the workspace
 };
-static size_t match_smem_bytes(int tm) { return (size_t)tm * (5 * 8 + 16 + 8 + 8 + 16 + 1) + 12 * kMatchWarps + 64 + 80; }
+constexpr int kElimSmemWords = 4096;   // 16 KB: up to 131072 priors
+static size_t match_smem_bytes(int tm, int elim_words) {
+  return (size_t)tm * (5 * 8 + 16 + 8 + 8 + 16 + 1) + 12 * kMatchWarps + 64 + 96 +
+         (elim_words <= kElimSmemWords ? (size_t)elim_words * 4 : 0);
+}
 
 enum { C_IMG = 0, C_LOGN, C_NRS, C_DONE, C_ROUND, C_DEGEN, C_MINELIM, C_OVERFLOW };
 
@@ -218,7 +226,8 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
   const int ntiles = (A + 31) >> 5;
   const R EPS = (R)1e-10;
   u32* log = P.ws_log + (size_t)blockIdx.x * kLogCap;
-  u32* elim = P.ws_elim + (size_t)blockIdx.x * P.elim_words;
+  // the greedy rounds read-modify-write this bitmap serially: keep it in shared memory when it fits
+  u32* elim = P.elim_in_smem ? S.elim_s : P.ws_elim + (size_t)blockIdx.x * P.elim_words;
   const u64 thr_key = key64((double)(R)P.thresh);
   const float thr_lo = f_down((double)(R)P.thresh);
 
@@ -419,7 +428,91 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
 
     // ---- greedy rounds (utils/bbox.py:62-68) --------------------------------------------------------
     for (;;) {
-      if (warp == 0) {
+      if (warp == 0 && T <= 128) {
+        // Fast path: the (<= 4) rows a lane owns are cached in registers, so a round is a handful of
+        // register operations, three REDUX and one shuffle -- no shared-memory chain on the serial path.
+        int round = S.ctl[C_ROUND];
+        int nrs = 0;
+        u64 rk[4];
+        int rc[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int t = lane + 32 * r;
+          const bool live = t < T && !S.dead[t];
+          rk[r] = live ? S.rowkey[t] : 0ull;
+          rc[r] = live ? S.rowcol[t] : -1;
+        }
+        while (round < T) {
+          u64 bk = rk[0];
+          int bt = lane;
+#pragma unroll
+          for (int r = 1; r < 4; ++r)
+            if (rk[r] > bk) { bk = rk[r]; bt = lane + 32 * r; }
+          if (bk == 0ull) bt = 0x7fffffff;
+          warp_argmax_u64(bk, bt);
+          int wt, wa;
+          if (bk > SSDG_KEY_ZERO || round == 0) {
+            wt = bt;
+            const int rr = wt >> 5;
+            const int mycol = rr == 0 ? rc[0] : (rr == 1 ? rc[1] : (rr == 2 ? rc[2] : rc[3]));
+            wa = __shfl_sync(SSDG_FULL, mycol, wt & 31);
+          } else {
+            // Knocked-out entries (0.0) tie with or beat every live entry: full rule, first flat index.
+            if (lane == 0) {
+              u64 best = 0ull;
+              long long bflat = 0x7fffffffffffffffll;
+              const int me = S.ctl[C_MINELIM];
+              for (int t = 0; t < T; ++t) {
+                u64 k; long long f;
+                if (S.dead[t]) { k = SSDG_KEY_ZERO; f = (long long)t * A; }
+                else {
+                  k = S.rowkey[t]; f = (long long)t * A + S.rowcol[t];
+                  if (k > best || (k == best && f < bflat)) { best = k; bflat = f; }
+                  k = SSDG_KEY_ZERO; f = (long long)t * A + me;
+                }
+                if (k > best || (k == best && f < bflat)) { best = k; bflat = f; }
+              }
+              S.red_idx[0] = (int)(bflat / A);
+              S.red_idx[1] = (int)(bflat % A);
+              S.ctl[C_DEGEN] = 1;
+            }
+            __syncwarp();
+            wt = S.red_idx[0];
+            wa = S.red_idx[1];
+          }
+          const bool fresh = !elim_test(wa);
+          __syncwarp();
+          if (lane == 0) {
+            S.pair_t[round] = wt;
+            S.pair_a[round] = wa;
+            S.dead[wt] = 1;
+            elim[wa >> 5] |= 1u << (wa & 31);
+            if (wa < S.ctl[C_MINELIM]) S.ctl[C_MINELIM] = wa;
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            if (lane + 32 * r == wt) { rk[r] = 0ull; rc[r] = -1; }
+          __syncwarp();
+          ++round;
+          if (fresh && round < T) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const bool need = rk[r] != 0ull && rc[r] == wa;
+              const u32 nm = __ballot_sync(SSDG_FULL, need);
+              if (need) {
+                const int t = lane + 32 * r;
+                S.rs_list[nrs + __popc(nm & ((1u << lane) - 1u))] = t;
+                S.rowkey[t] = 0ull;
+                S.rowcol[t] = 0x7fffffff;
+                S.glo[t].y = 0.f;
+              }
+              nrs += __popc(nm);
+            }
+          }
+          if (nrs > 0) break;
+        }
+        if (lane == 0) { S.ctl[C_ROUND] = round; S.ctl[C_NRS] = nrs; S.ctl[C_DONE] = round >= T; }
+      } else if (warp == 0) {
         int round = S.ctl[C_ROUND];
         int nrs = 0;
         while (round < T) {
@@ -601,7 +694,8 @@ extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const f
   P.elim_words = (n_priors + 31) / 32;
   P.ws_head = ws.head; P.ws_log = ws.log; P.ws_elim = ws.elim; P.tiles = ws.tiles;
   SSDG_CUDA_TRY(cudaMemsetAsync(P.ws_head, 0, 256, st));
-  size_t smem = match_smem_bytes(P.tm);
+  P.elim_in_smem = P.elim_words <= kElimSmemWords ? 1 : 0;
+  size_t smem = match_smem_bytes(P.tm, P.elim_words);
   if ((int)smem > max_smem_optin()) return SSDG_ERR_LIMIT;
   if (gt_dtype == SSDG_F32 && prior_dtype == SSDG_F64) return launch_match<float, double>(P, grid, smem, st);
   if (gt_dtype == SSDG_F32 && prior_dtype == SSDG_F32) return launch_match<float, float>(P, grid, smem, st);

@@ -391,6 +391,18 @@ def test_detect_other_parameters(priors300):
         _check_detect(pred_cls, pred_box, priors300, **kw)
 
 
+def test_detect_many_classes_and_odd_shapes():
+    """C > 97 (classes beyond the register bit-sets), prior counts that are not multiples of 4 or 32
+    (the non-TMA tile path), tiny images."""
+    rng = np.random.default_rng(12)
+    for (b, a, c, bias) in [(2, 333, 130, 3.0), (3, 64, 21, 2.0), (1, 37, 5, 0.0), (2, 1000, 200, 4.0)]:
+        pri = np.concatenate([rng.uniform(0.1, 0.9, (a, 2)), rng.uniform(0.05, 0.4, (a, 2))], 1)
+        pred_cls = rng.normal(size=(b, a, c)).astype(np.float32)
+        pred_cls[..., -1] += bias
+        pred_box = (rng.normal(size=(b, a, 4)) * 0.3).astype(np.float32)
+        _check_detect(pred_cls, pred_box, pri, score_thresh=0.01, top_k=100, iou_thresh=0.45)
+
+
 def test_nms_on_oracle_inputs_bit_exact(priors300):
     """The second stage alone, fed the oracle's own float32 scores and boxes: no tolerance anywhere."""
     pred_cls, pred_box = synth.make_predictions(34, 2, 8732, bg_bias=6.0)
