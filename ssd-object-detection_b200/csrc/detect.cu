@@ -23,7 +23,7 @@ namespace ssdg {
 
 constexpr int kFThreads = 512;
 constexpr int kFWarps = kFThreads / 32;
-constexpr int kNmsThreads = 256;
+constexpr int kNmsThreads = 128;
 constexpr int kNmsWarps = kNmsThreads / 32;
 constexpr int kBucketThreads = 512;
 constexpr int kABitsD = 21;     // prior index bits in a staged candidate (A < 2^21, C <= 2048)
@@ -109,20 +109,36 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
       }
       for (; c < C; ++c) m0 = fmaxf(m0, row[c]);
       m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      // exp(x - max) is written back into the row; one pre-filter bit per foreground class
       float s0 = 0.f, s1 = 0.f;
-      c = 0;
-      for (; c + 2 <= C; c += 2) {
-        const float e0 = __expf(row[c] - m), e1 = __expf(row[c + 1] - m);
-        row[c] = e0; row[c + 1] = e1;
-        s0 += e0; s1 += e1;
-      }
-      for (; c < C; ++c) { const float e0 = __expf(row[c] - m); row[c] = e0; s0 += e0; }
+      auto chunk = [&](int c0, int cn) {
+        u32 bits = 0u;
+        int cc = 0;
+        for (; cc + 2 <= cn; cc += 2) {
+          const float e0 = __expf(row[c0 + cc] - m), e1 = __expf(row[c0 + cc + 1] - m);
+          row[c0 + cc] = e0; row[c0 + cc + 1] = e1;
+          s0 += e0; s1 += e1;
+          if (e0 > pre) bits |= 1u << cc;
+          if (e1 > pre) bits |= 2u << cc;
+        }
+        if (cc < cn) {
+          const float e0 = __expf(row[c0 + cc] - m);
+          row[c0 + cc] = e0; s0 += e0;
+          if (e0 > pre) bits |= 1u << cc;
+        }
+        return bits;
+      };
+      bits0 = chunk(0, min(32, nfg));
+      if (nfg > 32) bits1 = chunk(32, min(32, nfg - 32));
+      if (nfg > 64) bits2 = chunk(64, min(32, nfg - 64));
+      for (c = min(nfg, 96); c < C; ++c) { const float e0 = __expf(row[c] - m); row[c] = e0; s0 += e0; }
       inv_s = __frcp_rn(s0 + s1);
-    }
-    const int lim = min(nfg, 96);
-    for (int c = 0; c < lim; ++c) {
-      const u32 hit = row[c] > pre ? 1u : 0u;
-      if (c < 32) bits0 |= hit << c; else if (c < 64) bits1 |= hit << (c - 32); else bits2 |= hit << (c - 64);
+    } else {
+      const int lim = min(nfg, 96);
+      for (int c = 0; c < lim; ++c) {
+        const u32 hit = row[c] > pre ? 1u : 0u;
+        if (c < 32) bits0 |= hit << c; else if (c < 64) bits1 |= hit << (c - 32); else bits2 |= hit << (c - 64);
+      }
     }
   }
   // exact test of the pre-filtered classes; count, scan, append
@@ -329,6 +345,21 @@ __device__ __forceinline__ void bitonic_sort_desc(u64* keys, int n, int tid) {
   __syncthreads();
 }
 
+// compare-exchange of the register-resident pairs (r, r|STRIDE) of an 8-keys-per-lane bitonic network
+template <int STRIDE>
+__device__ __forceinline__ void sort_inreg(u64 (&k)[8], int size, int lane) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    if ((r & STRIDE) == 0) {
+      const bool desc = ((8 * lane + r) & size) == 0;
+      const u64 a = k[r], b = k[r | STRIDE];
+      const bool sw = (a < b) == desc;
+      k[r] = sw ? b : a;
+      k[r | STRIDE] = sw ? a : b;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -391,29 +422,38 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
   }
   int sn = 32;
   while (sn < n) sn <<= 1;           // n <= sortn here; the keys beyond n are 0 and sort to the end
-  if (sn <= kNmsThreads) {
-    // one key per thread: short strides by shuffle, strides >= 32 through shared memory
+  if (sn <= 256) {
+    // One warp sorts up to 256 keys held 8 per lane (element e = 8*lane + r): strides 1, 2, 4 are
+    // register-to-register, strides 8..128 one shuffle per key; no barrier inside the network.
     __syncthreads();
-    u64 key = keys[tid < sortn ? tid : 0];
-    if (tid >= sn) key = 0ull;
-    for (int size = 2; size <= sn; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        u64 other;
-        if (stride < 32) {
-          other = __shfl_xor_sync(SSDG_FULL, key, stride);
-        } else {
-          __syncthreads();
-          if (tid < sortn) keys[tid] = key;
-          __syncthreads();
-          other = keys[(tid ^ stride) < sortn ? (tid ^ stride) : 0];
+    if (warp == 0) {
+      u64 k[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) k[r] = (8 * lane + r) < sn ? keys[8 * lane + r] : 0ull;
+      for (int size = 2; size <= sn; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          if (stride >= 8) {
+            const int ls = stride >> 3;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const u64 other = __shfl_xor_sync(SSDG_FULL, k[r], ls);
+              const int e = 8 * lane + r;
+              const bool take_max = ((e & stride) == 0) == ((e & size) == 0);
+              k[r] = ((k[r] > other) == take_max) ? k[r] : other;
+            }
+          } else if (stride == 4) {
+            sort_inreg<4>(k, size, lane);
+          } else if (stride == 2) {
+            sort_inreg<2>(k, size, lane);
+          } else {
+            sort_inreg<1>(k, size, lane);
+          }
         }
-        const bool take_max = ((tid & stride) == 0) == ((tid & size) == 0);
-        const bool gt = key > other;
-        key = (gt == take_max) ? key : other;
       }
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (8 * lane + r < sn) keys[8 * lane + r] = k[r];
     }
-    __syncthreads();
-    if (tid < sn) keys[tid] = key;
     __syncthreads();
   } else {
     bitonic_sort_desc(keys, sn, tid);
@@ -469,7 +509,8 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
       const float4 bj = crn[j];
       const float ex = fminf(bi.z, bj.z) - fmaxf(bi.x, bj.x);
       const float ey = fminf(bi.w, bj.w) - fmaxf(bi.y, bj.y);
-      if (ex > 0.f && ex * ey >= qi_lo + q2[j].y) maybe |= 1u << jj;
+      const u32 hit = (u32)(ex > 0.f) & (u32)(ex * ey >= qi_lo + q2[j].y);   // no branch
+      maybe |= hit << jj;
     }
     if (!fast_ok) maybe = 0xffffffffu;
     if (w == g) maybe &= (1u << lane) - 1u;

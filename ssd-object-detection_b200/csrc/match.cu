@@ -350,13 +350,6 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
             const int kk = k0 + __ffs(m) - 1;
             m &= m - 1;
             const int t = subset ? S.rs_list[kk] : kk;
-            bool need = valid;
-            if (valid && safe) {
-              const float4 gb = S.cbox[t];
-              const float2 gl = load_glo(t);
-              need = may_reach(gb.x, gb.y, gb.z, gb.w, gl.x, ax1, ay1, ax2, ay2, aw, ah, aalo, fminf(thr_lo, gl.y));
-            }
-            if (!__any_sync(SSDG_FULL, need)) continue;
             Corners<R> g = load_gt(t);
             u64 key = valid ? key64((double)iou_corners<R>(g, p, EPS)) : 0ull;
             if (key > ckey) { ckey = key; ct = t; }
