@@ -127,8 +127,18 @@ SSDG_API int ssdg_prior_boxes(const int32_t* feat_h, const int32_t* feat_w, cons
  * Limits: A < 2^21, max_gt <= 2048.
  */
 SSDG_API size_t ssdg_match_workspace_bytes(int32_t batch, int32_t n_priors, int32_t max_gt);
+/* Optional acceleration structure for a fixed prior set (the reference builds its priors once, in
+ * __init__, models/ssd_model.py:60,164): a permutation that groups priors of identical shape into
+ * spatially compact 32-prior tiles, plus per-tile statistics, so the matcher's tile-level IoU bound is
+ * tight.  It changes no result.  ssdg_prior_index_build copies the priors to the host, sorts there and
+ * SYNCHRONISES; call it once per prior set.  `index` is device memory of ssdg_prior_index_bytes bytes
+ * (256-byte aligned) that must stay alive and unmodified while it is passed to ssdg_match_encode. */
+SSDG_API size_t ssdg_prior_index_bytes(int32_t n_priors);
+SSDG_API int ssdg_prior_index_build(const void* priors, int32_t prior_dtype, int32_t n_priors, void* index,
+                           size_t index_bytes, void* stream);
 SSDG_API int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const float* gt_cls,
                       const int32_t* gt_offsets, const void* priors, int32_t prior_dtype,
+                      const void* prior_index /* NULL or from ssdg_prior_index_build for these priors */,
                       int32_t batch, int32_t n_priors, int32_t max_gt, double thresh,
                       int32_t* out_cls, float* out_box, float* out_loc, uint8_t* out_mask,
                       int32_t* out_match, void* workspace, size_t workspace_bytes, void* stream);

@@ -422,38 +422,40 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
   }
   int sn = 32;
   while (sn < n) sn <<= 1;           // n <= sortn here; the keys beyond n are 0 and sort to the end
-  if (sn <= 256) {
-    // One warp sorts up to 256 keys held 8 per lane (element e = 8*lane + r): strides 1, 2, 4 are
-    // register-to-register, strides 8..128 one shuffle per key; no barrier inside the network.
+  if (sn <= 2 * kNmsThreads) {
+    // Two keys per thread (element e = 2*tid + r): stride 1 is register-to-register, strides 2..32 one
+    // shuffle per key, only the strides that cross warps (>= 64) go through shared memory.
     __syncthreads();
-    if (warp == 0) {
-      u64 k[8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) k[r] = (8 * lane + r) < sn ? keys[8 * lane + r] : 0ull;
-      for (int size = 2; size <= sn; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-          if (stride >= 8) {
-            const int ls = stride >> 3;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              const u64 other = __shfl_xor_sync(SSDG_FULL, k[r], ls);
-              const int e = 8 * lane + r;
-              const bool take_max = ((e & stride) == 0) == ((e & size) == 0);
-              k[r] = ((k[r] > other) == take_max) ? k[r] : other;
-            }
-          } else if (stride == 4) {
-            sort_inreg<4>(k, size, lane);
-          } else if (stride == 2) {
-            sort_inreg<2>(k, size, lane);
+    u64 k0 = (2 * tid) < sn ? keys[2 * tid] : 0ull, k1 = (2 * tid + 1) < sn ? keys[2 * tid + 1] : 0ull;
+    const int e0 = 2 * tid, e1 = 2 * tid + 1;
+    for (int size = 2; size <= sn; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        if (stride == 1) {
+          const bool sw = (k0 < k1) == ((e0 & size) == 0);
+          const u64 a = k0, b = k1;
+          k0 = sw ? b : a; k1 = sw ? a : b;
+        } else {
+          u64 o0, o1;
+          if (stride <= 32) {
+            o0 = __shfl_xor_sync(SSDG_FULL, k0, stride >> 1);
+            o1 = __shfl_xor_sync(SSDG_FULL, k1, stride >> 1);
           } else {
-            sort_inreg<1>(k, size, lane);
+            __syncthreads();
+            if (e1 < sn) { keys[e0] = k0; keys[e1] = k1; }
+            __syncthreads();
+            o0 = e1 < sn ? keys[e0 ^ stride] : 0ull;
+            o1 = e1 < sn ? keys[e1 ^ stride] : 0ull;
           }
+          const bool t0 = ((e0 & stride) == 0) == ((e0 & size) == 0);
+          const bool t1 = ((e1 & stride) == 0) == ((e1 & size) == 0);
+          k0 = ((k0 > o0) == t0) ? k0 : o0;
+          k1 = ((k1 > o1) == t1) ? k1 : o1;
         }
       }
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-        if (8 * lane + r < sn) keys[8 * lane + r] = k[r];
     }
+    __syncthreads();
+    if (e0 < sn) keys[e0] = k0;
+    if (e1 < sn) keys[e1] = k1;
     __syncthreads();
   } else {
     bitonic_sort_desc(keys, sn, tid);

@@ -26,6 +26,12 @@
 //               to live columns).
 //   scatter     phase-1 pairs overwrite the phase-2 outputs the sweep already stored.
 #include <math_constants.h>
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <utility>
+#include <vector>
 #include "common.cuh"
 
 namespace ssdg {
@@ -66,7 +72,9 @@ struct MatchParams {
   u32* ws_head;          // [0] next image, [1] status bits
   u32* ws_log;           // per CTA kLogCap
   u32* ws_elim;          // per CTA elim_words
-  const TileStat* tiles; // [ceil(A/32)]
+  const TileStat* tiles; // [ntiles]
+  const int* perm;       // [ntiles*32] slot -> prior index (-1: padding); NULL: identity
+  int ntiles;
   int elim_words;
   int elim_in_smem;      // the knocked-out-column bitmap fits in shared memory
 };
@@ -136,13 +144,14 @@ __device__ __forceinline__ bool may_reach(float gx1, float gy1, float gx2, float
 
 // ---- per-tile statistics of the priors (once per launch) ------------------------------------------------
 template <typename TP>
-__global__ void __launch_bounds__(256) tile_stats_kernel(const void* __restrict__ priors, int A, TileStat* __restrict__ out) {
+__global__ void __launch_bounds__(256) tile_stats_kernel(const void* __restrict__ priors, int A, const int* __restrict__ perm,
+                                                         int ntiles, TileStat* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int tile = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int ntiles = (A + 31) >> 5;
   if (tile >= ntiles) return;
-  const int a = (tile << 5) + lane;
-  const bool valid = a < A;
+  const int slot = (tile << 5) + lane;
+  const int a = perm ? perm[slot] : slot;
+  const bool valid = a >= 0 && a < A;
   u32 kx1 = ~0u, ky1 = ~0u, kx2 = 0u, ky2 = 0u, kw = 0u, kh = 0u, ka = ~0u;
   bool safe = true;
   if (valid) {
@@ -223,7 +232,7 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
   S.carve(smem_raw, P.tm);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int A = P.A;
-  const int ntiles = (A + 31) >> 5;
+  const int ntiles = P.ntiles;
   const R EPS = (R)1e-10;
   u32* log = P.ws_log + (size_t)blockIdx.x * kLogCap;
   // the greedy rounds read-modify-write this bitmap serially: keep it in shared memory when it fits
@@ -313,8 +322,9 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
       const int nrow = subset ? S.ctl[C_NRS] : T;
       for (int tile = ntiles - 1 - warp; tile >= 0; tile -= kMatchWarps) {
         const TileStat ts = P.tiles[tile];
-        const int a = (tile << 5) + lane;
-        bool valid = a < A;
+        const int slot = (tile << 5) + lane;
+        const int a = P.perm ? __ldg(P.perm + slot) : slot;
+        bool valid = a >= 0 && a < A;
         bool loaded = false, safe = true;
         Corners<R> p;
         TP dx = 0, dy = 0, dw = 1, dh = 1;
@@ -612,9 +622,11 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
 
 template <typename TG, typename TP>
 static int launch_match(const MatchParams& P, int grid, size_t smem, cudaStream_t st) {
-  const int ntiles = (P.A + 31) / 32;
-  tile_stats_kernel<TP><<<(ntiles * 32 + 255) / 256, 256, 0, st>>>(P.priors, P.A, const_cast<TileStat*>(P.tiles));
-  SSDG_LAUNCH_CHECK();
+  if (!P.perm) {
+    tile_stats_kernel<TP><<<(P.ntiles * 32 + 255) / 256, 256, 0, st>>>(P.priors, P.A, nullptr, P.ntiles,
+                                                                       const_cast<TileStat*>(P.tiles));
+    SSDG_LAUNCH_CHECK();
+  }
   if (smem > 48 * 1024)
     SSDG_CUDA_TRY(cudaFuncSetAttribute(match_kernel<TG, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(SSDG_PROF_MATCH, st);
@@ -650,9 +662,101 @@ static size_t match_ws_layout(int n_priors, MatchWs* out, unsigned char* base) {
   return o;
 }
 
+// ---- prior index ---------------------------------------------------------------------------------------
+constexpr int kIndexMaxShapes = 64;
+struct IndexInfo { int n_priors, ntiles; };
+static std::mutex g_index_mu;
+static std::unordered_map<const void*, IndexInfo> g_index;   // device pointer -> geometry
+
+static size_t index_slots(int n_priors) { return ((size_t)n_priors + 31) / 32 * 32 + (size_t)kIndexMaxShapes * 32; }
+static size_t index_perm_offset() { return 256; }
+static size_t index_tiles_offset(int n_priors) { return 256 + align_up(index_slots(n_priors) * 4, 256); }
+
 }  // namespace ssdg
 
 using namespace ssdg;
+
+extern "C" size_t ssdg_prior_index_bytes(int32_t n_priors) {
+  if (n_priors <= 0) return 0;
+  return index_tiles_offset(n_priors) + align_up(index_slots(n_priors) / 32 * sizeof(TileStat), 256);
+}
+
+extern "C" int ssdg_prior_index_build(const void* priors, int32_t prior_dtype, int32_t n_priors, void* index,
+                                      size_t index_bytes, void* stream) {
+  if (!priors || !index || n_priors <= 0) return SSDG_ERR_ARG;
+  if (prior_dtype != SSDG_F32 && prior_dtype != SSDG_F64) return SSDG_ERR_ARG;
+  if (n_priors >= (1 << kABits)) return SSDG_ERR_LIMIT;
+  if (((uintptr_t)index & 255) || index_bytes < ssdg_prior_index_bytes(n_priors)) return SSDG_ERR_WORKSPACE;
+  if ((uintptr_t)priors & 15) return SSDG_ERR_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t esz = prior_dtype == SSDG_F64 ? 8 : 4;
+  std::vector<unsigned char> raw((size_t)n_priors * 4 * esz);
+  SSDG_CUDA_TRY(cudaMemcpyAsync(raw.data(), priors, raw.size(), cudaMemcpyDeviceToHost, st));
+  SSDG_CUDA_TRY(cudaStreamSynchronize(st));
+  auto at = [&](int a, int k) -> double {
+    return prior_dtype == SSDG_F64 ? reinterpret_cast<const double*>(raw.data())[(size_t)a * 4 + k]
+                                   : (double)reinterpret_cast<const float*>(raw.data())[(size_t)a * 4 + k];
+  };
+  // shape classes: identical (w, h); too many distinct shapes -> one class (spatial blocking only)
+  std::map<std::pair<double, double>, int> shape_id;
+  std::vector<int> cls(n_priors);
+  bool one_class = false;
+  for (int a = 0; a < n_priors && !one_class; ++a) {
+    auto key = std::make_pair(at(a, 2), at(a, 3));
+    auto it = shape_id.find(key);
+    if (it == shape_id.end()) {
+      if ((int)shape_id.size() >= kIndexMaxShapes) { one_class = true; break; }
+      it = shape_id.emplace(key, (int)shape_id.size()).first;
+    }
+    cls[a] = it->second;
+  }
+  if (one_class) std::fill(cls.begin(), cls.end(), 0);
+  const int ncls = one_class ? 1 : (int)shape_id.size();
+  std::vector<std::vector<int>> members(ncls);
+  for (int a = 0; a < n_priors; ++a) members[cls[a]].push_back(a);
+  std::vector<int> perm;
+  perm.reserve(index_slots(n_priors));
+  for (auto& mem : members) {
+    // block the class into ~32-prior cells of a g x g grid over its centres, row-major blocks
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (int a : mem) {
+      const double cx = at(a, 0), cy = at(a, 1);
+      if (cx == cx && cy == cy) { x0 = std::min(x0, cx); x1 = std::max(x1, cx); y0 = std::min(y0, cy); y1 = std::max(y1, cy); }
+    }
+    int g = 1;
+    while ((size_t)g * g * 32 < mem.size()) ++g;
+    const double sx = x1 > x0 ? g / (x1 - x0) : 0.0, sy = y1 > y0 ? g / (y1 - y0) : 0.0;
+    auto block = [&](int a) {
+      const double cx = at(a, 0), cy = at(a, 1);
+      int bx = (cx == cx) ? (int)std::min<double>(g - 1, std::max(0.0, (cx - x0) * sx)) : 0;
+      int by = (cy == cy) ? (int)std::min<double>(g - 1, std::max(0.0, (cy - y0) * sy)) : 0;
+      return by * g + bx;
+    };
+    std::vector<std::pair<int, int>> keyed;
+    keyed.reserve(mem.size());
+    for (int a : mem) keyed.emplace_back(block(a), a);
+    std::stable_sort(keyed.begin(), keyed.end());
+    for (auto& kv : keyed) perm.push_back(kv.second);
+    while (perm.size() % 32) perm.push_back(-1);
+  }
+  const int ntiles = (int)(perm.size() / 32);
+  if (perm.size() > index_slots(n_priors)) return SSDG_ERR_LIMIT;
+  unsigned char* base = (unsigned char*)index;
+  int header[4] = {n_priors, ntiles, 0, 0};
+  SSDG_CUDA_TRY(cudaMemcpyAsync(base, header, sizeof(header), cudaMemcpyHostToDevice, st));
+  SSDG_CUDA_TRY(cudaMemcpyAsync(base + index_perm_offset(), perm.data(), perm.size() * 4, cudaMemcpyHostToDevice, st));
+  TileStat* tiles = (TileStat*)(base + index_tiles_offset(n_priors));
+  const int* dperm = (const int*)(base + index_perm_offset());
+  if (prior_dtype == SSDG_F64)
+    tile_stats_kernel<double><<<(ntiles * 32 + 255) / 256, 256, 0, st>>>(priors, n_priors, dperm, ntiles, tiles);
+  else
+    tile_stats_kernel<float><<<(ntiles * 32 + 255) / 256, 256, 0, st>>>(priors, n_priors, dperm, ntiles, tiles);
+  SSDG_LAUNCH_CHECK();
+  SSDG_CUDA_TRY(cudaStreamSynchronize(st));
+  std::lock_guard<std::mutex> lk(g_index_mu);
+  g_index[index] = IndexInfo{n_priors, ntiles};
+  return SSDG_OK;
+}
 
 extern "C" size_t ssdg_match_workspace_bytes(int32_t batch, int32_t n_priors, int32_t max_gt) {
   (void)max_gt;
@@ -662,7 +766,7 @@ extern "C" size_t ssdg_match_workspace_bytes(int32_t batch, int32_t n_priors, in
 
 extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const float* gt_cls,
                                  const int32_t* gt_offsets, const void* priors, int32_t prior_dtype,
-                                 int32_t batch, int32_t n_priors, int32_t max_gt, double thresh,
+                                 const void* prior_index, int32_t batch, int32_t n_priors, int32_t max_gt, double thresh,
                                  int32_t* out_cls, float* out_box, float* out_loc, uint8_t* out_mask,
                                  int32_t* out_match, void* workspace, size_t workspace_bytes, void* stream) {
   if (!gt_boxes || !gt_cls || !gt_offsets || !priors || batch <= 0 || n_priors <= 0 || max_gt < 0) return SSDG_ERR_ARG;
@@ -686,6 +790,21 @@ extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const f
   P.out_cls = out_cls; P.out_box = out_box; P.out_loc = out_loc; P.out_mask = out_mask; P.out_match = out_match;
   P.elim_words = (n_priors + 31) / 32;
   P.ws_head = ws.head; P.ws_log = ws.log; P.ws_elim = ws.elim; P.tiles = ws.tiles;
+  P.perm = nullptr; P.ntiles = (n_priors + 31) / 32;
+  if (prior_index) {
+    IndexInfo info;
+    {
+      std::lock_guard<std::mutex> lk(g_index_mu);
+      auto it = g_index.find(prior_index);
+      if (it == g_index.end()) return SSDG_ERR_ARG;
+      info = it->second;
+    }
+    if (info.n_priors != n_priors) return SSDG_ERR_SHAPE;
+    const unsigned char* ib = (const unsigned char*)prior_index;
+    P.perm = (const int*)(ib + index_perm_offset());
+    P.tiles = (const TileStat*)(ib + index_tiles_offset(n_priors));
+    P.ntiles = info.ntiles;
+  }
   SSDG_CUDA_TRY(cudaMemsetAsync(P.ws_head, 0, 256, st));
   P.elim_in_smem = P.elim_words <= kElimSmemWords ? 1 : 0;
   size_t smem = match_smem_bytes(P.tm, P.elim_words);

@@ -44,7 +44,9 @@ PROTOTYPES = {
     "ssdg_prior_count": (_i64, [_pi32, _pi32, _pi32, _i32]),
     "ssdg_prior_boxes": (C.c_int, [_pi32, _pi32, _pf64, _pi32, _pf64, _i32, _f64, _vp, _i64, _vp]),
     "ssdg_match_workspace_bytes": (_sz, [_i32, _i32, _i32]),
-    "ssdg_match_encode": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f64,
+    "ssdg_prior_index_bytes": (_sz, [_i32]),
+    "ssdg_prior_index_build": (C.c_int, [_vp, _i32, _i32, _vp, _sz, _vp]),
+    "ssdg_match_encode": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _f64,
                                     _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ssdg_match_status": (C.c_int, [_vp, _pi32, _vp]),
     "ssdg_encode": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _i32, _vp]),

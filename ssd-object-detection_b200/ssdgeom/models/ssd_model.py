@@ -105,6 +105,7 @@ class SSDBoxGeometry:
         self.thresh = thresh                            # Config.thresh, :48
         self.input_size = table["input_size"]
         self._prior_dev = ops.prior_boxes(table["sizes"], table["s_k_refer"], table["aspect_ratio"], table["input_size"])
+        ops.prior_index(self._prior_dev)                # matcher acceleration index, built once
         self._prior_box = None
 
     def _build_prior_box(self, size_list):

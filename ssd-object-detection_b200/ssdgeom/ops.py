@@ -70,8 +70,25 @@ def prior_boxes(size_list, s_k_refer, aspect_ratio, input_size=300, stream=None)
 
 
 # ---- A3 + A4 + A5 ----------------------------------------------------------------------------------
+def prior_index(priors, stream=None) -> D.DeviceArray:
+    """Build (once per prior set; synchronises) the matcher's acceleration index for device priors and
+    cache it on the array object.  It changes no result."""
+    priors = D.as_device(priors)
+    cached = getattr(priors, "_ssdg_index", None)
+    if cached is not None:
+        return cached
+    lib = N.lib()
+    a = int(priors.shape[0])
+    idx = D.empty((int(lib.ssdg_prior_index_bytes(a)) + 255) // 256 * 256, np.uint8)
+    N.check(lib.ssdg_prior_index_build(priors.ptr, _code(priors.dtype), a, idx.ptr, idx.nbytes, D.stream_handle(stream)),
+            "prior_index_build")
+    idx._keep = priors
+    priors._ssdg_index = idx
+    return idx
+
+
 def match_encode(gt_boxes, gt_cls, gt_offsets, priors, batch: int, max_gt: int, thresh: float = 0.5,
-                 want=("cls", "loc", "mask"), out=None, stream=None) -> dict:
+                 want=("cls", "loc", "mask"), out=None, stream=None, index=None) -> dict:
     """Batched match_bbox + apply_anchor_box (utils/bbox.py:44-101, models/ssd_model.py:211-224).
     ``want`` selects outputs among cls, box, loc, mask, match; ``out`` may carry preallocated arrays."""
     gt_boxes, priors = D.as_device(gt_boxes), D.as_device(priors)
@@ -87,8 +104,10 @@ def match_encode(gt_boxes, gt_cls, gt_offsets, priors, batch: int, max_gt: int, 
     lib = N.lib()
     nbytes = lib.ssdg_match_workspace_bytes(batch, a, max_gt)
     ws = POOL.get("match", nbytes)
+    if index is None:
+        index = getattr(priors, "_ssdg_index", None)     # built by prior_index() for long-lived prior sets
     N.check(lib.ssdg_match_encode(gt_boxes.ptr, _code(gt_boxes.dtype), gt_cls.ptr, gt_offsets.ptr, priors.ptr,
-                                  _code(priors.dtype), batch, a, int(max_gt), float(thresh),
+                                  _code(priors.dtype), _p(index), batch, a, int(max_gt), float(thresh),
                                   _p(out.get("cls")), _p(out.get("box")), _p(out.get("loc")), _p(out.get("mask")),
                                   _p(out.get("match")), ws.ptr, ws.nbytes, D.stream_handle(stream)), "match_encode")
     out["_keep"] = (gt_boxes, gt_cls, gt_offsets, priors, ws)

@@ -21,6 +21,7 @@ class HotPath:
         self.score_thresh, self.top_k, self.iou_thresh = float(score_thresh), int(top_k), float(iou_thresh)
         self.priors = ops.prior_boxes(table["sizes"], table["s_k_refer"], table["aspect_ratio"], table["input_size"])
         self.A = a = int(self.priors.shape[0])
+        ops.prior_index(self.priors)                     # one-off, like the priors themselves
         b, c = self.batch, self.classes
         n_gt = int(total_gt if total_gt is not None else b * self.max_gt)
         self.gt_boxes = D.empty((n_gt, 4), np.float32)

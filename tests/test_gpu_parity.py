@@ -172,6 +172,39 @@ def test_assign_random_bit_exact(table, batch, max_t, mode, seed, priors300, pri
         close(o_loc[i], O.apply_anchor_box(w_box, priors).astype(np.float32))
 
 
+@pytest.mark.parametrize("table,batch,max_t,mode", [("ssd300", 12, 100, "max"), ("ssd300", 16, 100, "coco"),
+                                                   ("ssd512", 3, 100, "max"), ("ssd512", 2, 500, "max")])
+def test_assign_with_prior_index(table, batch, max_t, mode, priors300, priors512):
+    """The shape-sorted prior index is an acceleration structure only: identical outputs with and
+    without it, and equal to the oracle."""
+    priors = priors300 if table == "ssd300" else priors512
+    boxes, cls, off = synth.make_gt(41, batch, max_t, mode)
+    want = ("cls", "box", "loc", "mask", "match")
+    plain = ops.match_encode(boxes, cls, off, priors, batch, int(np.diff(off).max()), 0.5, want=want)
+    d_pri = D.to_device(priors)
+    idx = ops.prior_index(d_pri)
+    assert ops.prior_index(d_pri) is idx                      # cached on the array
+    fast = ops.match_encode(boxes, cls, off, d_pri, batch, int(np.diff(off).max()), 0.5, want=want)
+    for k in want:
+        assert np.array_equal(plain[k].to_host(), fast[k].to_host()), k
+    for i in (0, batch - 1):
+        w = O.match_bbox(cls[off[i]:off[i + 1]], boxes[off[i]:off[i + 1]], priors, 0.5, sweeps=False)
+        assert np.array_equal(fast["cls"].to_host()[i], w[0]) and np.array_equal(fast["mask"].to_host()[i].astype(bool), w[2])
+    # irregular priors (many distinct shapes -> single class, spatial blocking only) and float32 priors
+    rng = np.random.default_rng(3)
+    odd = np.concatenate([rng.uniform(0, 1, (1500, 2)), rng.uniform(0.03, 0.6, (1500, 2))], 1)
+    for pri in (odd, odd.astype(np.float32), priors[::5].astype(np.float32)):
+        d = D.to_device(pri)
+        ops.prior_index(d)
+        b2, c2, o2 = synth.make_gt(42, 4, 30, "max")
+        a = ops.match_encode(b2, c2, o2, pri, 4, 30, 0.5, want=want)
+        f = ops.match_encode(b2, c2, o2, d, 4, 30, 0.5, want=want)
+        for k in want:
+            assert np.array_equal(a[k].to_host(), f[k].to_host()), k
+        w = O.match_bbox(c2[o2[1]:o2[2]], b2[o2[1]:o2[2]], pri, 0.5, sweeps=False)
+        assert np.array_equal(f["cls"].to_host()[1], w[0]) and np.array_equal(f["mask"].to_host()[1].astype(bool), w[2])
+
+
 def test_assign_edge_cases(priors300):
     pri = priors300[::7].copy()
     # duplicates, GT outside the image, tiny GT, T == 1, ragged offsets incl. an empty image

@@ -68,7 +68,7 @@ def test_sass_has_bulk_tma_and_no_legacy_tensor_ops(native):
 def test_argument_errors_need_no_gpu(native):
     lib = native.lib()
     # argument validation happens before any CUDA call
-    assert lib.ssdg_match_encode(None, 0, None, None, None, 1, 1, 1, 1, 0.5, None, None, None, None, None, None, 0, None) == native.ERR_ARG
+    assert lib.ssdg_match_encode(None, 0, None, None, None, 1, None, 1, 1, 1, 0.5, None, None, None, None, None, None, 0, None) == native.ERR_ARG
     assert lib.ssdg_multibox_loss(None, None, None, None, None, 1, 1, 2, 3, None, None, None, None, None, None, 0, None) == native.ERR_ARG
     assert lib.ssdg_match_workspace_bytes(256, 8732, 100) > 0
     assert lib.ssdg_loss_workspace_bytes(256, 8732, 81) >= 256 * 8732 * 4
