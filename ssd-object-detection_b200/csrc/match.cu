@@ -9,22 +9,22 @@
 //     ALL rows, positive iff not (iou <= thresh).
 //   * Scatter (:84-90) in append order, later pairs overwrite; encode (:94-101).
 //
-// How the work is organised (32 priors = one warp tile, lane = prior):
-//   tile_stats  once per launch: outward-rounded float bounding box, max width/height and min area
-//               of every tile of priors (shared by all images).
-//   sweep       every warp walks its tiles from the last (largest priors of an SSD pyramid, which
-//               establish the row maxima early) to the first.  32 ground-truth rows at a time are
-//               tested against the tile with a conservative float upper bound of the IoU any prior
-//               of the tile can reach (one ballot); surviving (tile, row) pairs repeat the bound per
-//               lane, and only pairs that can still be a positive (> thresh) or the row's arg-max
-//               (>= running row maximum) reach the exact float64 evaluation.  Lanes keep their
-//               column's running first-arg-max in registers (all phase 2 needs); lanes that reach
-//               the running row maximum are logged after a REDUX warp arg-max.
-//   resolve     the log is replayed to find each row's first arg-max column.
-//   greedy      warp 0 runs the T rounds on the cached row maxima; rows whose cached column was just
-//               taken by another row are re-swept together (same code, restricted to those rows and
-//               to live columns).
-//   scatter     phase-1 pairs overwrite the phase-2 outputs the sweep already stored.
+// How the work is organised (32 priors = one tile; with a prior index every tile holds priors of one
+// shape in a compact block, so the per-tile statistics give a tight bound):
+//   search   one WARP per ground-truth row.  The warp bounds, for every tile, the IoU any of its priors
+//            can reach (conservative float upper bound from the tile statistics), evaluates the tile
+//            with the highest bound first, then every tile whose bound still reaches
+//            min(thresh, running row maximum): only those can hold a positive or the row's arg-max.
+//            Evaluation is the exact float64 formula, lane = prior.  The row maximum / first arg-max
+//            column live in the warp's registers (no atomics, no log); pairs above the threshold are
+//            appended to a small per-image list.
+//   columns  the list is reduced to each prior's first-arg-max row (phase 2) with two rounds of
+//            atomics on a per-CTA scratch that is only ever touched at listed priors.
+//   greedy   warp 0 runs the T rounds on the cached row maxima (rows cached in registers); rows whose
+//            cached column was just taken by another row are searched again over the live columns.
+//   output   every prior is written once, coalesced in prior order: unmatched rows copy a precomputed
+//            encoding (prior index) or compute it, positives encode their ground truth; the phase-1
+//            pairs overwrite last.
 #include <math_constants.h>
 #include <algorithm>
 #include <map>
@@ -37,24 +37,31 @@
 namespace ssdg {
 
 #ifndef SSDG_MATCH_THREADS
-#define SSDG_MATCH_THREADS 512
+#define SSDG_MATCH_THREADS 256
 #endif
 #ifndef SSDG_MATCH_CTAS_PER_SM
-#define SSDG_MATCH_CTAS_PER_SM 2
+#define SSDG_MATCH_CTAS_PER_SM 4
 #endif
 constexpr int kMatchThreads = SSDG_MATCH_THREADS;
 constexpr int kMatchWarps = kMatchThreads / 32;
 constexpr int kMatchCtasPerSm = SSDG_MATCH_CTAS_PER_SM;
 constexpr int kMatchMaxCtas = 1024;
-constexpr int kLogCap = 16384;
+constexpr int kCandCap = 8192;          // listed (row, prior) pairs above the threshold per image
 constexpr int kABits = 21;
 constexpr int kMaxGT = 2048;
+constexpr int kTileSmemMax = 1024;      // tile statistics staged in shared memory up to this many tiles
+constexpr int kElimSmemWords = 4096;    // 16 KB: bitmaps in shared memory up to 131072 priors
 
 struct TileStat {
   float x1, y1, x2, y2;   // bounding box of the tile's priors, rounded outwards
   float wmax, hmax;       // largest corner-derived width / height (rounded up)
   float amin;             // smallest area (rounded down)
   u32 safe;               // 1: every prior of the tile is finite
+};
+
+struct Cand {
+  u64 key;
+  int a, t;
 };
 
 struct MatchParams {
@@ -69,14 +76,17 @@ struct MatchParams {
   float* out_loc;
   uint8_t* out_mask;
   int* out_match;
-  u32* ws_head;          // [0] next image, [1] status bits
-  u32* ws_log;           // per CTA kLogCap
-  u32* ws_elim;          // per CTA elim_words
-  const TileStat* tiles; // [ntiles]
-  const int* perm;       // [ntiles*32] slot -> prior index (-1: padding); NULL: identity
+  u32* ws_head;             // [0] next image, [1] status bits
+  Cand* ws_cand;            // per CTA kCandCap
+  u64* ws_colkey;           // per CTA A
+  int* ws_colt;             // per CTA A
+  u32* ws_bits;             // per CTA 2*elim_words (knocked-out columns, touched columns) when not in smem
+  const TileStat* tiles;    // [ntiles]
+  const int* perm;          // [ntiles*32] slot -> prior index (-1: padding); NULL: identity
+  const float4* unmatched;  // [A] encoding of an all-zero box per prior; NULL: compute
   int ntiles;
   int elim_words;
-  int elim_in_smem;      // the knocked-out-column bitmap fits in shared memory
+  int bits_in_smem;
 };
 
 template <typename TG, typename TP>
@@ -126,23 +136,25 @@ __device__ __forceinline__ float4 encode_row(float bx, float by, float bw, float
   return make_float4((float)tx, (float)ty, (float)log(rw), (float)log(rh));
 }
 
-// Conservative float upper bound of the IoU the exact path would compute, as a cross-multiplied
-// comparison:  returns true unless  iou < bound  is certain.  (x1,y1,x2,y2) / (ex_cap, ey_cap) bound the
-// intersection extents from above, a_lo bounds the areas from below; directed rounding throughout.
-// Any NaN makes the comparison fail, i.e. the pair is kept for the exact evaluation.
-__device__ __forceinline__ bool may_reach(float gx1, float gy1, float gx2, float gy2, float ga_lo, float px1,
-                                          float py1, float px2, float py2, float ex_cap, float ey_cap, float pa_lo,
-                                          float bound) {
-  float ex = fmaxf(__fsub_ru(fminf(gx2, px2), fmaxf(gx1, px1)), 1.0001e-10f);
-  float ey = fmaxf(__fsub_ru(fminf(gy2, py2), fmaxf(gy1, py1)), 1.0001e-10f);
-  ex = fminf(ex, ex_cap);
-  ey = fminf(ey, ey_cap);
-  const float iub = __fmul_ru(ex, ey);
-  const float dlb = __fadd_rd(__fsub_rd(__fadd_rd(ga_lo, pa_lo), iub), 0.9999e-10f);
-  return !(dlb > 0.f && iub * 1.0001f < bound * dlb);
+// Conservative float bound of the IoU the exact path would compute for a ground truth against any prior
+// of a tile: iub bounds the intersection from above, dlb the denominator from below (outward-rounded
+// corners, directed rounding).  A NaN anywhere leaves dlb NaN.
+__device__ __forceinline__ void iou_bound(const float4& g, float ga_lo, const TileStat& s, float& iub, float& dlb) {
+  float ex = fmaxf(__fsub_ru(fminf(g.z, s.x2), fmaxf(g.x, s.x1)), 1.0001e-10f);
+  float ey = fmaxf(__fsub_ru(fminf(g.w, s.y2), fmaxf(g.y, s.y1)), 1.0001e-10f);
+  ex = fminf(ex, s.wmax);
+  ey = fminf(ey, s.hmax);
+  iub = __fmul_ru(ex, ey);
+  dlb = __fadd_rd(__fsub_rd(__fadd_rd(ga_lo, s.amin), iub), 0.9999e-10f);
+}
+// true unless  iou < bound  is certain for every prior of the tile
+__device__ __forceinline__ bool may_reach(const float4& g, float ga_lo, const TileStat& s, float bound) {
+  float iub, dlb;
+  iou_bound(g, ga_lo, s, iub, dlb);
+  return !s.safe || !(dlb > 0.f && iub * 1.0001f < bound * dlb);
 }
 
-// ---- per-tile statistics of the priors (once per launch) ------------------------------------------------
+// ---- per-tile statistics of the priors ---------------------------------------------------------------------
 template <typename TP>
 __global__ void __launch_bounds__(256) tile_stats_kernel(const void* __restrict__ priors, int A, const int* __restrict__ perm,
                                                          int ntiles, TileStat* __restrict__ out) {
@@ -179,20 +191,31 @@ __global__ void __launch_bounds__(256) tile_stats_kernel(const void* __restrict_
   if (lane == 0) out[tile] = st;
 }
 
+// encoding of an all-zero (unmatched) box against every prior (utils/bbox.py:85,98-99)
+template <typename TP>
+__global__ void __launch_bounds__(256) unmatched_kernel(const void* __restrict__ priors, int A, float4* __restrict__ out) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A) return;
+  TP dx, dy, dw, dh;
+  Vec4<TP>::load(priors, a, dx, dy, dw, dh);
+  out[a] = encode_row<TP>(0.f, 0.f, 0.f, 0.f, dx, dy, dw, dh);
+}
+
 template <typename TG, typename TP>
 struct MatchSmem {
   typedef typename Promote<TG, TP>::type R;
   R *gx1, *gy1, *gx2, *gy2, *ga;     // ground-truth corners / area in the result dtype
   float4* cbox;                      // outward-rounded float box of the ground truth
-  float2* glo;                       // .x float lower bound of the area (NaN: never cull), .y of the running row maximum
-  u64* rowkey;                       // running / cached row maximum (key64) over live columns
+  float* galo;                       // float lower bound of the area (NaN: never cull)
+  u64* rowkey;                       // cached row maximum (key64) over live columns
   int* rowcol;                       // first arg-max column of rowkey
   int *pair_t, *pair_a, *rs_list;
   uint8_t* dead;
-  u64* red_key;                      // [kMatchWarps]
-  int* red_idx;                      // [kMatchWarps]
+  int* red_idx;
   int* ctl;                          // control words, see enum
-  __device__ void carve(unsigned char* base, int tm) {
+  TileStat* tiles_s;                 // staged tile statistics (when they fit)
+  u32 *elim_s, *touch_s;             // bitmaps (when they fit)
+  __device__ void carve(unsigned char* base, int tm, int ntiles_s, int bit_words) {
     size_t o = 0;
     gx1 = (R*)(base + o); o += sizeof(R) * tm;
     gy1 = (R*)(base + o); o += sizeof(R) * tm;
@@ -201,85 +224,62 @@ struct MatchSmem {
     ga = (R*)(base + o); o += sizeof(R) * tm;
     o = (o + 15) & ~(size_t)15;
     cbox = (float4*)(base + o); o += 16 * (size_t)tm;
+    tiles_s = (TileStat*)(base + o); o += sizeof(TileStat) * (size_t)ntiles_s;
     rowkey = (u64*)(base + o); o += 8 * (size_t)tm;
-    glo = (float2*)(base + o); o += 8 * (size_t)tm;
-    red_key = (u64*)(base + o); o += 8 * kMatchWarps;
+    galo = (float*)(base + o); o += 4 * (size_t)tm;
     rowcol = (int*)(base + o); o += 4 * (size_t)tm;
     pair_t = (int*)(base + o); o += 4 * (size_t)tm;
     pair_a = (int*)(base + o); o += 4 * (size_t)tm;
     rs_list = (int*)(base + o); o += 4 * (size_t)tm;
-    red_idx = (int*)(base + o); o += 4 * kMatchWarps;
+    red_idx = (int*)(base + o); o += 4 * 4;
     ctl = (int*)(base + o); o += 4 * 16;
-    dead = (uint8_t*)(base + o); o += (size_t)tm;
-    o = (o + 15) & ~(size_t)15;
-    elim_s = (u32*)(base + o);
+    elim_s = (u32*)(base + o); o += 4 * (size_t)bit_words;
+    touch_s = (u32*)(base + o); o += 4 * (size_t)bit_words;
+    dead = (uint8_t*)(base + o);
   }
-  u32* elim_s;                       // [elim_words] when it fits, else the bitmap lives in the workspace
 };
-constexpr int kElimSmemWords = 4096;   // 16 KB: up to 131072 priors
-static size_t match_smem_bytes(int tm, int elim_words) {
-  return (size_t)tm * (5 * 8 + 16 + 8 + 8 + 16 + 1) + 12 * kMatchWarps + 64 + 96 +
-         (elim_words <= kElimSmemWords ? (size_t)elim_words * 4 : 0);
+static size_t match_smem_bytes(int tm, int ntiles_s, int bit_words) {
+  return (size_t)tm * (5 * 8 + 16 + 8 + 4 + 16 + 1) + (size_t)ntiles_s * sizeof(TileStat) + (size_t)bit_words * 8 + 16 + 64 + 96;
 }
 
-enum { C_IMG = 0, C_LOGN, C_NRS, C_DONE, C_ROUND, C_DEGEN, C_MINELIM, C_OVERFLOW };
+enum { C_IMG = 0, C_NCAND, C_NRS, C_DONE, C_ROUND, C_DEGEN, C_MINELIM };
 
 template <typename TG, typename TP>
 __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(MatchParams P) {
   typedef typename Promote<TG, TP>::type R;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   MatchSmem<TG, TP> S;
-  S.carve(smem_raw, P.tm);
+  const bool tiles_in_smem = P.ntiles <= kTileSmemMax;
+  S.carve(smem_raw, P.tm, tiles_in_smem ? P.ntiles : 0, P.bits_in_smem ? P.elim_words : 0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int A = P.A;
   const int ntiles = P.ntiles;
   const R EPS = (R)1e-10;
-  u32* log = P.ws_log + (size_t)blockIdx.x * kLogCap;
-  // the greedy rounds read-modify-write this bitmap serially: keep it in shared memory when it fits
-  u32* elim = P.elim_in_smem ? S.elim_s : P.ws_elim + (size_t)blockIdx.x * P.elim_words;
+  const TileStat* tiles = tiles_in_smem ? S.tiles_s : P.tiles;
+  u32* elim = P.bits_in_smem ? S.elim_s : P.ws_bits + (size_t)blockIdx.x * 2 * P.elim_words;
+  u32* touch = P.bits_in_smem ? S.touch_s : elim + P.elim_words;
+  Cand* cand = P.ws_cand + (size_t)blockIdx.x * kCandCap;
+  u64* colkey = P.ws_colkey + (size_t)blockIdx.x * A;
+  int* colt = P.ws_colt + (size_t)blockIdx.x * A;
   const u64 thr_key = key64((double)(R)P.thresh);
   const float thr_lo = f_down((double)(R)P.thresh);
 
-  auto load_prior = [&](int a, Corners<R>& p, bool& safe, TP& dx, TP& dy, TP& dw, TP& dh) {
+  // once per CTA: stage the tile statistics, clear the column scratch
+  if (tiles_in_smem)
+    for (int i = tid; i < ntiles; i += kMatchThreads) S.tiles_s[i] = P.tiles[i];
+  for (int a = tid; a < A; a += kMatchThreads) { colkey[a] = 0ull; colt[a] = 0x7fffffff; }
+
+  auto load_prior = [&](int a, Corners<R>& p, TP& dx, TP& dy, TP& dw, TP& dh) {
     Vec4<TP>::load(P.priors, a, dx, dy, dw, dh);
     Corners<TP> c = corners_of<TP>(dx, dy, dw, dh);
     p.x1 = (R)c.x1; p.y1 = (R)c.y1; p.x2 = (R)c.x2; p.y2 = (R)c.y2; p.area = (R)c.area;
-    safe = finite4((double)p.x1, (double)p.y1, (double)p.x2, (double)p.y2) && isfinite((double)p.area);
   };
   auto load_gt = [&](int t) {
     Corners<R> g;
     g.x1 = S.gx1[t]; g.y1 = S.gy1[t]; g.x2 = S.gx2[t]; g.y2 = S.gy2[t]; g.area = S.ga[t];
     return g;
   };
-  auto elim_test = [&](int a) { return (elim[a >> 5] >> (a & 31)) & 1u; };
-  auto load_glo = [&](int t) {   // one 8-byte volatile load
-    const u64 raw = *reinterpret_cast<volatile u64*>(&S.glo[t]);
-    return make_float2(__uint_as_float((u32)raw), __uint_as_float((u32)(raw >> 32)));
-  };
-
-  // Exhaustive exact scan of row t over the live columns (fallback when the log overflowed).
-  auto scan_row_exact = [&](int t) {
-    Corners<R> g = load_gt(t);
-    u64 bk = 0;
-    int ba = 0x7fffffff;
-    for (int a = tid; a < A; a += kMatchThreads) {
-      if (elim_test(a)) continue;
-      Corners<R> p; bool safe; TP dx, dy, dw, dh;
-      load_prior(a, p, safe, dx, dy, dw, dh);
-      u64 k = key64((double)iou_corners<R>(g, p, EPS));
-      if (k > bk) { bk = k; ba = a; }
-    }
-    warp_argmax_u64(bk, ba);
-    if (lane == 0) { S.red_key[warp] = bk; S.red_idx[warp] = ba; }
-    __syncthreads();
-    if (warp == 0) {
-      u64 k = lane < kMatchWarps ? S.red_key[lane] : 0ull;
-      int i = lane < kMatchWarps ? S.red_idx[lane] : 0x7fffffff;
-      warp_argmax_u64(k, i);
-      if (lane == 0) { S.rowkey[t] = k; S.rowcol[t] = i; }
-    }
-    __syncthreads();
-  };
+  auto bit_test = [&](const u32* bm, int a) { return (bm[a >> 5] >> (a & 31)) & 1u; };
 
   for (;;) {
     __syncthreads();
@@ -305,131 +305,128 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
       S.gx1[t] = x1; S.gy1[t] = y1; S.gx2[t] = x2; S.gy2[t] = y2; S.ga[t] = ar;
       const bool ok = finite4((double)x1, (double)y1, (double)x2, (double)y2) && isfinite((double)ar);
       S.cbox[t] = make_float4(f_down((double)x1), f_down((double)y1), f_up((double)x2), f_up((double)y2));
-      S.glo[t] = make_float2(ok ? f_down((double)ar) : CUDART_NAN_F, 0.f);
+      S.galo[t] = ok ? f_down((double)ar) : CUDART_NAN_F;
       S.rowkey[t] = 0ull;
       S.rowcol[t] = 0x7fffffff;
       S.dead[t] = 0;
     }
-    for (int w = tid; w < P.elim_words; w += kMatchThreads) elim[w] = 0u;
+    for (int w = tid; w < P.elim_words; w += kMatchThreads) { elim[w] = 0u; touch[w] = 0u; }
     if (tid == 0) {
-      S.ctl[C_LOGN] = 0; S.ctl[C_NRS] = 0; S.ctl[C_DONE] = 0; S.ctl[C_ROUND] = 0; S.ctl[C_DEGEN] = 0;
-      S.ctl[C_MINELIM] = 0x7fffffff; S.ctl[C_OVERFLOW] = 0;
+      S.ctl[C_NCAND] = 0; S.ctl[C_NRS] = 0; S.ctl[C_DONE] = 0; S.ctl[C_ROUND] = 0; S.ctl[C_DEGEN] = 0;
+      S.ctl[C_MINELIM] = 0x7fffffff;
     }
     __syncthreads();
 
-    // ---- sweep: all rows (first pass, also emits the phase-2 outputs) or the rows in rs_list ----------
-    auto sweep = [&](const bool subset) {
+    // ---- search: one warp per row; `subset`: only the rows in rs_list, over the live columns ---------
+    auto search = [&](const bool subset) {
       const int nrow = subset ? S.ctl[C_NRS] : T;
-      for (int tile = ntiles - 1 - warp; tile >= 0; tile -= kMatchWarps) {
-        const TileStat ts = P.tiles[tile];
-        const int slot = (tile << 5) + lane;
-        const int a = P.perm ? __ldg(P.perm + slot) : slot;
-        bool valid = a >= 0 && a < A;
-        bool loaded = false, safe = true;
-        Corners<R> p;
-        TP dx = 0, dy = 0, dw = 1, dh = 1;
-        float ax1 = 0.f, ay1 = 0.f, ax2 = 0.f, ay2 = 0.f, aw = 0.f, ah = 0.f, aalo = 0.f;
-        p.x1 = p.y1 = p.x2 = p.y2 = p.area = (R)0;
-        auto load_lane = [&]() {
-          if (subset && valid && elim_test(a)) valid = false;
+      for (int k = warp; k < nrow; k += kMatchWarps) {
+        const int t = subset ? S.rs_list[k] : k;
+        const Corners<R> g = load_gt(t);
+        const float4 gb = S.cbox[t];
+        const float galo = S.galo[t];
+        u64 best_key = 0ull;
+        int best_a = 0x7fffffff;
+        float rowlo = 0.f;
+        // exact evaluation of one tile for this row (all lanes)
+        auto evaluate = [&](int tile) {
+          const int slot = (tile << 5) + lane;
+          const int a = P.perm ? __ldg(P.perm + slot) : slot;
+          bool valid = a >= 0 && a < A;
+          if (subset && valid && bit_test(elim, a)) valid = false;
+          u64 key = 0ull;
           if (valid) {
-            load_prior(a, p, safe, dx, dy, dw, dh);
-            ax1 = f_down((double)p.x1); ay1 = f_down((double)p.y1);
-            ax2 = f_up((double)p.x2); ay2 = f_up((double)p.y2);
-            aw = fmaxf(__fsub_ru(ax2, ax1), 1.0001e-10f); ah = fmaxf(__fsub_ru(ay2, ay1), 1.0001e-10f);
-            aalo = f_down((double)p.area);
-          }
-          loaded = true;
-        };
-        if (!subset) load_lane();
-        u64 ckey = 0ull;
-        int ct = -1;
-        for (int k0 = 0; k0 < nrow; k0 += 32) {
-          const int k = k0 + lane;
-          bool reach = false;
-          if (k < nrow) {
-            const int t = subset ? S.rs_list[k] : k;
-            const float4 gb = S.cbox[t];
-            const float2 gl = load_glo(t);
-            reach = !ts.safe || may_reach(gb.x, gb.y, gb.z, gb.w, gl.x, ts.x1, ts.y1, ts.x2, ts.y2, ts.wmax, ts.hmax,
-                                          ts.amin, fminf(thr_lo, gl.y));
-          }
-          u32 m = __ballot_sync(SSDG_FULL, reach);
-          if (m && !loaded) load_lane();
-          while (m) {
-            const int kk = k0 + __ffs(m) - 1;
-            m &= m - 1;
-            const int t = subset ? S.rs_list[kk] : kk;
-            Corners<R> g = load_gt(t);
-            u64 key = valid ? key64((double)iou_corners<R>(g, p, EPS)) : 0ull;
-            if (key > ckey) { ckey = key; ct = t; }
-            const u64 rk = *reinterpret_cast<volatile u64*>(&S.rowkey[t]);
-            const bool pass = valid && key >= rk;
-            if (__any_sync(SSDG_FULL, pass)) {
-              const u64 wmax = warp_max_u64(pass ? key : 0ull);
-              const bool top = pass && key == wmax;
-              const u32 tmask = __ballot_sync(SSDG_FULL, top);
-              const int leader = __ffs(tmask) - 1;
-              int base = 0;
-              if (lane == leader) {
-                base = atomicAdd(&S.ctl[C_LOGN], __popc(tmask));
-                atomicMax(&S.rowkey[t], wmax);
-                const float lo = fmaxf(f_down(unkey64(wmax)), 0.f);
-                atomicMax(reinterpret_cast<int*>(&S.glo[t].y), __float_as_int(lo));
-              }
-              base = __shfl_sync(SSDG_FULL, base, leader);
-              if (top) {
-                int pos = base + __popc(tmask & ((1u << lane) - 1u));
-                if (pos < kLogCap) log[pos] = ((u32)t << kABits) | (u32)a;
-                else S.ctl[C_OVERFLOW] = 1;
-              }
+            Corners<R> p; TP dx, dy, dw, dh;
+            load_prior(a, p, dx, dy, dw, dh);
+            key = key64((double)iou_corners<R>(g, p, EPS));
+            if (!subset && key > thr_key) {   // phase-2 candidate
+              const int pos = atomicAdd(&S.ctl[C_NCAND], 1);
+              if (pos < kCandCap) { Cand c; c.key = key; c.a = a; c.t = t; cand[pos] = c; }
             }
           }
-        }
-        // phase-2 result for this prior (phase-1 priors are overwritten after the greedy rounds)
-        if (!subset && valid) {
-          const bool pos = ckey > thr_key;
-          float bx = 0.f, by = 0.f, bw = 0.f, bh = 0.f;
-          int lab = 0;
-          if (pos) {
-            TG gx, gy, gw, gh;
-            Vec4<TG>::load(P.gt_boxes, g0 + ct, gx, gy, gw, gh);
-            bx = (float)gx; by = (float)gy; bw = (float)gw; bh = (float)gh;
-            lab = (int)__ldg(P.gt_cls + g0 + ct);
+          u64 wk = key;
+          int wa = valid ? a : 0x7fffffff;
+          warp_argmax_u64(wk, wa);
+          if (wk > best_key || (wk == best_key && wa < best_a)) {
+            best_key = wk; best_a = wa;
+            rowlo = fmaxf(f_down(unkey64(wk)), 0.f);
           }
-          if (P.out_cls) P.out_cls[obase + a] = lab;
-          if (P.out_mask) P.out_mask[obase + a] = pos ? 1 : 0;
-          if (P.out_match) P.out_match[obase + a] = pos ? ct : -1;
-          if (P.out_box) reinterpret_cast<float4*>(P.out_box)[obase + a] = make_float4(bx, by, bw, bh);
-          if (P.out_loc) reinterpret_cast<float4*>(P.out_loc)[obase + a] = encode_row<TP>(bx, by, bw, bh, dx, dy, dw, dh);
+        };
+        // pass 1: the tile with the highest bound seeds the running maximum
+        float sub = -1.f;
+        int stile = 0x7fffffff;
+        for (int tb = 0; tb < ntiles; tb += 32) {
+          const int tile = tb + lane;
+          if (tile < ntiles) {
+            const TileStat ts = tiles[tile];
+            float iub, dlb;
+            iou_bound(gb, galo, ts, iub, dlb);
+            const float ub = (ts.safe && dlb > 0.f) ? __fdividef(iub, dlb) : CUDART_INF_F;
+            if (ub > sub) { sub = ub; stile = tile; }
+          }
         }
-      }
-      __syncthreads();
-      // resolve the row arg-max columns from the log (the smallest logged column that attains the maximum)
-      const bool overflow = S.ctl[C_OVERFLOW] != 0;
-      if (!overflow) {
-        const int n = S.ctl[C_LOGN];
-        for (int e = tid; e < n; e += kMatchThreads) {
-          const u32 v = log[e];
-          const int t = (int)(v >> kABits), a = (int)(v & ((1u << kABits) - 1u));
-          Corners<R> p; bool safe; TP dx, dy, dw, dh;
-          load_prior(a, p, safe, dx, dy, dw, dh);
-          Corners<R> g = load_gt(t);
-          if (key64((double)iou_corners<R>(g, p, EPS)) == S.rowkey[t]) atomicMin(&S.rowcol[t], a);
+        {
+          const u32 m = __reduce_max_sync(SSDG_FULL, key32(sub));
+          stile = (int)__reduce_min_sync(SSDG_FULL, key32(sub) == m ? (u32)stile : 0x7fffffffu);
         }
-        __syncthreads();
-      } else {
-        if (tid == 0) atomicOr(&P.ws_head[1], 4u);
-        for (int k = 0; k < nrow; ++k) scan_row_exact(subset ? S.rs_list[k] : k);
+        evaluate(stile);
+        // pass 2: every other tile whose bound still reaches min(thresh, running maximum)
+        for (int tb = 0; tb < ntiles; tb += 32) {
+          const int tile = tb + lane;
+          bool pending = tile < ntiles && tile != stile;
+          TileStat ts;
+          ts.x1 = ts.y1 = ts.x2 = ts.y2 = ts.wmax = ts.hmax = ts.amin = 0.f; ts.safe = 1u;
+          if (pending) ts = tiles[tile];
+          for (;;) {
+            const bool reach = pending && may_reach(gb, galo, ts, fminf(thr_lo, rowlo));
+            const u32 m = __ballot_sync(SSDG_FULL, reach);
+            if (!m) break;
+            const int l = __ffs(m) - 1;
+            if (lane == l) pending = false;
+            evaluate(tb + l);
+          }
+        }
+        if (lane == 0) { S.rowkey[t] = best_key; S.rowcol[t] = best_a; }
       }
-      if (tid == 0) { S.ctl[C_LOGN] = 0; S.ctl[C_OVERFLOW] = 0; }
-      __syncthreads();
     };
 
-    sweep(false);
-    if (T == 0) continue;
+    search(false);
+    __syncthreads();
+
+    // ---- phase 2: first-arg-max row of every listed prior ---------------------------------------------
+    const int ncand_raw = S.ctl[C_NCAND];
+    const bool cand_overflow = ncand_raw > kCandCap;
+    const int ncand = cand_overflow ? 0 : ncand_raw;
+    if (cand_overflow) {
+      // more pairs above the threshold than the list holds: exhaustive exact scan, one prior per thread
+      if (tid == 0) atomicOr(&P.ws_head[1], 4u);
+      for (int a = tid; a < A; a += kMatchThreads) {
+        Corners<R> p; TP dx, dy, dw, dh;
+        load_prior(a, p, dx, dy, dw, dh);
+        u64 bk = 0ull;
+        int bt = 0x7fffffff;
+        for (int t = 0; t < T; ++t) {
+          const u64 k = key64((double)iou_corners<R>(load_gt(t), p, EPS));
+          if (k > bk) { bk = k; bt = t; }
+        }
+        if (bk > thr_key) { colkey[a] = bk; colt[a] = bt; atomicOr(&touch[a >> 5], 1u << (a & 31)); }
+      }
+    } else {
+      for (int e = tid; e < ncand; e += kMatchThreads) {
+        const Cand c = cand[e];
+        atomicMax(&colkey[c.a], c.key);
+        atomicOr(&touch[c.a >> 5], 1u << (c.a & 31));
+      }
+      __syncthreads();
+      for (int e = tid; e < ncand; e += kMatchThreads) {
+        const Cand c = cand[e];
+        if (c.key == colkey[c.a]) atomicMin(&colt[c.a], c.t);
+      }
+    }
+    __syncthreads();
 
     // ---- greedy rounds (utils/bbox.py:62-68) --------------------------------------------------------
+    if (T > 0)
     for (;;) {
       if (warp == 0 && T <= 128) {
         // Fast path: the (<= 4) rows a lane owns are cached in registers, so a round is a handful of
@@ -483,7 +480,7 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
             wt = S.red_idx[0];
             wa = S.red_idx[1];
           }
-          const bool fresh = !elim_test(wa);
+          const bool fresh = !bit_test(elim, wa);
           __syncwarp();
           if (lane == 0) {
             S.pair_t[round] = wt;
@@ -502,13 +499,7 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
             for (int r = 0; r < 4; ++r) {
               const bool need = rk[r] != 0ull && rc[r] == wa;
               const u32 nm = __ballot_sync(SSDG_FULL, need);
-              if (need) {
-                const int t = lane + 32 * r;
-                S.rs_list[nrs + __popc(nm & ((1u << lane) - 1u))] = t;
-                S.rowkey[t] = 0ull;
-                S.rowcol[t] = 0x7fffffff;
-                S.glo[t].y = 0.f;
-              }
+              if (need) S.rs_list[nrs + __popc(nm & ((1u << lane) - 1u))] = lane + 32 * r;
               nrs += __popc(nm);
             }
           }
@@ -533,7 +524,6 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
             wt = bt;
             wa = S.rowcol[bt];
           } else {
-            // Knocked-out entries (0.0) tie with or beat every live entry: full rule, first flat index.
             if (lane == 0) {
               u64 best = 0ull;
               long long bflat = 0x7fffffffffffffffll;
@@ -556,7 +546,7 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
             wt = S.red_idx[0];
             wa = S.red_idx[1];
           }
-          const bool fresh = !elim_test(wa);
+          const bool fresh = !bit_test(elim, wa);
           __syncwarp();
           if (lane == 0) {
             S.pair_t[round] = wt;
@@ -572,12 +562,7 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
               const int t = t0 + lane;
               const bool need = t < T && !S.dead[t] && S.rowcol[t] == wa;
               const u32 nm = __ballot_sync(SSDG_FULL, need);
-              if (need) {
-                S.rs_list[nrs + __popc(nm & ((1u << lane) - 1u))] = t;
-                S.rowkey[t] = 0ull;
-                S.rowcol[t] = 0x7fffffff;
-                S.glo[t].y = 0.f;
-              }
+              if (need) S.rs_list[nrs + __popc(nm & ((1u << lane) - 1u))] = t;
               nrs += __popc(nm);
             }
           }
@@ -589,13 +574,44 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
       const int nrs = S.ctl[C_NRS];
       const bool done = S.ctl[C_DONE] != 0;
       if (done && nrs == 0) break;
-      if (nrs > 0) sweep(true);
+      if (nrs > 0) search(true);
+      __syncthreads();
       if (tid == 0) S.ctl[C_NRS] = 0;
       __syncthreads();
       if (done) break;
     }
 
-    // ---- scatter the phase-1 pairs (utils/bbox.py:87-90; later pairs win) ----------------------------
+    // ---- output: every prior once, in prior order (phase 2), then the phase-1 pairs ---------------------
+    for (int a = tid; a < A; a += kMatchThreads) {
+      const bool pos = bit_test(touch, a) != 0;
+      float bx = 0.f, by = 0.f, bw = 0.f, bh = 0.f;
+      int lab = 0, ct = -1;
+      if (pos) {
+        ct = colt[a];
+        TG gx, gy, gw, gh;
+        Vec4<TG>::load(P.gt_boxes, g0 + ct, gx, gy, gw, gh);
+        bx = (float)gx; by = (float)gy; bw = (float)gw; bh = (float)gh;
+        lab = (int)__ldg(P.gt_cls + g0 + ct);
+        colkey[a] = 0ull; colt[a] = 0x7fffffff;     // leave the scratch clean for the next image
+      }
+      if (P.out_cls) P.out_cls[obase + a] = lab;
+      if (P.out_mask) P.out_mask[obase + a] = pos ? 1 : 0;
+      if (P.out_match) P.out_match[obase + a] = ct;
+      if (P.out_box) reinterpret_cast<float4*>(P.out_box)[obase + a] = make_float4(bx, by, bw, bh);
+      if (P.out_loc) {
+        float4 enc;
+        if (!pos && P.unmatched) {
+          enc = __ldg(P.unmatched + a);
+        } else {
+          TP dx, dy, dw, dh;
+          Vec4<TP>::load(P.priors, a, dx, dy, dw, dh);
+          enc = encode_row<TP>(bx, by, bw, bh, dx, dy, dw, dh);
+        }
+        reinterpret_cast<float4*>(P.out_loc)[obase + a] = enc;
+      }
+    }
+    __syncthreads();
+    // phase-1 pairs (utils/bbox.py:87-90; later pairs win)
     const bool degen = S.ctl[C_DEGEN] != 0;
     for (int k = tid; k < T; k += kMatchThreads) {
       const int t = S.pair_t[k], a = S.pair_a[k];
@@ -636,6 +652,7 @@ static int launch_match(const MatchParams& P, int grid, size_t smem, cudaStream_
   return SSDG_OK;
 }
 
+static int match_ws_ctas(int batch) { return batch < kMatchMaxCtas ? batch : kMatchMaxCtas; }
 static int match_grid(int batch) {
   int g = sm_count() * kMatchCtasPerSm;
   if (g > kMatchMaxCtas) g = kMatchMaxCtas;
@@ -644,21 +661,27 @@ static int match_grid(int batch) {
 
 struct MatchWs {
   u32* head;
-  u32* log;
-  u32* elim;
+  Cand* cand;
+  u64* colkey;
+  int* colt;
+  u32* bits;
   TileStat* tiles;
 };
-static size_t match_ws_layout(int n_priors, MatchWs* out, unsigned char* base) {
+static size_t match_ws_layout(int n_priors, int ctas, MatchWs* out, unsigned char* base) {
   size_t o = 0;
-  const size_t elim_words = ((size_t)n_priors + 31) / 32;
+  const size_t words = ((size_t)n_priors + 31) / 32;
   if (out) out->head = (u32*)(base + o);
   o += 256;
-  if (out) out->log = (u32*)(base + o);
-  o += (size_t)kMatchMaxCtas * kLogCap * 4;
-  if (out) out->elim = (u32*)(base + o);
-  o += align_up((size_t)kMatchMaxCtas * elim_words * 4, 256);
+  if (out) out->cand = (Cand*)(base + o);
+  o += align_up((size_t)ctas * kCandCap * sizeof(Cand), 256);
+  if (out) out->colkey = (u64*)(base + o);
+  o += align_up((size_t)ctas * n_priors * 8, 256);
+  if (out) out->colt = (int*)(base + o);
+  o += align_up((size_t)ctas * n_priors * 4, 256);
+  if (out) out->bits = (u32*)(base + o);
+  o += align_up((size_t)ctas * 2 * words * 4, 256);
   if (out) out->tiles = (TileStat*)(base + o);
-  o += align_up(elim_words * sizeof(TileStat), 256);
+  o += align_up(words * sizeof(TileStat), 256);
   return o;
 }
 
@@ -671,6 +694,9 @@ static std::unordered_map<const void*, IndexInfo> g_index;   // device pointer -
 static size_t index_slots(int n_priors) { return ((size_t)n_priors + 31) / 32 * 32 + (size_t)kIndexMaxShapes * 32; }
 static size_t index_perm_offset() { return 256; }
 static size_t index_tiles_offset(int n_priors) { return 256 + align_up(index_slots(n_priors) * 4, 256); }
+static size_t index_unmatched_offset(int n_priors) {
+  return index_tiles_offset(n_priors) + align_up(index_slots(n_priors) / 32 * sizeof(TileStat), 256);
+}
 
 }  // namespace ssdg
 
@@ -678,7 +704,7 @@ using namespace ssdg;
 
 extern "C" size_t ssdg_prior_index_bytes(int32_t n_priors) {
   if (n_priors <= 0) return 0;
-  return index_tiles_offset(n_priors) + align_up(index_slots(n_priors) / 32 * sizeof(TileStat), 256);
+  return index_unmatched_offset(n_priors) + align_up((size_t)n_priors * 16, 256);
 }
 
 extern "C" int ssdg_prior_index_build(const void* priors, int32_t prior_dtype, int32_t n_priors, void* index,
@@ -746,11 +772,15 @@ extern "C" int ssdg_prior_index_build(const void* priors, int32_t prior_dtype, i
   SSDG_CUDA_TRY(cudaMemcpyAsync(base, header, sizeof(header), cudaMemcpyHostToDevice, st));
   SSDG_CUDA_TRY(cudaMemcpyAsync(base + index_perm_offset(), perm.data(), perm.size() * 4, cudaMemcpyHostToDevice, st));
   TileStat* tiles = (TileStat*)(base + index_tiles_offset(n_priors));
+  float4* unmatched = (float4*)(base + index_unmatched_offset(n_priors));
   const int* dperm = (const int*)(base + index_perm_offset());
-  if (prior_dtype == SSDG_F64)
+  if (prior_dtype == SSDG_F64) {
     tile_stats_kernel<double><<<(ntiles * 32 + 255) / 256, 256, 0, st>>>(priors, n_priors, dperm, ntiles, tiles);
-  else
+    unmatched_kernel<double><<<(n_priors + 255) / 256, 256, 0, st>>>(priors, n_priors, unmatched);
+  } else {
     tile_stats_kernel<float><<<(ntiles * 32 + 255) / 256, 256, 0, st>>>(priors, n_priors, dperm, ntiles, tiles);
+    unmatched_kernel<float><<<(n_priors + 255) / 256, 256, 0, st>>>(priors, n_priors, unmatched);
+  }
   SSDG_LAUNCH_CHECK();
   SSDG_CUDA_TRY(cudaStreamSynchronize(st));
   std::lock_guard<std::mutex> lk(g_index_mu);
@@ -761,7 +791,7 @@ extern "C" int ssdg_prior_index_build(const void* priors, int32_t prior_dtype, i
 extern "C" size_t ssdg_match_workspace_bytes(int32_t batch, int32_t n_priors, int32_t max_gt) {
   (void)max_gt;
   if (batch <= 0 || n_priors <= 0) return 0;
-  return match_ws_layout(n_priors, nullptr, nullptr);
+  return match_ws_layout(n_priors, match_ws_ctas(batch), nullptr, nullptr);
 }
 
 extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const float* gt_cls,
@@ -781,7 +811,7 @@ extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const f
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = match_grid(batch);
   MatchWs ws;
-  match_ws_layout(n_priors, &ws, (unsigned char*)workspace);
+  match_ws_layout(n_priors, match_ws_ctas(batch), &ws, (unsigned char*)workspace);
   MatchParams P;
   P.gt_boxes = gt_boxes; P.gt_cls = gt_cls; P.gt_off = gt_offsets; P.priors = priors;
   P.B = batch; P.A = n_priors; P.max_gt = max_gt; P.tm = ((max_gt + 31) / 32) * 32;
@@ -789,8 +819,8 @@ extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const f
   P.thresh = thresh;
   P.out_cls = out_cls; P.out_box = out_box; P.out_loc = out_loc; P.out_mask = out_mask; P.out_match = out_match;
   P.elim_words = (n_priors + 31) / 32;
-  P.ws_head = ws.head; P.ws_log = ws.log; P.ws_elim = ws.elim; P.tiles = ws.tiles;
-  P.perm = nullptr; P.ntiles = (n_priors + 31) / 32;
+  P.ws_head = ws.head; P.ws_cand = ws.cand; P.ws_colkey = ws.colkey; P.ws_colt = ws.colt; P.ws_bits = ws.bits;
+  P.tiles = ws.tiles; P.perm = nullptr; P.unmatched = nullptr; P.ntiles = (n_priors + 31) / 32;
   if (prior_index) {
     IndexInfo info;
     {
@@ -803,11 +833,12 @@ extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const f
     const unsigned char* ib = (const unsigned char*)prior_index;
     P.perm = (const int*)(ib + index_perm_offset());
     P.tiles = (const TileStat*)(ib + index_tiles_offset(n_priors));
+    P.unmatched = (const float4*)(ib + index_unmatched_offset(n_priors));
     P.ntiles = info.ntiles;
   }
   SSDG_CUDA_TRY(cudaMemsetAsync(P.ws_head, 0, 256, st));
-  P.elim_in_smem = P.elim_words <= kElimSmemWords ? 1 : 0;
-  size_t smem = match_smem_bytes(P.tm, P.elim_words);
+  P.bits_in_smem = P.elim_words <= kElimSmemWords ? 1 : 0;
+  const size_t smem = match_smem_bytes(P.tm, P.ntiles <= kTileSmemMax ? P.ntiles : 0, P.bits_in_smem ? P.elim_words : 0);
   if ((int)smem > max_smem_optin()) return SSDG_ERR_LIMIT;
   if (gt_dtype == SSDG_F32 && prior_dtype == SSDG_F64) return launch_match<float, double>(P, grid, smem, st);
   if (gt_dtype == SSDG_F32 && prior_dtype == SSDG_F32) return launch_match<float, float>(P, grid, smem, st);
