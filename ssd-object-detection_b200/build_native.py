@@ -23,6 +23,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
           "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+COMMON += os.environ.get("SSDG_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DSSDG_MATCH_TIMING for phase clocks
 UNITS = {
     "api.cu": [],
     "geom.cu": ["-fmad=false"],

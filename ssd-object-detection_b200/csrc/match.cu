@@ -37,13 +37,12 @@
 namespace ssdg {
 
 #ifndef SSDG_MATCH_THREADS
-#define SSDG_MATCH_THREADS 256
+#define SSDG_MATCH_THREADS 512
 #endif
 #ifndef SSDG_MATCH_CTAS_PER_SM
-#define SSDG_MATCH_CTAS_PER_SM 4
+#define SSDG_MATCH_CTAS_PER_SM 2
 #endif
 constexpr int kMatchThreads = SSDG_MATCH_THREADS;
-constexpr int kMatchWarps = kMatchThreads / 32;
 constexpr int kMatchCtasPerSm = SSDG_MATCH_CTAS_PER_SM;
 constexpr int kMatchMaxCtas = 1024;
 constexpr int kCandCap = 8192;          // listed (row, prior) pairs above the threshold per image
@@ -57,6 +56,7 @@ struct TileStat {
   float wmax, hmax;       // largest corner-derived width / height (rounded up)
   float amin;             // smallest area (rounded down)
   u32 safe;               // 1: every prior of the tile is finite
+  float cx1, cy1, cx2, cy2;   // range of the priors' corner mid-points (rounded outwards)
 };
 
 struct Cand {
@@ -83,6 +83,7 @@ struct MatchParams {
   u32* ws_bits;             // per CTA 2*elim_words (knocked-out columns, touched columns) when not in smem
   const TileStat* tiles;    // [ntiles]
   const int* perm;          // [ntiles*32] slot -> prior index (-1: padding); NULL: identity
+  const void* pprior;       // [ntiles*32,4] the priors in slot order (same dtype); NULL: gather through perm
   const float4* unmatched;  // [A] encoding of an all-zero box per prior; NULL: compute
   int ntiles;
   int elim_words;
@@ -142,8 +143,13 @@ __device__ __forceinline__ float4 encode_row(float bx, float by, float bw, float
 __device__ __forceinline__ void iou_bound(const float4& g, float ga_lo, const TileStat& s, float& iub, float& dlb) {
   float ex = fmaxf(__fsub_ru(fminf(g.z, s.x2), fmaxf(g.x, s.x1)), 1.0001e-10f);
   float ey = fmaxf(__fsub_ru(fminf(g.w, s.y2), fmaxf(g.y, s.y1)), 1.0001e-10f);
-  ex = fminf(ex, s.wmax);
-  ey = fminf(ey, s.hmax);
+  // a prior with mid-point c and half-extent h overlaps the ground truth by at most  g.hi - (c - h)  and
+  // (c + h) - g.lo:  bound both with the tile's mid-point range
+  const float hw = s.wmax * 0.50001f, hh = s.hmax * 0.50001f;
+  ex = fminf(ex, fminf(__fadd_ru(__fsub_ru(g.z, s.cx1), hw), __fsub_ru(__fadd_ru(s.cx2, hw), g.x)));
+  ey = fminf(ey, fminf(__fadd_ru(__fsub_ru(g.w, s.cy1), hh), __fsub_ru(__fadd_ru(s.cy2, hh), g.y)));
+  ex = fmaxf(fminf(ex, s.wmax), 1.0001e-10f);
+  ey = fmaxf(fminf(ey, s.hmax), 1.0001e-10f);
   iub = __fmul_ru(ex, ey);
   dlb = __fadd_rd(__fsub_rd(__fadd_rd(ga_lo, s.amin), iub), 0.9999e-10f);
 }
@@ -165,6 +171,7 @@ __global__ void __launch_bounds__(256) tile_stats_kernel(const void* __restrict_
   const int a = perm ? perm[slot] : slot;
   const bool valid = a >= 0 && a < A;
   u32 kx1 = ~0u, ky1 = ~0u, kx2 = 0u, ky2 = 0u, kw = 0u, kh = 0u, ka = ~0u;
+  u32 kc1 = ~0u, kd1 = ~0u, kc2 = 0u, kd2 = 0u;
   bool safe = true;
   if (valid) {
     TP cx, cy, w, h;
@@ -177,9 +184,16 @@ __global__ void __launch_bounds__(256) tile_stats_kernel(const void* __restrict_
       kx1 = key32(x1); ky1 = key32(y1); kx2 = key32(x2); ky2 = key32(y2);
       kw = key32(__fsub_ru(x2, x1)); kh = key32(__fsub_ru(y2, y1));
       ka = key32(f_down((double)c.area));
+      const double mx = 0.5 * ((double)c.x1 + (double)c.x2), my = 0.5 * ((double)c.y1 + (double)c.y2);
+      kc1 = key32(f_down(mx - 1e-12 * fabs(mx))); kc2 = key32(f_up(mx + 1e-12 * fabs(mx)));
+      kd1 = key32(f_down(my - 1e-12 * fabs(my))); kd2 = key32(f_up(my + 1e-12 * fabs(my)));
     }
   }
   TileStat st;
+  st.cx1 = unkey32(__reduce_min_sync(SSDG_FULL, kc1));
+  st.cy1 = unkey32(__reduce_min_sync(SSDG_FULL, kd1));
+  st.cx2 = unkey32(__reduce_max_sync(SSDG_FULL, kc2));
+  st.cy2 = unkey32(__reduce_max_sync(SSDG_FULL, kd2));
   st.x1 = unkey32(__reduce_min_sync(SSDG_FULL, kx1));
   st.y1 = unkey32(__reduce_min_sync(SSDG_FULL, ky1));
   st.x2 = unkey32(__reduce_max_sync(SSDG_FULL, kx2));
@@ -214,6 +228,7 @@ struct MatchSmem {
   int* red_idx;
   int* ctl;                          // control words, see enum
   TileStat* tiles_s;                 // staged tile statistics (when they fit)
+  float* ub_s;                       // [warps][ntiles_s] per-warp cache of the rows' tile bounds
   u32 *elim_s, *touch_s;             // bitmaps (when they fit)
   __device__ void carve(unsigned char* base, int tm, int ntiles_s, int bit_words) {
     size_t o = 0;
@@ -225,6 +240,7 @@ struct MatchSmem {
     o = (o + 15) & ~(size_t)15;
     cbox = (float4*)(base + o); o += 16 * (size_t)tm;
     tiles_s = (TileStat*)(base + o); o += sizeof(TileStat) * (size_t)ntiles_s;
+    ub_s = (float*)(base + o); o += 4 * (size_t)ntiles_s * (SSDG_MATCH_THREADS / 32);
     rowkey = (u64*)(base + o); o += 8 * (size_t)tm;
     galo = (float*)(base + o); o += 4 * (size_t)tm;
     rowcol = (int*)(base + o); o += 4 * (size_t)tm;
@@ -239,10 +255,11 @@ struct MatchSmem {
   }
 };
 static size_t match_smem_bytes(int tm, int ntiles_s, int bit_words) {
-  return (size_t)tm * (5 * 8 + 16 + 8 + 4 + 16 + 1) + (size_t)ntiles_s * sizeof(TileStat) + (size_t)bit_words * 8 + 16 + 64 + 96;
+  return (size_t)tm * (5 * 8 + 16 + 8 + 4 + 16 + 1) + (size_t)ntiles_s * (sizeof(TileStat) + 4 * (SSDG_MATCH_THREADS / 32)) +
+         (size_t)bit_words * 8 + 16 + 64 + 96;
 }
 
-enum { C_IMG = 0, C_NCAND, C_NRS, C_DONE, C_ROUND, C_DEGEN, C_MINELIM };
+enum { C_IMG = 0, C_NCAND, C_NRS, C_DONE, C_ROUND, C_DEGEN, C_MINELIM, C_NEXTROW };
 
 template <typename TG, typename TP>
 __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(MatchParams P) {
@@ -281,8 +298,17 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
   };
   auto bit_test = [&](const u32* bm, int a) { return (bm[a >> 5] >> (a & 31)) & 1u; };
 
+#ifdef SSDG_MATCH_TIMING
+  long long tk0 = 0;
+#define TICK(slot) do { __syncthreads(); if (tid == 0) { long long n_ = clock64(); atomicAdd((unsigned long long*)&P.ws_head[8 + 2 * (slot)], (unsigned long long)(n_ - tk0)); tk0 = n_; } } while (0)
+#else
+#define TICK(slot) do { } while (0)
+#endif
   for (;;) {
     __syncthreads();
+#ifdef SSDG_MATCH_TIMING
+    if (tid == 0) tk0 = clock64();
+#endif
     if (tid == 0) S.ctl[C_IMG] = (int)atomicAdd(&P.ws_head[0], 1u);
     __syncthreads();
     const int img = S.ctl[C_IMG];
@@ -313,14 +339,18 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
     for (int w = tid; w < P.elim_words; w += kMatchThreads) { elim[w] = 0u; touch[w] = 0u; }
     if (tid == 0) {
       S.ctl[C_NCAND] = 0; S.ctl[C_NRS] = 0; S.ctl[C_DONE] = 0; S.ctl[C_ROUND] = 0; S.ctl[C_DEGEN] = 0;
-      S.ctl[C_MINELIM] = 0x7fffffff;
+      S.ctl[C_MINELIM] = 0x7fffffff; S.ctl[C_NEXTROW] = 0;
     }
     __syncthreads();
 
     // ---- search: one warp per row; `subset`: only the rows in rs_list, over the live columns ---------
     auto search = [&](const bool subset) {
       const int nrow = subset ? S.ctl[C_NRS] : T;
-      for (int k = warp; k < nrow; k += kMatchWarps) {
+      for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(&S.ctl[C_NEXTROW], 1);    // rows differ in cost: hand them out dynamically
+        k = __shfl_sync(SSDG_FULL, k, 0);
+        if (k >= nrow) break;
         const int t = subset ? S.rs_list[k] : k;
         const Corners<R> g = load_gt(t);
         const float4 gb = S.cbox[t];
@@ -337,7 +367,13 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
           u64 key = 0ull;
           if (valid) {
             Corners<R> p; TP dx, dy, dw, dh;
-            load_prior(a, p, dx, dy, dw, dh);
+            if (P.pprior) {   // slot-ordered copy: no dependent load behind the permutation
+              Vec4<TP>::load(P.pprior, slot, dx, dy, dw, dh);
+              Corners<TP> c = corners_of<TP>(dx, dy, dw, dh);
+              p.x1 = (R)c.x1; p.y1 = (R)c.y1; p.x2 = (R)c.x2; p.y2 = (R)c.y2; p.area = (R)c.area;
+            } else {
+              load_prior(a, p, dx, dy, dw, dh);
+            }
             key = key64((double)iou_corners<R>(g, p, EPS));
             if (!subset && key > thr_key) {   // phase-2 candidate
               const int pos = atomicAdd(&S.ctl[C_NCAND], 1);
@@ -352,16 +388,25 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
             rowlo = fmaxf(f_down(unkey64(wk)), 0.f);
           }
         };
-        // pass 1: the tile with the highest bound seeds the running maximum
+#ifdef SSDG_MATCH_TIMING
+        long long w0 = clock64(), wev = 0, w1 = 0; int nev = 0;
+#define EVAL(x) do { long long e0_ = clock64(); evaluate(x); wev += clock64() - e0_; ++nev; } while (0)
+#else
+#define EVAL(x) evaluate(x)
+#endif
+        // pass 1: bound every tile (cached per warp when the tiles are staged); the highest seeds the maximum
         float sub = -1.f;
         int stile = 0x7fffffff;
+        float* ubw = S.ub_s + (size_t)warp * ntiles;
+#pragma unroll 4
         for (int tb = 0; tb < ntiles; tb += 32) {
           const int tile = tb + lane;
           if (tile < ntiles) {
             const TileStat ts = tiles[tile];
             float iub, dlb;
             iou_bound(gb, galo, ts, iub, dlb);
-            const float ub = (ts.safe && dlb > 0.f) ? __fdividef(iub, dlb) : CUDART_INF_F;
+            const float ub = (ts.safe && dlb > 0.f) ? __fdividef(iub, dlb) * 1.0002f : CUDART_INF_F;
+            if (tiles_in_smem) ubw[tile] = ub;
             if (ub > sub) { sub = ub; stile = tile; }
           }
         }
@@ -369,29 +414,47 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
           const u32 m = __reduce_max_sync(SSDG_FULL, key32(sub));
           stile = (int)__reduce_min_sync(SSDG_FULL, key32(sub) == m ? (u32)stile : 0x7fffffffu);
         }
-        evaluate(stile);
+#ifdef SSDG_MATCH_TIMING
+        w1 = clock64();
+#endif
+        EVAL(stile);
         // pass 2: every other tile whose bound still reaches min(thresh, running maximum)
         for (int tb = 0; tb < ntiles; tb += 32) {
           const int tile = tb + lane;
           bool pending = tile < ntiles && tile != stile;
+          float ub = 0.f;
           TileStat ts;
-          ts.x1 = ts.y1 = ts.x2 = ts.y2 = ts.wmax = ts.hmax = ts.amin = 0.f; ts.safe = 1u;
-          if (pending) ts = tiles[tile];
+          ts.x1 = ts.y1 = ts.x2 = ts.y2 = ts.wmax = ts.hmax = ts.amin = ts.cx1 = ts.cy1 = ts.cx2 = ts.cy2 = 0.f; ts.safe = 1u;
+          if (pending) {
+            if (tiles_in_smem) ub = ubw[tile]; else ts = tiles[tile];
+          }
           for (;;) {
-            const bool reach = pending && may_reach(gb, galo, ts, fminf(thr_lo, rowlo));
+            const float bound = fminf(thr_lo, rowlo);
+            const bool reach = pending && (tiles_in_smem ? !(ub < bound) : may_reach(gb, galo, ts, bound));
             const u32 m = __ballot_sync(SSDG_FULL, reach);
             if (!m) break;
             const int l = __ffs(m) - 1;
             if (lane == l) pending = false;
-            evaluate(tb + l);
+            EVAL(tb + l);
           }
         }
         if (lane == 0) { S.rowkey[t] = best_key; S.rowcol[t] = best_a; }
+#ifdef SSDG_MATCH_TIMING
+        if (lane == 0 && !subset) {
+          atomicAdd((unsigned long long*)&P.ws_head[24], (unsigned long long)(w1 - w0));                 // pass 1
+          atomicAdd((unsigned long long*)&P.ws_head[26], (unsigned long long)wev);                       // evaluations
+          atomicAdd((unsigned long long*)&P.ws_head[28], (unsigned long long)(clock64() - w1 - wev));    // pass 2 tests
+          atomicAdd((unsigned long long*)&P.ws_head[30], (unsigned long long)nev);
+        }
+#endif
       }
     };
 
+    TICK(0);
     search(false);
     __syncthreads();
+    if (tid == 0) S.ctl[C_NEXTROW] = 0;
+    TICK(1);
 
     // ---- phase 2: first-arg-max row of every listed prior ---------------------------------------------
     const int ncand_raw = S.ctl[C_NCAND];
@@ -425,6 +488,7 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
     }
     __syncthreads();
 
+    TICK(2);
     // ---- greedy rounds (utils/bbox.py:62-68) --------------------------------------------------------
     if (T > 0)
     for (;;) {
@@ -576,11 +640,12 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
       if (done && nrs == 0) break;
       if (nrs > 0) search(true);
       __syncthreads();
-      if (tid == 0) S.ctl[C_NRS] = 0;
+      if (tid == 0) { S.ctl[C_NRS] = 0; S.ctl[C_NEXTROW] = 0; }
       __syncthreads();
       if (done) break;
     }
 
+    TICK(3);
     // ---- output: every prior once, in prior order (phase 2), then the phase-1 pairs ---------------------
     for (int a = tid; a < A; a += kMatchThreads) {
       const bool pos = bit_test(touch, a) != 0;
@@ -633,6 +698,7 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
         reinterpret_cast<float4*>(P.out_loc)[obase + a] = encode_row<TP>(bx, by, bw, bh, dx, dy, dw, dh);
       }
     }
+    TICK(4);
   }
 }
 
@@ -687,7 +753,7 @@ static size_t match_ws_layout(int n_priors, int ctas, MatchWs* out, unsigned cha
 
 // ---- prior index ---------------------------------------------------------------------------------------
 constexpr int kIndexMaxShapes = 64;
-struct IndexInfo { int n_priors, ntiles; };
+struct IndexInfo { int n_priors, ntiles, dtype; };
 static std::mutex g_index_mu;
 static std::unordered_map<const void*, IndexInfo> g_index;   // device pointer -> geometry
 
@@ -697,6 +763,7 @@ static size_t index_tiles_offset(int n_priors) { return 256 + align_up(index_slo
 static size_t index_unmatched_offset(int n_priors) {
   return index_tiles_offset(n_priors) + align_up(index_slots(n_priors) / 32 * sizeof(TileStat), 256);
 }
+static size_t index_pprior_offset(int n_priors) { return index_unmatched_offset(n_priors) + align_up((size_t)n_priors * 16, 256); }
 
 }  // namespace ssdg
 
@@ -704,7 +771,7 @@ using namespace ssdg;
 
 extern "C" size_t ssdg_prior_index_bytes(int32_t n_priors) {
   if (n_priors <= 0) return 0;
-  return index_unmatched_offset(n_priors) + align_up((size_t)n_priors * 16, 256);
+  return index_pprior_offset(n_priors) + align_up(index_slots(n_priors) * 32, 256);
 }
 
 extern "C" int ssdg_prior_index_build(const void* priors, int32_t prior_dtype, int32_t n_priors, void* index,
@@ -771,6 +838,14 @@ extern "C" int ssdg_prior_index_build(const void* priors, int32_t prior_dtype, i
   int header[4] = {n_priors, ntiles, 0, 0};
   SSDG_CUDA_TRY(cudaMemcpyAsync(base, header, sizeof(header), cudaMemcpyHostToDevice, st));
   SSDG_CUDA_TRY(cudaMemcpyAsync(base + index_perm_offset(), perm.data(), perm.size() * 4, cudaMemcpyHostToDevice, st));
+  {
+    // the priors in slot order (padding slots hold a copy of prior 0; they are never valid)
+    std::vector<unsigned char> pp(perm.size() * 4 * esz);
+    for (size_t sl = 0; sl < perm.size(); ++sl)
+      std::copy_n(raw.data() + (size_t)(perm[sl] < 0 ? 0 : perm[sl]) * 4 * esz, 4 * esz, pp.data() + sl * 4 * esz);
+    SSDG_CUDA_TRY(cudaMemcpyAsync(base + index_pprior_offset(n_priors), pp.data(), pp.size(), cudaMemcpyHostToDevice, st));
+    SSDG_CUDA_TRY(cudaStreamSynchronize(st));
+  }
   TileStat* tiles = (TileStat*)(base + index_tiles_offset(n_priors));
   float4* unmatched = (float4*)(base + index_unmatched_offset(n_priors));
   const int* dperm = (const int*)(base + index_perm_offset());
@@ -784,7 +859,7 @@ extern "C" int ssdg_prior_index_build(const void* priors, int32_t prior_dtype, i
   SSDG_LAUNCH_CHECK();
   SSDG_CUDA_TRY(cudaStreamSynchronize(st));
   std::lock_guard<std::mutex> lk(g_index_mu);
-  g_index[index] = IndexInfo{n_priors, ntiles};
+  g_index[index] = IndexInfo{n_priors, ntiles, prior_dtype};
   return SSDG_OK;
 }
 
@@ -820,7 +895,7 @@ extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const f
   P.out_cls = out_cls; P.out_box = out_box; P.out_loc = out_loc; P.out_mask = out_mask; P.out_match = out_match;
   P.elim_words = (n_priors + 31) / 32;
   P.ws_head = ws.head; P.ws_cand = ws.cand; P.ws_colkey = ws.colkey; P.ws_colt = ws.colt; P.ws_bits = ws.bits;
-  P.tiles = ws.tiles; P.perm = nullptr; P.unmatched = nullptr; P.ntiles = (n_priors + 31) / 32;
+  P.tiles = ws.tiles; P.perm = nullptr; P.unmatched = nullptr; P.pprior = nullptr; P.ntiles = (n_priors + 31) / 32;
   if (prior_index) {
     IndexInfo info;
     {
@@ -829,11 +904,12 @@ extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const f
       if (it == g_index.end()) return SSDG_ERR_ARG;
       info = it->second;
     }
-    if (info.n_priors != n_priors) return SSDG_ERR_SHAPE;
+    if (info.n_priors != n_priors || info.dtype != prior_dtype) return SSDG_ERR_SHAPE;
     const unsigned char* ib = (const unsigned char*)prior_index;
     P.perm = (const int*)(ib + index_perm_offset());
     P.tiles = (const TileStat*)(ib + index_tiles_offset(n_priors));
     P.unmatched = (const float4*)(ib + index_unmatched_offset(n_priors));
+    P.pprior = ib + index_pprior_offset(n_priors);
     P.ntiles = info.ntiles;
   }
   SSDG_CUDA_TRY(cudaMemsetAsync(P.ws_head, 0, 256, st));
