@@ -182,6 +182,17 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, u3
       : "memory");
 }
 
+// exp(x - m) as FADD + FMUL + MUFU:  ex2.approx.ftz((x - m) * log2e)  -- __expf without its
+// denormal-range fix-ups.  The subtraction comes first so the terms near the maximum (the ones that
+// matter) carry no argument error; relative error ~2^-22 + 2^-24*|x-m|; flush-to-zero below 2^-126.
+#define SSDG_LOG2E 1.4426950408889634f
+__device__ __forceinline__ float exp2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float exp_shifted(float x, float m) { return exp2_ftz((x - m) * SSDG_LOG2E); }
+
 // streaming stores / loads that do not pollute L1
 __device__ __forceinline__ void st_cs(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_cs(float4* p, float4 v) { __stcs(p, v); }

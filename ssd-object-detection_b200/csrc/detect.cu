@@ -110,28 +110,34 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
       for (; c < C; ++c) m0 = fmaxf(m0, row[c]);
       m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       // exp(x - max) is written back into the row; one pre-filter bit per foreground class
+      const float nml = m;
       float s0 = 0.f, s1 = 0.f;
-      auto chunk = [&](int c0, int cn) {
+      auto chunk32 = [&](int c0) {   // a full word of 32 classes, fully unrolled: the bit positions are immediates
         u32 bits = 0u;
-        int cc = 0;
-        for (; cc + 2 <= cn; cc += 2) {
-          const float e0 = __expf(row[c0 + cc] - m), e1 = __expf(row[c0 + cc + 1] - m);
-          row[c0 + cc] = e0; row[c0 + cc + 1] = e1;
+        float* r = row + c0;
+#pragma unroll
+        for (int cc = 0; cc < 32; cc += 2) {
+          const float e0 = exp_shifted(r[cc], nml), e1 = exp_shifted(r[cc + 1], nml);
+          r[cc] = e0; r[cc + 1] = e1;
           s0 += e0; s1 += e1;
           if (e0 > pre) bits |= 1u << cc;
           if (e1 > pre) bits |= 2u << cc;
         }
-        if (cc < cn) {
-          const float e0 = __expf(row[c0 + cc] - m);
+        return bits;
+      };
+      auto chunk = [&](int c0, int cn) {
+        u32 bits = 0u;
+        for (int cc = 0; cc < cn; ++cc) {
+          const float e0 = exp_shifted(row[c0 + cc], nml);
           row[c0 + cc] = e0; s0 += e0;
           if (e0 > pre) bits |= 1u << cc;
         }
         return bits;
       };
-      bits0 = chunk(0, min(32, nfg));
-      if (nfg > 32) bits1 = chunk(32, min(32, nfg - 32));
-      if (nfg > 64) bits2 = chunk(64, min(32, nfg - 64));
-      for (c = min(nfg, 96); c < C; ++c) { const float e0 = __expf(row[c] - m); row[c] = e0; s0 += e0; }
+      bits0 = nfg >= 32 ? chunk32(0) : chunk(0, nfg);
+      if (nfg > 32) bits1 = nfg >= 64 ? chunk32(32) : chunk(32, nfg - 32);
+      if (nfg > 64) bits2 = nfg >= 96 ? chunk32(64) : chunk(64, nfg - 64);
+      for (c = min(nfg, 96); c < C; ++c) { const float e0 = exp_shifted(row[c], nml); row[c] = e0; s0 += e0; }
       inv_s = __frcp_rn(s0 + s1);
     } else {
       const int lim = min(nfg, 96);

@@ -70,11 +70,13 @@ __device__ __forceinline__ void row_lse(const float* __restrict__ row, int C, fl
   for (; c < C; ++c) m0 = fmaxf(m0, row[c]);
   m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  const float nml = m;
   c = 0;
   for (; c + 4 <= C; c += 4) {
-    s0 += __expf(row[c] - m); s1 += __expf(row[c + 1] - m); s2 += __expf(row[c + 2] - m); s3 += __expf(row[c + 3] - m);
+    s0 += exp_shifted(row[c], nml); s1 += exp_shifted(row[c + 1], nml);
+    s2 += exp_shifted(row[c + 2], nml); s3 += exp_shifted(row[c + 3], nml);
   }
-  for (; c < C; ++c) s0 += __expf(row[c] - m);
+  for (; c < C; ++c) s0 += exp_shifted(row[c], nml);
   s = (s0 + s1) + (s2 + s3);
 }
 
