@@ -112,7 +112,10 @@ def run_reference(args):
     line = base_line(args, value, dt / args.steps * 1e3, n_gpus=args.gpus)
     line.update({"impl": "reference", "dtype": "f64", "cpu_baseline": cb, "gpu_launches": 0,
                  "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    line["config"]["workload"] = workload_name(args) + " [CPU port, %d-image sample per step]" % arm.images
+    from ssdgeom import synth
+    line["config"]["priors"] = synth.num_priors(synth.TABLES[args.table])
+    line["config"]["l2"] = "inputs larger than L2 (logits %.0f MB per GPU)" % (
+        args.batch * line["config"]["priors"] * 81 * 4 / 1e6)
     print(json.dumps(line), flush=True)
 
 
@@ -149,7 +152,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -167,11 +170,21 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
-    def summary(self, t0, t1):
+    def summary(self, t0, t1, load0=None, load1=None):
+        """Median SM clock and throttle reasons over the timed window [t0, t1]; when that window is too
+        short for three samples, over the whole period the GPU was under this benchmark's load."""
+        out = self._summary(t0 - 0.02, t1 + 0.02)
+        out["window"] = "timed region"
+        if out["samples"] < 3 and load0 is not None:
+            out = self._summary(load0, load1)
+            out["window"] = "whole loaded period (timed region shorter than 3 samples)"
+        return out
+
+    def _summary(self, t0, t1):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for t, row in self.rows:
-            if t < t0 or t > t1 + 0.15:
+            if t < t0 or t > t1:
                 continue
             f = [x.strip() for x in row.split(",")]
             try:
@@ -242,14 +255,15 @@ def run_ours(args):
         hp.step()
         exchange()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.2)
+    t_load0 = time.perf_counter()
     for _ in range(max(args.warmup, 3)):
         full_step()
     hp.s_main.sync()
 
     # ---- timed region: device-resident chain ------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
     ev0, ev1 = D.Event(), D.Event()
     barrier()
     t0 = time.perf_counter()
@@ -261,7 +275,6 @@ def run_ours(args):
     barrier()
     t1 = time.perf_counter()
     ms_total = ev0.elapsed_ms(ev1)
-    clocks = sampler.summary(t0, t1)
 
     def max_over_ranks(v):
         if world == 1:
@@ -304,7 +317,7 @@ def run_ours(args):
     time_stage("loss_ms", hp.loss_stage, [N.PROF_CE])
     time_stage("detect_ms", hp.detect_stage, [N.PROF_FILTER, N.PROF_NMS])
     N.lib().ssdg_profile_enable(0)
-    sampler_end = time.perf_counter()
+    clocks = sampler.summary(t0, t1, t_load0, time.perf_counter())
 
     # ---- end to end through the host API -------------------------------------------------------------------
     e2e = None
@@ -342,8 +355,15 @@ def run_ours(args):
     ce_bytes = b * loss_bytes_img                              # algorithmic bytes of one ce_kernel launch
     ce_ms = kernel_ms.get(N.PROF_CE, 0.0)
     achieved = ce_bytes / (ce_ms * 1e-3) / 1e9 if ce_ms > 0 else 0.0
+    traffic = None
+    try:      # dram__bytes_read.sum + dram__bytes_write.sum of one ce_kernel launch (ncu --set full), same shape only
+        cap = json.load(open(os.path.join(ROOT, "profiles", "ce_kernel_traffic.json")))
+        if cap.get("batch") == b and cap.get("priors") == a and cap.get("classes") == c:
+            traffic = cap["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": "ce_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": ce_ms,
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": ce_ms,
             "algorithmic_bytes_per_launch": ce_bytes}
     filt_bytes = b * a * (c * 4 + 16)
     f_ms = kernel_ms.get(N.PROF_FILTER, 0.0)

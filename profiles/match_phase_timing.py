@@ -15,3 +15,5 @@ print("phase clocks per image (setup, search, phase2, greedy, output):", [int(x)
 w = head[24:32].view(np.uint64)
 rows = 256*100
 print("per row: pass1 clk %d, evaluations clk %d (n=%.2f), pass2 tests clk %d" % (w[0]//rows, w[1]//rows, w[3]/rows, w[2]//rows))
+
+print("re-search events per image %.2f, rows per image %.2f, clocks per image %d" % (head[40]/256, head[41]/256, int(head[42:44].view(np.uint64)[0])//256))

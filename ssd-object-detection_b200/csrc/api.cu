@@ -113,6 +113,16 @@ int ssdg_stream_create(void** stream) {
   *stream = (void*)s;
   return (int)e;
 }
+int ssdg_stream_create_priority(void** stream, int high_priority) {
+  if (!stream) return SSDG_ERR_ARG;
+  int lo = 0, hi = 0;   // numerically lower = higher priority
+  cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (e != cudaSuccess) return (int)e;
+  cudaStream_t s;
+  e = cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo);
+  *stream = (void*)s;
+  return (int)e;
+}
 int ssdg_stream_destroy(void* stream) { return (int)cudaStreamDestroy((cudaStream_t)stream); }
 int ssdg_stream_sync(void* stream) { return (int)cudaStreamSynchronize((cudaStream_t)stream); }
 int ssdg_event_create(void** event) {

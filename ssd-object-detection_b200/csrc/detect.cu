@@ -208,7 +208,7 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
 }
 
 template <typename TP, bool kProbs>
-__global__ void __launch_bounds__(kFThreads, 1) filter_kernel(DetectParams P, int warps_per_cta) {
+__global__ void __launch_bounds__(kFThreads, 2) filter_kernel(DetectParams P, int warps_per_cta) {   // <= 64 registers: leaves room for a matcher CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int C = P.C, A = P.A, tpi = P.tpi;
   const size_t tile_floats = (size_t)32 * C;
@@ -638,6 +638,7 @@ static int run_filter(DetectParams& P, int prior_dtype, cudaStream_t st) {
   }
   prof_end(SSDG_PROF_FILTER, st);
   SSDG_LAUNCH_CHECK();
+  SSDG_CUDA_TRY(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   bucket_kernel<<<P.B, kBucketThreads, (size_t)2 * (P.C - 1) * 4, st>>>(P);
   SSDG_LAUNCH_CHECK();
   return SSDG_OK;
@@ -657,6 +658,7 @@ static int run_nms(const DetectWs& ws, const float* boxes, long long batch, int 
     SSDG_CUDA_TRY(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long lists = batch * (C - 1);
   if (lists > 0x7fffffffll) return SSDG_ERR_LIMIT;
+  SSDG_CUDA_TRY(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   prof_begin(SSDG_PROF_NMS, st);
   nms_kernel<<<(unsigned)lists, kNmsThreads, smem, st>>>(Q);
   prof_end(SSDG_PROF_NMS, st);

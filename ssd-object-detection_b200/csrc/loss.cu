@@ -499,6 +499,8 @@ extern "C" int ssdg_multibox_loss(const int32_t* gt_cls, const float* gt_box, co
   const long long sneed = (P.N / 4 + 255) / 256;
   if (sneed < sgrid) sgrid = (int)(sneed > 0 ? sneed : 1);
   if (sgrid > 1024) sgrid = 1024;
+  SSDG_CUDA_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  SSDG_CUDA_TRY(cudaFuncSetAttribute(final_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   select_kernel<<<sgrid, 256, 0, st>>>(P, 1);
   select_kernel<<<sgrid, 256, 0, st>>>(P, 2);
   final_kernel<<<sgrid, 256, 0, st>>>(P);

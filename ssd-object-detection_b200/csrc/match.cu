@@ -223,7 +223,7 @@ struct MatchSmem {
   float* galo;                       // float lower bound of the area (NaN: never cull)
   u64* rowkey;                       // cached row maximum (key64) over live columns
   int* rowcol;                       // first arg-max column of rowkey
-  int *pair_t, *pair_a, *rs_list;
+  int *pair_t, *pair_a, *rs_list, *order;
   uint8_t* dead;
   int* red_idx;
   int* ctl;                          // control words, see enum
@@ -247,6 +247,7 @@ struct MatchSmem {
     pair_t = (int*)(base + o); o += 4 * (size_t)tm;
     pair_a = (int*)(base + o); o += 4 * (size_t)tm;
     rs_list = (int*)(base + o); o += 4 * (size_t)tm;
+    order = (int*)(base + o); o += 4 * (size_t)tm;
     red_idx = (int*)(base + o); o += 4 * 4;
     ctl = (int*)(base + o); o += 4 * 16;
     elim_s = (u32*)(base + o); o += 4 * (size_t)bit_words;
@@ -255,11 +256,11 @@ struct MatchSmem {
   }
 };
 static size_t match_smem_bytes(int tm, int ntiles_s, int bit_words) {
-  return (size_t)tm * (5 * 8 + 16 + 8 + 4 + 16 + 1) + (size_t)ntiles_s * (sizeof(TileStat) + 4 * (SSDG_MATCH_THREADS / 32)) +
+  return (size_t)tm * (5 * 8 + 16 + 8 + 4 + 20 + 1) + (size_t)ntiles_s * (sizeof(TileStat) + 4 * (SSDG_MATCH_THREADS / 32)) +
          (size_t)bit_words * 8 + 16 + 64 + 96;
 }
 
-enum { C_IMG = 0, C_NCAND, C_NRS, C_DONE, C_ROUND, C_DEGEN, C_MINELIM, C_NEXTROW };
+enum { C_IMG = 0, C_NCAND, C_NRS, C_DONE, C_ROUND, C_DEGEN, C_MINELIM, C_NEXTROW, C_RLO, C_RA, C_RKEY_LO, C_RKEY_HI, C_GENERIC, C_HEAD, C_NLIVE };
 
 template <typename TG, typename TP>
 __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(MatchParams P) {
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
     for (int w = tid; w < P.elim_words; w += kMatchThreads) { elim[w] = 0u; touch[w] = 0u; }
     if (tid == 0) {
       S.ctl[C_NCAND] = 0; S.ctl[C_NRS] = 0; S.ctl[C_DONE] = 0; S.ctl[C_ROUND] = 0; S.ctl[C_DEGEN] = 0;
-      S.ctl[C_MINELIM] = 0x7fffffff; S.ctl[C_NEXTROW] = 0;
+      S.ctl[C_MINELIM] = 0x7fffffff; S.ctl[C_NEXTROW] = 0; S.ctl[C_GENERIC] = 0; S.ctl[C_HEAD] = 0; S.ctl[C_NLIVE] = -1;
     }
     __syncthreads();
 
@@ -451,6 +452,68 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
     };
 
     TICK(0);
+    // Re-search of ONE row over the live columns by the whole CTA (a row whose cached column was taken):
+    // the warps split the tiles, share the running maximum through shared memory, and the first
+    // arg-max column is settled after a barrier.  Same exact evaluation, same bound, just parallel.
+    auto research_row = [&](int t) {
+      u64* skey = reinterpret_cast<u64*>(&S.ctl[C_RKEY_LO]);   // 8-byte aligned pair of control words
+      if (tid == 0) { *skey = 0ull; S.ctl[C_RA] = 0x7fffffff; S.ctl[C_RLO] = 0; }
+      __syncthreads();
+      const Corners<R> g = load_gt(t);
+      const float4 gb = S.cbox[t];
+      const float galo = S.galo[t];
+      u64 my_key = 0ull;
+      int my_a = 0x7fffffff;
+      for (int tb = warp * 32; tb < ntiles; tb += (kMatchThreads / 32) * 32) {
+        const int tile = tb + lane;
+        bool pending = tile < ntiles;
+        float ub = 0.f;
+        if (pending) {
+          const TileStat ts = tiles[tile];
+          float iub, dlb;
+          iou_bound(gb, galo, ts, iub, dlb);
+          ub = (ts.safe && dlb > 0.f) ? __fdividef(iub, dlb) * 1.0002f : CUDART_INF_F;
+        }
+        for (;;) {
+          const float rowlo = __int_as_float(*reinterpret_cast<volatile int*>(&S.ctl[C_RLO]));
+          const bool reach = pending && !(ub < fminf(thr_lo, rowlo));
+          if (!__ballot_sync(SSDG_FULL, reach)) break;
+          // highest bound first
+          const u32 mk = __reduce_max_sync(SSDG_FULL, reach ? key32(ub) : 0u);
+          const int l = __ffs(__ballot_sync(SSDG_FULL, reach && key32(ub) == mk)) - 1;
+          if (lane == l) pending = false;
+          const int slot = ((tb + l) << 5) + lane;
+          const int a = P.perm ? __ldg(P.perm + slot) : slot;
+          const bool valid = a >= 0 && a < A && !bit_test(elim, a);
+          u64 key = 0ull;
+          if (valid) {
+            Corners<R> p; TP dx, dy, dw, dh;
+            if (P.pprior) {
+              Vec4<TP>::load(P.pprior, slot, dx, dy, dw, dh);
+              Corners<TP> c = corners_of<TP>(dx, dy, dw, dh);
+              p.x1 = (R)c.x1; p.y1 = (R)c.y1; p.x2 = (R)c.x2; p.y2 = (R)c.y2; p.area = (R)c.area;
+            } else {
+              load_prior(a, p, dx, dy, dw, dh);
+            }
+            key = key64((double)iou_corners<R>(g, p, EPS));
+          }
+          u64 wk = key;
+          int wa = valid ? a : 0x7fffffff;
+          warp_argmax_u64(wk, wa);
+          if (wk > my_key || (wk == my_key && wa < my_a)) { my_key = wk; my_a = wa; }
+          if (lane == 0 && wk > 0ull) {
+            atomicMax(skey, wk);
+            atomicMax(&S.ctl[C_RLO], __float_as_int(fmaxf(f_down(unkey64(wk)), 0.f)));
+          }
+        }
+      }
+      __syncthreads();
+      if (lane == 0 && my_key == *skey && my_key != 0ull) atomicMin(&S.ctl[C_RA], my_a);
+      __syncthreads();
+      if (tid == 0) { S.rowkey[t] = *skey; S.rowcol[t] = S.ctl[C_RA]; }
+      __syncthreads();
+    };
+
     search(false);
     __syncthreads();
     if (tid == 0) S.ctl[C_NEXTROW] = 0;
@@ -492,84 +555,78 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
     // ---- greedy rounds (utils/bbox.py:62-68) --------------------------------------------------------
     if (T > 0)
     for (;;) {
-      if (warp == 0 && T <= 128) {
-        // Fast path: the (<= 4) rows a lane owns are cached in registers, so a round is a handful of
-        // register operations, three REDUX and one shuffle -- no shared-memory chain on the serial path.
+      // Fast path.  The global arg-max of a round is the row with the largest cached maximum, so the
+      // rounds walk the rows in descending (key, then ascending row) order -- a priority queue with lazy
+      // re-evaluation: a row whose cached column has been taken in the meantime only gives an upper
+      // bound, so it is re-searched (with every other stale row) and the order is rebuilt.
+      const bool fast = T <= 128 && !S.ctl[C_GENERIC];
+      if (fast && S.ctl[C_NLIVE] < 0) {
+        // (re)build the order of the live rows by rank counting: one warp per row, lanes split the others
+        for (int t = warp; t < T; t += kMatchThreads / 32) {
+          if (S.dead[t]) continue;
+          const u64 kt = S.rowkey[t];
+          int cnt = 0;
+          for (int u = lane; u < T; u += 32)
+            if (!S.dead[u]) { const u64 ku = S.rowkey[u]; cnt += (ku > kt || (ku == kt && u < t)) ? 1 : 0; }
+          cnt = (int)__reduce_add_sync(SSDG_FULL, (u32)cnt);
+          if (lane == 0) S.order[cnt] = t;
+        }
+        if (warp == 0) {
+          int nl = 0;
+          for (int u = lane; u < T; u += 32) nl += S.dead[u] ? 0 : 1;
+          nl = (int)__reduce_add_sync(SSDG_FULL, (u32)nl);
+          if (lane == 0) { S.ctl[C_NLIVE] = nl; S.ctl[C_HEAD] = 0; }
+        }
+        __syncthreads();
+      }
+      if (warp == 0 && fast) {
         int round = S.ctl[C_ROUND];
+        int head = S.ctl[C_HEAD];
+        const int nlive = S.ctl[C_NLIVE];
         int nrs = 0;
-        u64 rk[4];
-        int rc[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int t = lane + 32 * r;
-          const bool live = t < T && !S.dead[t];
-          rk[r] = live ? S.rowkey[t] : 0ull;
-          rc[r] = live ? S.rowcol[t] : -1;
-        }
-        while (round < T) {
-          u64 bk = rk[0];
-          int bt = lane;
-#pragma unroll
-          for (int r = 1; r < 4; ++r)
-            if (rk[r] > bk) { bk = rk[r]; bt = lane + 32 * r; }
-          if (bk == 0ull) bt = 0x7fffffff;
-          warp_argmax_u64(bk, bt);
-          int wt, wa;
-          if (bk > SSDG_KEY_ZERO || round == 0) {
-            wt = bt;
-            const int rr = wt >> 5;
-            const int mycol = rr == 0 ? rc[0] : (rr == 1 ? rc[1] : (rr == 2 ? rc[2] : rc[3]));
-            wa = __shfl_sync(SSDG_FULL, mycol, wt & 31);
-          } else {
-            // Knocked-out entries (0.0) tie with or beat every live entry: full rule, first flat index.
-            if (lane == 0) {
-              u64 best = 0ull;
-              long long bflat = 0x7fffffffffffffffll;
-              const int me = S.ctl[C_MINELIM];
-              for (int t = 0; t < T; ++t) {
-                u64 k; long long f;
-                if (S.dead[t]) { k = SSDG_KEY_ZERO; f = (long long)t * A; }
-                else {
-                  k = S.rowkey[t]; f = (long long)t * A + S.rowcol[t];
-                  if (k > best || (k == best && f < bflat)) { best = k; bflat = f; }
-                  k = SSDG_KEY_ZERO; f = (long long)t * A + me;
-                }
-                if (k > best || (k == best && f < bflat)) { best = k; bflat = f; }
-              }
-              S.red_idx[0] = (int)(bflat / A);
-              S.red_idx[1] = (int)(bflat % A);
-              S.ctl[C_DEGEN] = 1;
-            }
-            __syncwarp();
-            wt = S.red_idx[0];
-            wa = S.red_idx[1];
+        bool stop = false;
+        // 32 queue positions per step: all positions before the first stale one are taken at once
+        while (!stop && head < nlive && round < T) {
+          const int p = head + lane;
+          const bool in = p < nlive && (round + lane) < T;
+          int t = 0, a = 0;
+          u64 k = ~0ull;
+          if (in) { t = S.order[p]; k = S.rowkey[t]; a = S.rowcol[t]; }
+          const bool degen_here = in && k <= SSDG_KEY_ZERO && (round + lane) > 0;
+          const u32 same = __match_any_sync(SSDG_FULL, in ? a : -1 - lane);
+          const bool stale = in && (bit_test(elim, a) || (same & ((1u << lane) - 1u)) != 0u);
+          const u32 bad = __ballot_sync(SSDG_FULL, stale || degen_here || !in);
+          const int ntake = bad ? __ffs(bad) - 1 : 32;
+          if (lane < ntake) {
+            S.pair_t[round + lane] = t;
+            S.pair_a[round + lane] = a;
+            S.dead[t] = 1;
+            atomicOr(&elim[a >> 5], 1u << (a & 31));
+            atomicMin(&S.ctl[C_MINELIM], a);
           }
-          const bool fresh = !bit_test(elim, wa);
           __syncwarp();
-          if (lane == 0) {
-            S.pair_t[round] = wt;
-            S.pair_a[round] = wa;
-            S.dead[wt] = 1;
-            elim[wa >> 5] |= 1u << (wa & 31);
-            if (wa < S.ctl[C_MINELIM]) S.ctl[C_MINELIM] = wa;
+          round += ntake; head += ntake;
+          if (ntake < 32) {
+            const u32 dg = __ballot_sync(SSDG_FULL, degen_here);
+            const u32 st = __ballot_sync(SSDG_FULL, stale);
+            if (dg && (__ffs(dg) - 1) == ntake) { if (lane == 0) S.ctl[C_GENERIC] = 1; stop = true; }
+            else if (st && (__ffs(st) - 1) == ntake) stop = true;
           }
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-            if (lane + 32 * r == wt) { rk[r] = 0ull; rc[r] = -1; }
-          __syncwarp();
-          ++round;
-          if (fresh && round < T) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              const bool need = rk[r] != 0ull && rc[r] == wa;
-              const u32 nm = __ballot_sync(SSDG_FULL, need);
-              if (need) S.rs_list[nrs + __popc(nm & ((1u << lane) - 1u))] = lane + 32 * r;
-              nrs += __popc(nm);
-            }
-          }
-          if (nrs > 0) break;
         }
-        if (lane == 0) { S.ctl[C_ROUND] = round; S.ctl[C_NRS] = nrs; S.ctl[C_DONE] = round >= T; }
+        if (stop && round < T) {
+          // every live row whose cached column is gone is re-searched now; the order is rebuilt afterwards
+          __syncwarp();
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int t = lane + 32 * r;
+            const bool need = t < T && !S.dead[t] && bit_test(elim, S.rowcol[t]);
+            const u32 nm = __ballot_sync(SSDG_FULL, need);
+            if (need) S.rs_list[nrs + __popc(nm & ((1u << lane) - 1u))] = t;
+            nrs += __popc(nm);
+          }
+          if (lane == 0) S.ctl[C_NLIVE] = -1;
+        }
+        if (lane == 0) { S.ctl[C_ROUND] = round; S.ctl[C_HEAD] = head; S.ctl[C_NRS] = nrs; S.ctl[C_DONE] = round >= T; }
       } else if (warp == 0) {
         int round = S.ctl[C_ROUND];
         int nrs = 0;
@@ -638,7 +695,14 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
       const int nrs = S.ctl[C_NRS];
       const bool done = S.ctl[C_DONE] != 0;
       if (done && nrs == 0) break;
-      if (nrs > 0) search(true);
+#ifdef SSDG_MATCH_TIMING
+      if (tid == 0 && nrs > 0) { atomicAdd(&P.ws_head[40], 1u); atomicAdd(&P.ws_head[41], (u32)nrs); }
+      long long rs0 = clock64();
+#endif
+      for (int i = 0; i < nrs; ++i) research_row(S.rs_list[i]);
+#ifdef SSDG_MATCH_TIMING
+      if (tid == 0 && nrs > 0) atomicAdd((unsigned long long*)&P.ws_head[42], (unsigned long long)(clock64() - rs0));
+#endif
       __syncthreads();
       if (tid == 0) { S.ctl[C_NRS] = 0; S.ctl[C_NEXTROW] = 0; }
       __syncthreads();
@@ -647,8 +711,7 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
 
     TICK(3);
     // ---- output: every prior once, in prior order (phase 2), then the phase-1 pairs ---------------------
-    for (int a = tid; a < A; a += kMatchThreads) {
-      const bool pos = bit_test(touch, a) != 0;
+    auto emit_prior = [&](int a, bool pos, const float4& un) {
       float bx = 0.f, by = 0.f, bw = 0.f, bh = 0.f;
       int lab = 0, ct = -1;
       if (pos) {
@@ -664,16 +727,32 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
       if (P.out_match) P.out_match[obase + a] = ct;
       if (P.out_box) reinterpret_cast<float4*>(P.out_box)[obase + a] = make_float4(bx, by, bw, bh);
       if (P.out_loc) {
-        float4 enc;
-        if (!pos && P.unmatched) {
-          enc = __ldg(P.unmatched + a);
-        } else {
+        float4 enc = un;
+        if (pos || !P.unmatched) {
           TP dx, dy, dw, dh;
           Vec4<TP>::load(P.priors, a, dx, dy, dw, dh);
           enc = encode_row<TP>(bx, by, bw, bh, dx, dy, dw, dh);
         }
         reinterpret_cast<float4*>(P.out_loc)[obase + a] = enc;
       }
+    };
+    {
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      int a = tid;
+      for (; a + 3 * kMatchThreads < A; a += 4 * kMatchThreads) {   // four independent priors per iteration
+        float4 u[4];
+        bool p4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int aq = a + q * kMatchThreads;
+          p4[q] = bit_test(touch, aq) != 0;
+          u[q] = (P.unmatched && P.out_loc) ? __ldg(P.unmatched + aq) : z4;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) emit_prior(a + q * kMatchThreads, p4[q], u[q]);
+      }
+      for (; a < A; a += kMatchThreads)
+        emit_prior(a, bit_test(touch, a) != 0, (P.unmatched && P.out_loc) ? __ldg(P.unmatched + a) : z4);
     }
     __syncthreads();
     // phase-1 pairs (utils/bbox.py:87-90; later pairs win)
@@ -711,6 +790,8 @@ static int launch_match(const MatchParams& P, int grid, size_t smem, cudaStream_
   }
   if (smem > 48 * 1024)
     SSDG_CUDA_TRY(cudaFuncSetAttribute(match_kernel<TG, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // same shared-memory carve-out as the streaming kernels so CTAs of both can share an SM
+  SSDG_CUDA_TRY(cudaFuncSetAttribute(match_kernel<TG, TP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   prof_begin(SSDG_PROF_MATCH, st);
   match_kernel<TG, TP><<<grid, kMatchThreads, smem, st>>>(P);
   prof_end(SSDG_PROF_MATCH, st);

@@ -32,6 +32,7 @@ PROTOTYPES = {
     "ssdg_memcpy_d2h": (C.c_int, [_vp, _vp, _sz, _vp]),
     "ssdg_memset": (C.c_int, [_vp, C.c_int, _sz, _vp]),
     "ssdg_stream_create": (C.c_int, [C.POINTER(_vp)]),
+    "ssdg_stream_create_priority": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "ssdg_stream_destroy": (C.c_int, [_vp]),
     "ssdg_stream_sync": (C.c_int, [_vp]),
     "ssdg_event_create": (C.c_int, [C.POINTER(_vp)]),

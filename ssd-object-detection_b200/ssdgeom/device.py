@@ -13,9 +13,13 @@ from . import _native as N
 class Stream:
     """Owning CUDA stream (non-blocking)."""
 
-    def __init__(self):
+    def __init__(self, priority=None):
+        """priority: None (default), "high" or "low" (the device's extreme stream priorities)."""
         h = C.c_void_p()
-        N.check(N.lib().ssdg_stream_create(C.byref(h)), "stream_create")
+        if priority is None:
+            N.check(N.lib().ssdg_stream_create(C.byref(h)), "stream_create")
+        else:
+            N.check(N.lib().ssdg_stream_create_priority(C.byref(h), 1 if priority == "high" else 0), "stream_create")
         self.handle = h.value
 
     def sync(self):

@@ -33,7 +33,9 @@ class HotPath:
                     "mask": D.empty((b, a), np.uint8)}
         self.loss = {"result": D.empty((N.LOSS_RESULT_LEN,), np.float64)}
         self.det = {"kept": D.empty((b, c - 1, self.top_k), np.int32), "count": D.empty((b, c - 1), np.int32)}
-        self.s_main, self.s_a, self.s_d = D.Stream(), D.Stream(), D.Stream()
+        # the post-processing branch is the longer one: its CTAs are scheduled first, the assignment/loss
+        # branch fills the gaps
+        self.s_main, self.s_a, self.s_d = D.Stream(), D.Stream("low"), D.Stream("high")
         self.ev_begin, self.ev_a, self.ev_d = D.Event(), D.Event(), D.Event()
         self.kernel_launches_per_step = 7   # match | ce, select x2, final | filter, nms
         self.h2d_bytes = (self.gt_boxes.nbytes + self.gt_cls.nbytes + self.gt_off.nbytes + self.pred_cls.nbytes +
@@ -58,9 +60,11 @@ class HotPath:
         self.ev_begin.record(self.s_main)
         D.stream_wait_event(self.s_a, self.ev_begin)
         D.stream_wait_event(self.s_d, self.ev_begin)
+        # enqueue the long, high-priority branch first: its CTAs own the SMs from the start and the
+        # latency-bound matcher then shares them with the small NMS CTAs instead of blocking the filter
+        self.detect_stage(self.s_d)
         self.assign(self.s_a)
         self.loss_stage(self.s_a)
-        self.detect_stage(self.s_d)
         self.ev_a.record(self.s_a)
         self.ev_d.record(self.s_d)
         D.stream_wait_event(self.s_main, self.ev_a)
