@@ -88,6 +88,10 @@ SSDG_API int ssdg_event_elapsed_ms(void* start, void* stop, float* ms); /* synch
 #define SSDG_PROF_FILTER 2
 #define SSDG_PROF_NMS 3
 SSDG_API int ssdg_profile_enable(int enable);
+/* Scheduling hook: when set (non-NULL), ssdg_detect / ssdg_nms record this cudaEvent_t on their stream right
+ * after the HBM-bound filter + bucket kernels and before the ALU-bound nms_kernel, so a caller can start
+ * latency-bound work (the matcher) on another stream exactly when it overlaps best.  NULL clears it. */
+SSDG_API int ssdg_detect_set_mid_event(void* event);
 SSDG_API int ssdg_profile_last_ms(int which, float* ms);
 
 /* ---- A1: anchors -------------------------------------------------------------------------------

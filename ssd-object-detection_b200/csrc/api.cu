@@ -27,6 +27,8 @@ int max_smem_optin() {
   }
   return g_smem_optin[d];
 }
+static cudaEvent_t g_mid_event = nullptr;
+cudaEvent_t detect_mid_event() { return g_mid_event; }
 static bool g_prof = false;
 static cudaEvent_t g_prof_ev[8][2];
 static bool g_prof_have[8];
@@ -47,6 +49,10 @@ void prof_end(int which, cudaStream_t st) {
 
 extern "C" {
 
+int ssdg_detect_set_mid_event(void* event) {
+  ssdg::g_mid_event = (cudaEvent_t)event;
+  return SSDG_OK;
+}
 int ssdg_profile_enable(int enable) {
   ssdg::g_prof = enable != 0;
   return SSDG_OK;

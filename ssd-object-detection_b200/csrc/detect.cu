@@ -641,6 +641,7 @@ static int run_filter(DetectParams& P, int prior_dtype, cudaStream_t st) {
   SSDG_CUDA_TRY(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   bucket_kernel<<<P.B, kBucketThreads, (size_t)2 * (P.C - 1) * 4, st>>>(P);
   SSDG_LAUNCH_CHECK();
+  if (detect_mid_event()) SSDG_CUDA_TRY(cudaEventRecord(detect_mid_event(), st));
   return SSDG_OK;
 }
 

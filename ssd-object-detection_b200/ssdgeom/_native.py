@@ -41,6 +41,7 @@ PROTOTYPES = {
     "ssdg_stream_wait_event": (C.c_int, [_vp, _vp]),
     "ssdg_event_elapsed_ms": (C.c_int, [_vp, _vp, C.POINTER(_f32)]),
     "ssdg_profile_enable": (C.c_int, [C.c_int]),
+    "ssdg_detect_set_mid_event": (C.c_int, [_vp]),
     "ssdg_profile_last_ms": (C.c_int, [C.c_int, C.POINTER(_f32)]),
     "ssdg_prior_count": (_i64, [_pi32, _pi32, _pi32, _i32]),
     "ssdg_prior_boxes": (C.c_int, [_pi32, _pi32, _pf64, _pi32, _pf64, _i32, _f64, _vp, _i64, _vp]),

@@ -36,7 +36,8 @@ class HotPath:
         # the post-processing branch is the longer one: its CTAs are scheduled first, the assignment/loss
         # branch fills the gaps
         self.s_main, self.s_a, self.s_d = D.Stream(), D.Stream("low"), D.Stream("high")
-        self.ev_begin, self.ev_a, self.ev_d = D.Event(), D.Event(), D.Event()
+        self.ev_begin, self.ev_a, self.ev_d, self.ev_mid = D.Event(), D.Event(), D.Event(), D.Event()
+        self.stagger = False   # measured: co-running the matcher with nms_kernel is slower than with the filter pass
         self.kernel_launches_per_step = 7   # match | ce, select x2, final | filter, nms
         self.h2d_bytes = (self.gt_boxes.nbytes + self.gt_cls.nbytes + self.gt_off.nbytes + self.pred_cls.nbytes +
                           self.pred_box.nbytes)
@@ -62,7 +63,15 @@ class HotPath:
         D.stream_wait_event(self.s_d, self.ev_begin)
         # enqueue the long, high-priority branch first: its CTAs own the SMs from the start and the
         # latency-bound matcher then shares them with the small NMS CTAs instead of blocking the filter
-        self.detect_stage(self.s_d)
+        if self.stagger:
+            # The filter pass is HBM-bound and owns the SMs' registers and shared memory; the matcher is
+            # latency-bound and shares an SM best with the small, ALU-bound NMS CTAs: start it when they start.
+            N.lib().ssdg_detect_set_mid_event(self.ev_mid.handle)
+            self.detect_stage(self.s_d)
+            N.lib().ssdg_detect_set_mid_event(None)
+            D.stream_wait_event(self.s_a, self.ev_mid)
+        else:
+            self.detect_stage(self.s_d)
         self.assign(self.s_a)
         self.loss_stage(self.s_a)
         self.ev_a.record(self.s_a)
