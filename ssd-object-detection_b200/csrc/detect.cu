@@ -25,7 +25,7 @@ constexpr int kFThreads = 512;
 constexpr int kFWarps = kFThreads / 32;
 constexpr int kNmsThreads = 128;
 constexpr int kNmsWarps = kNmsThreads / 32;
-constexpr int kBucketThreads = 512;
+constexpr int kBucketThreads = 1024;
 constexpr int kABitsD = 21;     // prior index bits in a staged candidate (A < 2^21, C <= 2048)
 
 struct DetectParams {
@@ -176,7 +176,8 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
       const int c = c0 + __ffs(bits) - 1;
       bits &= bits - 1;
       const float score = kProbs ? row[c] : row[c] * inv_s;
-      *dst++ = ((u64)key32(score) << 32) | (u64)(((u32)c << kABitsD) | (u32)a);
+      const u32 sk = kProbs ? key32(score) : (__float_as_uint(score) | 0x80000000u);   // softmax scores are >= +0
+      *dst++ = ((u64)sk << 32) | (u64)(((u32)c << kABitsD) | (u32)a);
     }
   };
   emit(bits0, 0); emit(bits1, 32); emit(bits2, 64);
@@ -264,21 +265,53 @@ __global__ void __launch_bounds__(kFThreads, 2) filter_kernel(DetectParams P, in
   }
 }
 
-// Counting sort of one image's candidates by class.
+// Counting sort of one image's candidates by class.  The tile segments are addressed as one flat list
+// through a prefix of the tile counts (binary search in shared memory), so every thread has several
+// independent loads in flight instead of walking tiles one dependent load after the other.
 __global__ void __launch_bounds__(kBucketThreads) bucket_kernel(DetectParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nfg = P.C - 1, tpi = P.tpi, b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   u32* hist = reinterpret_cast<u32*>(smem_raw);   // [nfg]
   u32* off = hist + nfg;                          // [nfg]
+  u32* tpre = off + nfg;                          // [tpi + 1] exclusive prefix of the tile counts
   for (int c = tid; c < nfg; c += kBucketThreads) hist[c] = 0u;
-  __syncthreads();
   const u32* tcnt = P.tile_cnt + (size_t)b * tpi;
-  const u64* seg = P.seg + (size_t)b * tpi * (size_t)(32 * nfg);
-  for (int j = warp; j < tpi; j += kBucketThreads / 32) {
-    const int cnt = (int)tcnt[j];
-    const u64* s = seg + (size_t)j * (32 * nfg);
-    for (int e = lane; e < cnt; e += 32) atomicAdd(&hist[(u32)s[e] >> kABitsD], 1u);
+  const size_t tstride = (size_t)32 * nfg;
+  const u64* seg = P.seg + (size_t)b * tpi * tstride;
+  if (warp == 0) {
+    u32 running = 0u;
+    for (int j0 = 0; j0 < tpi; j0 += 32) {
+      const int j = j0 + lane;
+      const u32 cnt = j < tpi ? tcnt[j] : 0u;
+      u32 incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 v = __shfl_up_sync(SSDG_FULL, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (j < tpi) tpre[j] = running + incl - cnt;
+      running += __shfl_sync(SSDG_FULL, incl, 31);
+    }
+    if (lane == 0) tpre[tpi] = running;
+  }
+  __syncthreads();
+  const int total = (int)tpre[tpi];
+  auto fetch = [&](int e) {
+    int lo = 0, hi = tpi;            // largest j with tpre[j] <= e
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if ((int)tpre[mid] <= e) lo = mid; else hi = mid;
+    }
+    return seg[(size_t)lo * tstride + (e - (int)tpre[lo])];
+  };
+  for (int e0 = tid; e0 < total; e0 += 4 * kBucketThreads) {
+    u64 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const int e = e0 + q * kBucketThreads; v[q] = e < total ? fetch(e) : 0ull; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (e0 + q * kBucketThreads < total) atomicAdd(&hist[(u32)v[q] >> kABitsD], 1u);
   }
   __syncthreads();
   if (warp == 0) {
@@ -301,15 +334,18 @@ __global__ void __launch_bounds__(kBucketThreads) bucket_kernel(DetectParams P) 
     }
   }
   __syncthreads();
-  u64* out = P.sorted + (size_t)b * tpi * (size_t)(32 * nfg);
-  for (int j = warp; j < tpi; j += kBucketThreads / 32) {
-    const int cnt = (int)tcnt[j];
-    const u64* s = seg + (size_t)j * (32 * nfg);
-    for (int e = lane; e < cnt; e += 32) {
-      const u64 v = s[e];
-      const u32 low = (u32)v;
-      const u32 pos = atomicAdd(&off[low >> kABitsD], 1u);
-      out[pos] = (v & 0xffffffff00000000ull) | (u64)(~(low & ((1u << kABitsD) - 1u)));
+  u64* out = P.sorted + (size_t)b * tpi * tstride;
+  for (int e0 = tid; e0 < total; e0 += 4 * kBucketThreads) {
+    u64 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const int e = e0 + q * kBucketThreads; v[q] = e < total ? fetch(e) : 0ull; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (e0 + q * kBucketThreads < total) {
+        const u32 low = (u32)v[q];
+        const u32 pos = atomicAdd(&off[low >> kABitsD], 1u);
+        out[pos] = (v[q] & 0xffffffff00000000ull) | (u64)(~(low & ((1u << kABitsD) - 1u)));
+      }
     }
   }
 }
@@ -639,7 +675,13 @@ static int run_filter(DetectParams& P, int prior_dtype, cudaStream_t st) {
   prof_end(SSDG_PROF_FILTER, st);
   SSDG_LAUNCH_CHECK();
   SSDG_CUDA_TRY(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  bucket_kernel<<<P.B, kBucketThreads, (size_t)2 * (P.C - 1) * 4, st>>>(P);
+  {
+    const size_t bsm = ((size_t)2 * (P.C - 1) + P.tpi + 1) * 4;
+    if ((int)bsm > max_smem_optin()) return SSDG_ERR_LIMIT;
+    if (bsm > 48 * 1024)
+      SSDG_CUDA_TRY(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    bucket_kernel<<<P.B, kBucketThreads, bsm, st>>>(P);
+  }
   SSDG_LAUNCH_CHECK();
   if (detect_mid_event()) SSDG_CUDA_TRY(cudaEventRecord(detect_mid_event(), st));
   return SSDG_OK;
