@@ -265,9 +265,7 @@ __global__ void __launch_bounds__(kFThreads, 2) filter_kernel(DetectParams P, in
   }
 }
 
-// Counting sort of one image's candidates by class.  The tile segments are addressed as one flat list
-// through a prefix of the tile counts (binary search in shared memory), so every thread has several
-// independent loads in flight instead of walking tiles one dependent load after the other.
+// Counting sort of one image's candidates by class (shared-memory histogram, scan, scatter).
 __global__ void __launch_bounds__(kBucketThreads) bucket_kernel(DetectParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nfg = P.C - 1, tpi = P.tpi, b = blockIdx.x;
@@ -296,23 +294,33 @@ __global__ void __launch_bounds__(kBucketThreads) bucket_kernel(DetectParams P) 
     if (lane == 0) tpre[tpi] = running;
   }
   __syncthreads();
-  const int total = (int)tpre[tpi];
-  auto fetch = [&](int e) {
-    int lo = 0, hi = tpi;            // largest j with tpre[j] <= e
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if ((int)tpre[mid] <= e) lo = mid; else hi = mid;
+  // Each warp takes four tiles at a time: the first 64 entries of each (all of them, for trained-like
+  // scores) are loaded up front, so eight independent loads per lane are in flight.
+  constexpr int kBW = kBucketThreads / 32;
+  auto for_tiles = [&](auto&& visit) {
+    for (int j0 = warp * 4; j0 < tpi; j0 += kBW * 4) {
+      u64 v[4][2];
+      int cnt[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = j0 + q;
+        cnt[q] = j < tpi ? (int)(tpre[j + 1] - tpre[j]) : 0;
+        const u64* sp = seg + (size_t)j * tstride;
+        v[q][0] = lane < cnt[q] ? sp[lane] : 0ull;
+        v[q][1] = lane + 32 < cnt[q] ? sp[lane + 32] : 0ull;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (lane < cnt[q]) visit(v[q][0]);
+        if (lane + 32 < cnt[q]) visit(v[q][1]);
+        if (cnt[q] > 64) {
+          const u64* sp = seg + (size_t)(j0 + q) * tstride;
+          for (int e = lane + 64; e < cnt[q]; e += 32) visit(sp[e]);
+        }
+      }
     }
-    return seg[(size_t)lo * tstride + (e - (int)tpre[lo])];
   };
-  for (int e0 = tid; e0 < total; e0 += 4 * kBucketThreads) {
-    u64 v[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { const int e = e0 + q * kBucketThreads; v[q] = e < total ? fetch(e) : 0ull; }
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (e0 + q * kBucketThreads < total) atomicAdd(&hist[(u32)v[q] >> kABitsD], 1u);
-  }
+  for_tiles([&](u64 v) { atomicAdd(&hist[(u32)v >> kABitsD], 1u); });
   __syncthreads();
   if (warp == 0) {
     u32 running = 0u;
@@ -335,19 +343,11 @@ __global__ void __launch_bounds__(kBucketThreads) bucket_kernel(DetectParams P) 
   }
   __syncthreads();
   u64* out = P.sorted + (size_t)b * tpi * tstride;
-  for (int e0 = tid; e0 < total; e0 += 4 * kBucketThreads) {
-    u64 v[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { const int e = e0 + q * kBucketThreads; v[q] = e < total ? fetch(e) : 0ull; }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (e0 + q * kBucketThreads < total) {
-        const u32 low = (u32)v[q];
-        const u32 pos = atomicAdd(&off[low >> kABitsD], 1u);
-        out[pos] = (v[q] & 0xffffffff00000000ull) | (u64)(~(low & ((1u << kABitsD) - 1u)));
-      }
-    }
-  }
+  for_tiles([&](u64 v) {
+    const u32 low = (u32)v;
+    const u32 pos = atomicAdd(&off[low >> kABitsD], 1u);
+    out[pos] = (v & 0xffffffff00000000ull) | (u64)(~(low & ((1u << kABitsD) - 1u)));
+  });
 }
 
 // ---- per-(image, class) NMS ---------------------------------------------------------------------------

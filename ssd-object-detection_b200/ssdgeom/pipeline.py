@@ -38,7 +38,7 @@ class HotPath:
         self.s_main, self.s_a, self.s_d = D.Stream(), D.Stream("low"), D.Stream("high")
         self.ev_begin, self.ev_a, self.ev_d, self.ev_mid = D.Event(), D.Event(), D.Event(), D.Event()
         self.stagger = False   # measured: co-running the matcher with nms_kernel is slower than with the filter pass
-        self.kernel_launches_per_step = 7   # match | ce, select x2, final | filter, nms
+        self.kernel_launches_per_step = 8   # match | ce, select x2, final | filter, bucket, nms
         self.h2d_bytes = (self.gt_boxes.nbytes + self.gt_cls.nbytes + self.gt_off.nbytes + self.pred_cls.nbytes +
                           self.pred_box.nbytes)
         self.d2h_bytes = self.loss["result"].nbytes + self.det["kept"].nbytes + self.det["count"].nbytes
