@@ -25,6 +25,7 @@ constexpr int kFThreads = 512;
 constexpr int kFWarps = kFThreads / 32;
 constexpr int kNmsThreads = 128;
 constexpr int kNmsWarps = kNmsThreads / 32;
+constexpr int kSlabs = 16, kSlabLevels = 5;   // 16 slabs per axis, sparse table of window sizes 1,2,4,8,16
 constexpr int kBucketThreads = 1024;
 constexpr int kABitsD = 21;     // prior index bits in a staged candidate (A < 2^21, C <= 2048)
 
@@ -414,6 +415,9 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
   u32* keptw = sup + (size_t)sortn * WP;                        // [W]
   u32* remw = keptw + W;                                        // [W]
   u32* hist = remw + W;                                         // [256]
+  u32* slabx = hist + 256;                                      // [kSlabLevels][kSlabs][W] range-OR tables of the x extents
+  u32* slaby = slabx + kSlabLevels * kSlabs * W;                // same for y
+  float* dom = reinterpret_cast<float*>(slaby + kSlabLevels * kSlabs * W);   // [4 + 4*kNmsWarps] slab domain
   __shared__ u64 sel_prefix;
   __shared__ int sel_k, sel_fill;
 
@@ -533,6 +537,113 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
   __syncthreads();
 
   // Suppression bits, lower triangle: sup[i][w] bit l  <=>  iou(box_{32w+l}, box_i) > thresh, 32w+l < i.
+  if (fast_ok) {
+    // Slab join.  If iou(i, j) > thr then the x overlap is at least thr * w_i, so box j's x extent meets
+    // the SHRUNK extent [x1_i + t w_i, x2_i - t w_i] of box i (t = 0.98 thr; its midpoint when t >= 0.5),
+    // and the same in y.  Every box registers its full extents in 16 slabs per axis (one bitset per slab);
+    // a sparse table gives the OR over any slab range in two loads; row i then only tests the boxes
+    // found for its shrunk extents in both axes -- a few percent of all pairs.
+    // The overlap bound below is stated in the formula's areas w*h; it carries over to the corner extents
+    // when every box's extents reproduce its area to 0.1% (always, unless a box is a few ulps wide).
+    int inexact = 0;
+    {
+      u32 k1 = ~0u, k2 = ~0u, k3 = 0u, k4 = 0u;
+      for (int i = tid; i < m; i += kNmsThreads) {
+        if (isfinite(q2[i].y)) {
+          const float4 c = crn[i];
+          const float pr = (c.z - c.x) * (c.w - c.y);
+          inexact |= !(area[i] >= 0.999f * pr && area[i] <= 1.001f * pr);
+          k1 = min(k1, key32(c.x)); k2 = min(k2, key32(c.y)); k3 = max(k3, key32(c.z)); k4 = max(k4, key32(c.w));
+        }
+      }
+      k1 = __reduce_min_sync(SSDG_FULL, k1); k2 = __reduce_min_sync(SSDG_FULL, k2);
+      k3 = __reduce_max_sync(SSDG_FULL, k3); k4 = __reduce_max_sync(SSDG_FULL, k4);
+      if (lane == 0) {
+        dom[4 + 4 * warp + 0] = unkey32(k1); dom[4 + 4 * warp + 1] = unkey32(k2);
+        dom[4 + 4 * warp + 2] = unkey32(k3); dom[4 + 4 * warp + 3] = unkey32(k4);
+      }
+      for (int i = tid; i < 2 * kSlabLevels * kSlabs * W; i += kNmsThreads) slabx[i] = 0u;   // both tables
+      inexact = __syncthreads_or(inexact);
+      if (tid == 0) {
+        float x1 = CUDART_INF_F, y1 = CUDART_INF_F, x2 = -CUDART_INF_F, y2 = -CUDART_INF_F;
+        for (int w = 0; w < kNmsWarps; ++w) {
+          x1 = fminf(x1, dom[4 + 4 * w]); y1 = fminf(y1, dom[5 + 4 * w]);
+          x2 = fmaxf(x2, dom[6 + 4 * w]); y2 = fmaxf(y2, dom[7 + 4 * w]);
+        }
+        dom[0] = x1; dom[1] = y1;
+        dom[2] = (x2 > x1) ? (float)kSlabs / (x2 - x1) : 0.f;
+        dom[3] = (y2 > y1) ? (float)kSlabs / (y2 - y1) : 0.f;
+      }
+      __syncthreads();
+    }
+    const float dx0 = dom[0], dy0 = dom[1], dsx = dom[2], dsy = dom[3];
+    auto slab = [&](float v, float o, float sc) {   // monotone in v
+      const float f = (v - o) * sc;
+      return f >= (float)(kSlabs - 1) ? kSlabs - 1 : (f > 0.f ? (int)f : 0);
+    };
+    for (int i = tid; i < m; i += kNmsThreads) {
+      if (!isfinite(q2[i].y)) continue;
+      const float4 c = crn[i];
+      const u32 bit = 1u << (i & 31);
+      const int wi = i >> 5;
+      for (int sl = slab(c.x, dx0, dsx), e = slab(c.z, dx0, dsx); sl <= e; ++sl) atomicOr(&slabx[sl * W + wi], bit);
+      for (int sl = slab(c.y, dy0, dsy), e = slab(c.w, dy0, dsy); sl <= e; ++sl) atomicOr(&slaby[sl * W + wi], bit);
+    }
+    __syncthreads();
+    for (int k = 1; k < kSlabLevels; ++k) {
+      const int half = 1 << (k - 1);
+      for (int idx = tid; idx < kSlabs * W; idx += kNmsThreads) {
+        const int sl = idx / W, w = idx - sl * W;
+        const int s2 = sl + half;
+        const u32* px = slabx + (k - 1) * kSlabs * W;
+        const u32* py = slaby + (k - 1) * kSlabs * W;
+        slabx[k * kSlabs * W + idx] = px[idx] | (s2 < kSlabs ? px[s2 * W + w] : 0u);
+        slaby[k * kSlabs * W + idx] = py[idx] | (s2 < kSlabs ? py[s2 * W + w] : 0u);
+      }
+      __syncthreads();
+    }
+    // iou > thr, den >= 0.998 max(area), ey <= h'_i  =>  ex > 0.997 thr w'_i;  no shrink if a box is inexact
+    const float tshr = inexact ? 0.f : fminf(0.98f * thr, 0.5f);
+    for (int i = tid; i < m; i += kNmsThreads) {
+      const int gi = i >> 5;
+      const float4 bi = crn[i];
+      const float qi_lo = q2[i].y;
+      const bool sane = isfinite(qi_lo);
+      const float wdt = bi.z - bi.x, hgt = bi.w - bi.y;
+      // widen by a guard that covers the float rounding of the shrunk ends
+      const float ti = tshr;
+      const float gx = 1e-6f * (fabsf(bi.x) + fabsf(bi.z)), gy = 1e-6f * (fabsf(bi.y) + fabsf(bi.w));
+      const int ax = slab(bi.x + ti * wdt - gx, dx0, dsx), bx = slab(bi.z - ti * wdt + gx, dx0, dsx);
+      const int ay = slab(bi.y + ti * hgt - gy, dy0, dsy), by = slab(bi.w - ti * hgt + gy, dy0, dsy);
+      const int kx = 31 - __clz(max(bx - ax, 0) + 1), ky = 31 - __clz(max(by - ay, 0) + 1);
+      const u32* tx0 = slabx + (kx * kSlabs + ax) * W;
+      const u32* tx1 = slabx + (kx * kSlabs + max(bx - (1 << kx) + 1, ax)) * W;
+      const u32* ty0 = slaby + (ky * kSlabs + ay) * W;
+      const u32* ty1 = slaby + (ky * kSlabs + max(by - (1 << ky) + 1, ay)) * W;
+      for (int w = 0; w <= gi; ++w) {
+        u32 cand = sane ? ((tx0[w] | tx1[w]) & (ty0[w] | ty1[w])) : 0u;
+        if (w == gi) cand &= (1u << (i & 31)) - 1u;
+        u32 bits = 0u;
+        while (cand) {
+          const int jj = __ffs(cand) - 1;
+          cand &= cand - 1;
+          const int j = (w << 5) + jj;
+          const float4 bj = crn[j];
+          const float fx = fminf(bi.z, bj.z) - fmaxf(bi.x, bj.x);
+          const float fy = fminf(bi.w, bj.w) - fmaxf(bi.y, bj.y);
+          if (!(fx > 0.f && fx * fy >= qi_lo + q2[j].y)) continue;   // cheap float test, 1e-4 margin
+          // the formula itself: IEEE float32, no contraction (utils/bbox.py:13-25)
+          const float ex = fmaxf(0.f, __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
+          const float ey = fmaxf(0.f, __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
+          const float inter = __fmul_rn(ex, ey);
+          const float den = __fadd_rn(__fsub_rn(__fadd_rn(area[j], area[i]), inter), 1e-10f);
+          if (__fdiv_rn(inter, den) > thr) bits |= 1u << jj;
+        }
+        sup[(size_t)i * WP + w] = bits;
+      }
+    }
+  } else {
+  // No division-free test for this threshold: all pairs, the formula itself.
   // Task (g, w<=g): lane = row 32g+lane, loop over the 32 columns of group w (uniform shared loads).
   const int ngroups = mpad >> 5;
   const int ntasks = ngroups * (ngroups + 1) / 2;
@@ -573,6 +684,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
       if (__fdiv_rn(inter, den) > thr) bits |= 1u << jj;
     }
     sup[(size_t)i * WP + w] = bits;
+  }
   }
   __syncthreads();
 
@@ -627,7 +739,8 @@ static int next_pow2(int v) {
 }
 static size_t nms_smem_bytes(int sortn) {
   const int W = sortn / 32, WP = W | 1;
-  return (size_t)sortn * (8 + 16 + 8 + 4) + (size_t)sortn * WP * 4 + 2 * W * 4 + 256 * 4 + 128;
+  return (size_t)sortn * (8 + 16 + 8 + 4) + (size_t)sortn * WP * 4 + 2 * W * 4 + 256 * 4 +
+         (size_t)2 * kSlabLevels * kSlabs * W * 4 + (4 + 4 * kNmsWarps) * 4 + 128;
 }
 
 struct DetectWs {

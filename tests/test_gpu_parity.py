@@ -466,6 +466,34 @@ def test_nms_heavy_overlap_chain():
         assert np.array_equal(count[0], w_count) and np.array_equal(kept[0], w_kept), thr
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_nms_random_geometry_all_thresholds(seed):
+    """Random box clouds -- clusters of near-duplicates, boxes a few ulps wide, zero / negative sizes, boxes far
+    outside the unit square -- at thresholds on both sides of 0.5 and at the values that switch the kernel to its
+    all-pairs path (<= 0, huge).  Kept sets must equal the sequential greedy of the oracle, bit for bit."""
+    rng = np.random.default_rng(100 + seed)
+    a, c = 700, 4
+    centres = rng.uniform(0.1, 0.9, (12, 2))
+    pick = rng.integers(0, 12, a)
+    boxes = np.empty((1, a, 4), np.float32)
+    boxes[0, :, :2] = centres[pick] + rng.normal(0, 0.02, (a, 2))
+    boxes[0, :, 2:] = rng.uniform(0.05, 0.3, (a, 2)) * rng.choice([1.0, 1.0, 1.0, 0.1, 3.0], (a, 1))
+    boxes[0, 0:40, 2:] = rng.uniform(1e-7, 3e-7, (40, 2))              # a few ulps wide at these centres
+    boxes[0, 40:60, 2] = 0.0
+    boxes[0, 60:70, 3] = -0.1
+    boxes[0, 70:90, :2] += 50.0                                        # far away, coarse float grid
+    boxes[0, 90:100] = boxes[0, 100:110]                               # exact duplicates
+    if seed == 2:
+        boxes[0, :, 2:] = rng.uniform(1e-7, 1e-6, (a, 2))              # every box tiny: extents unreliable
+        boxes[0, :, :2] = 0.5 + rng.integers(0, 8, (a, 2)) * 1.2e-7
+    probs = rng.uniform(0.0, 1.0, (1, a, c)).astype(np.float32)
+    for thr in (0.45, 0.5, 0.3, 0.7, 0.95, 0.02, 0.0, -1.0, 2e6):
+        kept, count = M.nms(probs, boxes, top_k=200, iou_thresh=thr)
+        w_kept, w_count = O.nms_per_class(probs[0], boxes[0], top_k=200, iou_thresh=thr)
+        assert np.array_equal(count[0], w_count), (seed, thr)
+        assert np.array_equal(kept[0], w_kept), (seed, thr)
+
+
 def test_score_head(priors300):
     pred_cls, _ = synth.make_predictions(35, 2, 8732, bg_bias=2.0)
     score, cls, mask = M.score_head(pred_cls, thresh=0.3)
