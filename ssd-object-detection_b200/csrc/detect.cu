@@ -25,7 +25,7 @@ constexpr int kFThreads = 512;
 constexpr int kFWarps = kFThreads / 32;
 constexpr int kNmsThreads = 128;
 constexpr int kNmsWarps = kNmsThreads / 32;
-constexpr int kSlabs = 16, kSlabLevels = 5;   // 16 slabs per axis, sparse table of window sizes 1,2,4,8,16
+constexpr int kSlabs = 32;   // slabs per axis of the NMS candidate join
 constexpr int kBucketThreads = 1024;
 constexpr int kABitsD = 21;     // prior index bits in a staged candidate (A < 2^21, C <= 2048)
 
@@ -415,9 +415,9 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
   u32* keptw = sup + (size_t)sortn * WP;                        // [W]
   u32* remw = keptw + W;                                        // [W]
   u32* hist = remw + W;                                         // [256]
-  u32* slabx = hist + 256;                                      // [kSlabLevels][kSlabs][W] range-OR tables of the x extents
-  u32* slaby = slabx + kSlabLevels * kSlabs * W;                // same for y
-  float* dom = reinterpret_cast<float*>(slaby + kSlabLevels * kSlabs * W);   // [4 + 4*kNmsWarps] slab domain
+  u32* slabx = hist + 256;                                      // [W][kSlabs] boxes whose shrunk x extent touches the slab
+  u32* slaby = slabx + kSlabs * W;                              // same for y
+  float* dom = reinterpret_cast<float*>(slaby + kSlabs * W);    // [4 + 4*kNmsWarps] slab domain
   __shared__ u64 sel_prefix;
   __shared__ int sel_k, sel_fill;
 
@@ -538,13 +538,13 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
 
   // Suppression bits, lower triangle: sup[i][w] bit l  <=>  iou(box_{32w+l}, box_i) > thresh, 32w+l < i.
   if (fast_ok) {
-    // Slab join.  If iou(i, j) > thr then the x overlap is at least thr * w_i, so box j's x extent meets
-    // the SHRUNK extent [x1_i + t w_i, x2_i - t w_i] of box i (t = 0.98 thr; its midpoint when t >= 0.5),
-    // and the same in y.  Every box registers its full extents in 16 slabs per axis (one bitset per slab);
-    // a sparse table gives the OR over any slab range in two loads; row i then only tests the boxes
-    // found for its shrunk extents in both axes -- a few percent of all pairs.
-    // The overlap bound below is stated in the formula's areas w*h; it carries over to the corner extents
-    // when every box's extents reproduce its area to 0.1% (always, unless a box is a few ulps wide).
+    // Slab join.  iou(i, j) > thr means inter > q (area_i + area_j) with q = thr / (1 + thr); the y overlap is
+    // at most min(h_i, h_j), so the x overlap exceeds q (w_i + w_j): the x extents of i and j, each SHRUNK by
+    // q times its width at both ends, still meet (and the same in y).  Every box registers its shrunk extents
+    // in 32 slabs per axis (one bitset per slab); row i ORs the bitsets of the slabs its own shrunk extents
+    // touch, and only the boxes found in both axes -- a few percent of all pairs -- get the overlap test.
+    // The bound is stated in the formula's areas w*h; it carries over to the corner extents when every box's
+    // extents reproduce its area to 0.1% (always, unless a box is a few ulps wide) -- else nothing is shrunk.
     int inexact = 0;
     {
       u32 k1 = ~0u, k2 = ~0u, k3 = 0u, k4 = 0u;
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
         dom[4 + 4 * warp + 0] = unkey32(k1); dom[4 + 4 * warp + 1] = unkey32(k2);
         dom[4 + 4 * warp + 2] = unkey32(k3); dom[4 + 4 * warp + 3] = unkey32(k4);
       }
-      for (int i = tid; i < 2 * kSlabLevels * kSlabs * W; i += kNmsThreads) slabx[i] = 0u;   // both tables
+      for (int i = tid; i < 2 * kSlabs * W; i += kNmsThreads) slabx[i] = 0u;   // both axes
       inexact = __syncthreads_or(inexact);
       if (tid == 0) {
         float x1 = CUDART_INF_F, y1 = CUDART_INF_F, x2 = -CUDART_INF_F, y2 = -CUDART_INF_F;
@@ -581,47 +581,37 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
       const float f = (v - o) * sc;
       return f >= (float)(kSlabs - 1) ? kSlabs - 1 : (f > 0.f ? (int)f : 0);
     };
+    // 0.98: inter > q (a_i + a_j) and the 0.1% above leave ex > 0.997 q (w'_i + w'_j); the guard g covers the
+    // float rounding of the shrunk ends (a few ulps of the coordinates)
+    const float tq = inexact ? 0.f : fminf(0.98f * q, 0.49f);
+    // slab bitsets as [word][slab]: lanes with different slabs hit different banks
     for (int i = tid; i < m; i += kNmsThreads) {
       if (!isfinite(q2[i].y)) continue;
       const float4 c = crn[i];
       const u32 bit = 1u << (i & 31);
-      const int wi = i >> 5;
-      for (int sl = slab(c.x, dx0, dsx), e = slab(c.z, dx0, dsx); sl <= e; ++sl) atomicOr(&slabx[sl * W + wi], bit);
-      for (int sl = slab(c.y, dy0, dsy), e = slab(c.w, dy0, dsy); sl <= e; ++sl) atomicOr(&slaby[sl * W + wi], bit);
+      const int wi = (i >> 5) * kSlabs;
+      const float sx = tq * (c.z - c.x) - 1e-6f * (fabsf(c.x) + fabsf(c.z));
+      const float sy = tq * (c.w - c.y) - 1e-6f * (fabsf(c.y) + fabsf(c.w));
+      const int ax = slab(c.x + sx, dx0, dsx), bx = max(slab(c.z - sx, dx0, dsx), ax);
+      const int ay = slab(c.y + sy, dy0, dsy), by = max(slab(c.w - sy, dy0, dsy), ay);
+      for (int sl = ax; sl <= bx; ++sl) atomicOr(&slabx[wi + sl], bit);
+      for (int sl = ay; sl <= by; ++sl) atomicOr(&slaby[wi + sl], bit);
     }
     __syncthreads();
-    for (int k = 1; k < kSlabLevels; ++k) {
-      const int half = 1 << (k - 1);
-      for (int idx = tid; idx < kSlabs * W; idx += kNmsThreads) {
-        const int sl = idx / W, w = idx - sl * W;
-        const int s2 = sl + half;
-        const u32* px = slabx + (k - 1) * kSlabs * W;
-        const u32* py = slaby + (k - 1) * kSlabs * W;
-        slabx[k * kSlabs * W + idx] = px[idx] | (s2 < kSlabs ? px[s2 * W + w] : 0u);
-        slaby[k * kSlabs * W + idx] = py[idx] | (s2 < kSlabs ? py[s2 * W + w] : 0u);
-      }
-      __syncthreads();
-    }
-    // iou > thr, den >= 0.998 max(area), ey <= h'_i  =>  ex > 0.997 thr w'_i;  no shrink if a box is inexact
-    const float tshr = inexact ? 0.f : fminf(0.98f * thr, 0.5f);
     for (int i = tid; i < m; i += kNmsThreads) {
       const int gi = i >> 5;
       const float4 bi = crn[i];
       const float qi_lo = q2[i].y;
       const bool sane = isfinite(qi_lo);
-      const float wdt = bi.z - bi.x, hgt = bi.w - bi.y;
-      // widen by a guard that covers the float rounding of the shrunk ends
-      const float ti = tshr;
-      const float gx = 1e-6f * (fabsf(bi.x) + fabsf(bi.z)), gy = 1e-6f * (fabsf(bi.y) + fabsf(bi.w));
-      const int ax = slab(bi.x + ti * wdt - gx, dx0, dsx), bx = slab(bi.z - ti * wdt + gx, dx0, dsx);
-      const int ay = slab(bi.y + ti * hgt - gy, dy0, dsy), by = slab(bi.w - ti * hgt + gy, dy0, dsy);
-      const int kx = 31 - __clz(max(bx - ax, 0) + 1), ky = 31 - __clz(max(by - ay, 0) + 1);
-      const u32* tx0 = slabx + (kx * kSlabs + ax) * W;
-      const u32* tx1 = slabx + (kx * kSlabs + max(bx - (1 << kx) + 1, ax)) * W;
-      const u32* ty0 = slaby + (ky * kSlabs + ay) * W;
-      const u32* ty1 = slaby + (ky * kSlabs + max(by - (1 << ky) + 1, ay)) * W;
+      const float sx = tq * (bi.z - bi.x) - 1e-6f * (fabsf(bi.x) + fabsf(bi.z));
+      const float sy = tq * (bi.w - bi.y) - 1e-6f * (fabsf(bi.y) + fabsf(bi.w));
+      const int ax = slab(bi.x + sx, dx0, dsx), bx = max(slab(bi.z - sx, dx0, dsx), ax);
+      const int ay = slab(bi.y + sy, dy0, dsy), by = max(slab(bi.w - sy, dy0, dsy), ay);
       for (int w = 0; w <= gi; ++w) {
-        u32 cand = sane ? ((tx0[w] | tx1[w]) & (ty0[w] | ty1[w])) : 0u;
+        u32 mx = 0u, my = 0u;
+        for (int sl = ax; sl <= bx; ++sl) mx |= slabx[w * kSlabs + sl];
+        for (int sl = ay; sl <= by; ++sl) my |= slaby[w * kSlabs + sl];
+        u32 cand = sane ? (mx & my) : 0u;
         if (w == gi) cand &= (1u << (i & 31)) - 1u;
         u32 bits = 0u;
         while (cand) {
@@ -740,7 +730,7 @@ static int next_pow2(int v) {
 static size_t nms_smem_bytes(int sortn) {
   const int W = sortn / 32, WP = W | 1;
   return (size_t)sortn * (8 + 16 + 8 + 4) + (size_t)sortn * WP * 4 + 2 * W * 4 + 256 * 4 +
-         (size_t)2 * kSlabLevels * kSlabs * W * 4 + (4 + 4 * kNmsWarps) * 4 + 128;
+         (size_t)2 * kSlabs * W * 4 + (4 + 4 * kNmsWarps) * 4 + 128;
 }
 
 struct DetectWs {
