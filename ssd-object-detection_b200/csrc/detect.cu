@@ -365,44 +365,6 @@ struct NmsParams {
   float* out_score;
 };
 
-// Bitonic sort (descending) of n = 2^k keys in shared memory.  Pair i of a stage is handled by thread
-// i (mod blockDim); for strides <= 32 all pairs of a warp live in that warp's own 64-key block, so
-// only the long strides need a block-wide barrier.
-__device__ __forceinline__ void bitonic_sort_desc(u64* keys, int n, int tid) {
-  __syncthreads();
-  bool wide_prev = true;
-  for (int size = 2; size <= n; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      const bool wide = stride > 32;
-      if (wide || wide_prev) __syncthreads(); else __syncwarp();
-      wide_prev = wide;
-      for (int i = tid; i < (n >> 1); i += kNmsThreads) {
-        const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = ((lo & size) == 0);
-        const u64 a = keys[lo], b = keys[hi];
-        if ((a < b) == desc) { keys[lo] = b; keys[hi] = a; }
-      }
-    }
-  }
-  __syncthreads();
-}
-
-// compare-exchange of the register-resident pairs (r, r|STRIDE) of an 8-keys-per-lane bitonic network
-template <int STRIDE>
-__device__ __forceinline__ void sort_inreg(u64 (&k)[8], int size, int lane) {
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    if ((r & STRIDE) == 0) {
-      const bool desc = ((8 * lane + r) & size) == 0;
-      const u64 a = k[r], b = k[r | STRIDE];
-      const bool sw = (a < b) == desc;
-      k[r] = sw ? b : a;
-      k[r | STRIDE] = sw ? a : b;
-    }
-  }
-}
-
 __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -418,6 +380,8 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
   u32* slabx = hist + 256;                                      // [W][kSlabs] boxes whose shrunk x extent touches the slab
   u32* slaby = slabx + kSlabs * W;                              // same for y
   float* dom = reinterpret_cast<float*>(slaby + kSlabs * W);    // [4 + 4*kNmsWarps] slab domain
+  u32* bstart = reinterpret_cast<u32*>(dom + 4 + 4 * kNmsWarps);  // [256] rank sort: first slot of each bucket
+  u32* mm = bstart + 256;                                       // [4] min/max of the score and prior words
   __shared__ u64 sel_prefix;
   __shared__ int sel_k, sel_fill;
 
@@ -466,45 +430,63 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
     __syncthreads();
     n = min(sel_fill, sortn);
   }
-  int sn = 32;
-  while (sn < n) sn <<= 1;           // n <= sortn here; the keys beyond n are 0 and sort to the end
-  if (sn <= 2 * kNmsThreads) {
-    // Two keys per thread (element e = 2*tid + r): stride 1 is register-to-register, strides 2..32 one
-    // shuffle per key, only the strides that cross warps (>= 64) go through shared memory.
+  // Rank sort, descending (keys are unique).  256 buckets, monotone in the key: by the score word, scaled to
+  // the list's own [min, max] -- or by the prior word when every score is the same.  rank = elements in
+  // higher buckets + elements of the own bucket with a larger key; buckets hold a couple of keys each unless
+  // the scores are pathologically clustered (then the count loop gets long, the result stays exact).
+  {
+    u64* tmp = reinterpret_cast<u64*>(crn);   // [n] keys grouped by bucket; crn is filled after the sort
+    if (tid < 4) mm[tid] = (tid & 1) ? 0u : ~0u;
+    for (int i = tid; i < 256; i += kNmsThreads) hist[i] = 0u;
     __syncthreads();
-    u64 k0 = (2 * tid) < sn ? keys[2 * tid] : 0ull, k1 = (2 * tid + 1) < sn ? keys[2 * tid + 1] : 0ull;
-    const int e0 = 2 * tid, e1 = 2 * tid + 1;
-    for (int size = 2; size <= sn; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        if (stride == 1) {
-          const bool sw = (k0 < k1) == ((e0 & size) == 0);
-          const u64 a = k0, b = k1;
-          k0 = sw ? b : a; k1 = sw ? a : b;
-        } else {
-          u64 o0, o1;
-          if (stride <= 32) {
-            o0 = __shfl_xor_sync(SSDG_FULL, k0, stride >> 1);
-            o1 = __shfl_xor_sync(SSDG_FULL, k1, stride >> 1);
-          } else {
-            __syncthreads();
-            if (e1 < sn) { keys[e0] = k0; keys[e1] = k1; }
-            __syncthreads();
-            o0 = e1 < sn ? keys[e0 ^ stride] : 0ull;
-            o1 = e1 < sn ? keys[e1 ^ stride] : 0ull;
-          }
-          const bool t0 = ((e0 & stride) == 0) == ((e0 & size) == 0);
-          const bool t1 = ((e1 & stride) == 0) == ((e1 & size) == 0);
-          k0 = ((k0 > o0) == t0) ? k0 : o0;
-          k1 = ((k1 > o1) == t1) ? k1 : o1;
-        }
+    u32 hmin = ~0u, hmax = 0u, lmin = ~0u, lmax = 0u;
+    for (int i = tid; i < n; i += kNmsThreads) {
+      const u64 v = keys[i];
+      hmin = min(hmin, (u32)(v >> 32)); hmax = max(hmax, (u32)(v >> 32));
+      lmin = min(lmin, (u32)v); lmax = max(lmax, (u32)v);
+    }
+    hmin = __reduce_min_sync(SSDG_FULL, hmin); hmax = __reduce_max_sync(SSDG_FULL, hmax);
+    lmin = __reduce_min_sync(SSDG_FULL, lmin); lmax = __reduce_max_sync(SSDG_FULL, lmax);
+    if (lane == 0) { atomicMin(&mm[0], hmin); atomicMax(&mm[1], hmax); atomicMin(&mm[2], lmin); atomicMax(&mm[3], lmax); }
+    __syncthreads();
+    const bool byscore = mm[1] > mm[0];
+    const u32 kbase = byscore ? mm[0] : mm[2];
+    const float kscale = 256.f / ((float)((byscore ? mm[1] : mm[3]) - kbase) + 1.f);
+    auto bucket = [&](u64 v) {   // conversions, the product and the truncation are all monotone
+      const u32 x = (byscore ? (u32)(v >> 32) : (u32)v) - kbase;
+      return min(255, (int)((float)x * kscale));
+    };
+    for (int i = tid; i < n; i += kNmsThreads) atomicAdd(&hist[bucket(keys[i])], 1u);
+    __syncthreads();
+    if (warp == 0) {   // start[b] = number of keys in buckets above b; lane l owns buckets 255-8l .. 248-8l
+      u32 c[8], tot = 0u;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { c[r] = hist[255 - 8 * lane - r]; tot += c[r]; }
+      u32 incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 v = __shfl_up_sync(SSDG_FULL, incl, o);
+        if (lane >= o) incl += v;
       }
+      u32 run = incl - tot;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { bstart[255 - 8 * lane - r] = run; hist[255 - 8 * lane - r] = run; run += c[r]; }
     }
     __syncthreads();
-    if (e0 < sn) keys[e0] = k0;
-    if (e1 < sn) keys[e1] = k1;
+    for (int i = tid; i < n; i += kNmsThreads) {
+      const u64 v = keys[i];
+      tmp[atomicAdd(&hist[bucket(v)], 1u)] = v;   // hist[b] ends as the end of bucket b
+    }
     __syncthreads();
-  } else {
-    bitonic_sort_desc(keys, sn, tid);
+    for (int i = tid; i < n; i += kNmsThreads) {
+      const u64 v = tmp[i];
+      const int bk = bucket(v);
+      const int s0 = (int)bstart[bk], s1 = (int)hist[bk];
+      int r = s0;
+      for (int t = s0; t < s1; ++t) r += tmp[t] > v;
+      keys[r] = v;
+    }
+    __syncthreads();
   }
   const int m = min(n, P.top_k);
   const int mpad = (m + 31) & ~31;
@@ -607,10 +589,19 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
       const float sy = tq * (bi.w - bi.y) - 1e-6f * (fabsf(bi.y) + fabsf(bi.w));
       const int ax = slab(bi.x + sx, dx0, dsx), bx = max(slab(bi.z - sx, dx0, dsx), ax);
       const int ay = slab(bi.y + sy, dy0, dsy), by = max(slab(bi.w - sy, dy0, dsy), ay);
+      // shrunk extents mostly touch one to three slabs: three fixed loads per axis, a loop for the rest
+      const int ax1 = min(ax + 1, bx), ax2 = min(ax + 2, bx), ay1 = min(ay + 1, by), ay2 = min(ay + 2, by);
+      const bool wide = bx - ax > 2 || by - ay > 2;
       for (int w = 0; w <= gi; ++w) {
-        u32 mx = 0u, my = 0u;
-        for (int sl = ax; sl <= bx; ++sl) mx |= slabx[w * kSlabs + sl];
-        for (int sl = ay; sl <= by; ++sl) my |= slaby[w * kSlabs + sl];
+        const u32* px = slabx + w * kSlabs;
+        const u32* py = slaby + w * kSlabs;
+        u32 mx = px[ax] | px[ax1] | px[ax2], my = py[ay] | py[ay1] | py[ay2];
+        if (wide) {
+#pragma unroll 1
+          for (int sl = ax + 3; sl <= bx; ++sl) mx |= px[sl];
+#pragma unroll 1
+          for (int sl = ay + 3; sl <= by; ++sl) my |= py[sl];
+        }
         u32 cand = sane ? (mx & my) : 0u;
         if (w == gi) cand &= (1u << (i & 31)) - 1u;
         u32 bits = 0u;
@@ -730,7 +721,7 @@ static int next_pow2(int v) {
 static size_t nms_smem_bytes(int sortn) {
   const int W = sortn / 32, WP = W | 1;
   return (size_t)sortn * (8 + 16 + 8 + 4) + (size_t)sortn * WP * 4 + 2 * W * 4 + 256 * 4 +
-         (size_t)2 * kSlabs * W * 4 + (4 + 4 * kNmsWarps) * 4 + 128;
+         (size_t)2 * kSlabs * W * 4 + (4 + 4 * kNmsWarps) * 4 + 260 * 4 + 128;
 }
 
 struct DetectWs {
