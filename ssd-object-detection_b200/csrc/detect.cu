@@ -83,11 +83,29 @@ __device__ __forceinline__ float4 decode_row(float4 t, const void* priors, int a
   return o;
 }
 
-// One warp tile: `rows` priors of image b starting at prior 32*j; lane r owns row r.  After the call
-// the rows hold exp(x - max) (or the probabilities when P.probs is set).  kProbs: the rows already hold
-// probabilities.  Scores are  p_c = exp(x_c - max) * (1 / sum)  in float32.
-template <typename TP, bool kProbs>
-__device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j, int rows, float* tile, int lane) {
+// 32x32 bit matrix across the warp: lane r passes row r, lane c receives column c (bit r = bit c of row r).
+__device__ __forceinline__ u32 warp_transpose32(u32 x, int lane) {
+#pragma unroll
+  for (int j = 16; j >= 1; j >>= 1) {
+    const u32 mk = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+    const u32 y = __shfl_xor_sync(SSDG_FULL, x, j);
+    x = (lane & j) ? ((x & ~mk) | ((y >> j) & mk)) : ((x & mk) | ((y << j) & ~mk));
+  }
+  return x;
+}
+
+// One warp tile: `rows` priors of image b starting at prior 32*j.
+//   row phase    lane r owns row r: max, then  e_c = 2^(x_c*log2e - max*log2e)  (one FFMA + MUFU per class; the
+//                rounded constant is the same for every class of the row and cancels in e/sum), the sum, and one
+//                pre-filter bit per class (e_c > thresh can only be necessary: the sum is >= ~1).
+//   class phase  the bit matrix is transposed, lane l now owns classes l, 32+l, 64+l of ALL rows: candidates
+//                cluster in a few rows (weak background) but spread evenly over classes, so the exact test
+//                p_c = e_c * (1/sum) > thresh  and the append loop run with balanced lanes.
+// kWrite: the rows hold e_c afterwards (probabilities output / score head need them); otherwise e_c is
+// recomputed for the few pre-filtered classes.  kProbs: the rows already hold probabilities.
+template <typename TP, bool kProbs, bool kWrite>
+__device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j, int rows, float* tile, float2* aux,
+                                            int lane) {
   const int C = P.C, nfg = P.C - 1;
   const bool valid = lane < rows;
   const int a = j * 32 + lane;
@@ -96,9 +114,8 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
   const float thr = P.score_thresh;
   float4 tbox = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!kProbs && valid && P.boxes) tbox = __ldg(reinterpret_cast<const float4*>(P.pred_box) + n);  // early: hide latency
-  float m = 0.f, inv_s = 1.f;
-  // a class can only be a candidate if exp(x_c - max) > thresh (the sum is >= 1): one bit per class
-  // (first 96 classes in registers; more classes fall back to re-testing every class)
+  float inv_s = 1.f, kexp = 0.f;
+  // first 96 classes as bit words in registers; more classes fall back to re-testing every class
   const float pre = kProbs ? thr : thr * 0.999f;
   u32 bits0 = 0u, bits1 = 0u, bits2 = 0u;
   if (valid) {
@@ -109,17 +126,15 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
         m0 = fmaxf(m0, row[c]); m1 = fmaxf(m1, row[c + 1]); m2 = fmaxf(m2, row[c + 2]); m3 = fmaxf(m3, row[c + 3]);
       }
       for (; c < C; ++c) m0 = fmaxf(m0, row[c]);
-      m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      // exp(x - max) is written back into the row; one pre-filter bit per foreground class
-      const float nml = m;
+      kexp = -fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * SSDG_LOG2E;
       float s0 = 0.f, s1 = 0.f;
       auto chunk32 = [&](int c0) {   // a full word of 32 classes, fully unrolled: the bit positions are immediates
         u32 bits = 0u;
         float* r = row + c0;
 #pragma unroll
         for (int cc = 0; cc < 32; cc += 2) {
-          const float e0 = exp_shifted(r[cc], nml), e1 = exp_shifted(r[cc + 1], nml);
-          r[cc] = e0; r[cc + 1] = e1;
+          const float e0 = exp2_ftz(fmaf(r[cc], SSDG_LOG2E, kexp)), e1 = exp2_ftz(fmaf(r[cc + 1], SSDG_LOG2E, kexp));
+          if (kWrite) { r[cc] = e0; r[cc + 1] = e1; }
           s0 += e0; s1 += e1;
           if (e0 > pre) bits |= 1u << cc;
           if (e1 > pre) bits |= 2u << cc;
@@ -129,8 +144,9 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
       auto chunk = [&](int c0, int cn) {
         u32 bits = 0u;
         for (int cc = 0; cc < cn; ++cc) {
-          const float e0 = exp_shifted(row[c0 + cc], nml);
-          row[c0 + cc] = e0; s0 += e0;
+          const float e0 = exp2_ftz(fmaf(row[c0 + cc], SSDG_LOG2E, kexp));
+          if (kWrite) row[c0 + cc] = e0;
+          s0 += e0;
           if (e0 > pre) bits |= 1u << cc;
         }
         return bits;
@@ -138,7 +154,10 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
       bits0 = nfg >= 32 ? chunk32(0) : chunk(0, nfg);
       if (nfg > 32) bits1 = nfg >= 64 ? chunk32(32) : chunk(32, nfg - 32);
       if (nfg > 64) bits2 = nfg >= 96 ? chunk32(64) : chunk(64, nfg - 64);
-      for (c = min(nfg, 96); c < C; ++c) { const float e0 = exp_shifted(row[c], nml); row[c] = e0; s0 += e0; }
+      for (c = min(nfg, 96); c < C; ++c) {   // background and the classes beyond 96: always stored
+        const float e0 = exp2_ftz(fmaf(row[c], SSDG_LOG2E, kexp));
+        row[c] = e0; s0 += e0;
+      }
       inv_s = __frcp_rn(s0 + s1);
     } else {
       const int lim = min(nfg, 96);
@@ -148,21 +167,36 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
       }
     }
   }
-  // exact test of the pre-filtered classes; count, scan, append
-  auto exact = [&](u32 bits, int c0) {
+  if (!kProbs) aux[lane] = make_float2(kexp, inv_s);
+  // class phase: lane l <-> classes l, 32+l, 64+l; bit r <-> row r
+  u32 t0 = warp_transpose32(bits0, lane);                    // includes the __syncwarp the shared writes need
+  u32 t1 = nfg > 32 ? warp_transpose32(bits1, lane) : 0u;
+  u32 t2 = nfg > 64 ? warp_transpose32(bits2, lane) : 0u;
+  __syncwarp();
+  auto score_at = [&](float* p, int r) {
+    if (kProbs) return *p;
+    const float2 ax = aux[r];
+    return (kWrite ? *p : exp2_ftz(fmaf(*p, SSDG_LOG2E, ax.x))) * ax.y;
+  };
+  auto exact = [&](u32 rb, int c) {   // keeps the rows whose score passes; without kWrite the score replaces the logit
     u32 keep = 0u;
-    while (bits) {
-      const int cc = __ffs(bits) - 1;
-      bits &= bits - 1;
-      if ((kProbs ? row[c0 + cc] : row[c0 + cc] * inv_s) > thr) keep |= 1u << cc;
+    while (rb) {
+      const int r = __ffs(rb) - 1;
+      rb &= rb - 1;
+      float* p = tile + r * C + c;
+      const float sc = score_at(p, r);
+      if (sc > thr) {
+        keep |= 1u << r;
+        if (!kProbs && !kWrite) *p = sc;
+      }
     }
     return keep;
   };
-  bits0 = exact(bits0, 0); bits1 = exact(bits1, 32); bits2 = exact(bits2, 64);
-  int extra = 0;   // classes beyond 96: counted here, emitted below
+  t0 = exact(t0, lane); t1 = exact(t1, 32 + lane); t2 = exact(t2, 64 + lane);
+  int extra = 0;   // classes beyond 96 (row phase layout): counted here, emitted below
   if (valid)
     for (int c = 96; c < nfg; ++c) extra += ((kProbs ? row[c] : row[c] * inv_s) > thr) ? 1 : 0;
-  const int mine = __popc(bits0) + __popc(bits1) + __popc(bits2) + extra;
+  const int mine = __popc(t0) + __popc(t1) + __popc(t2) + extra;
   int incl = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -172,23 +206,24 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
   const size_t tix = (size_t)b * P.tpi + j;
   if (lane == 31) P.tile_cnt[tix] = (u32)incl;
   u64* dst = P.seg + tix * (size_t)(32 * nfg) + (incl - mine);
-  auto emit = [&](u32 bits, int c0) {
-    while (bits) {
-      const int c = c0 + __ffs(bits) - 1;
-      bits &= bits - 1;
-      const float score = kProbs ? row[c] : row[c] * inv_s;
+  auto emit = [&](u32 rb, int c) {
+    while (rb) {
+      const int r = __ffs(rb) - 1;
+      rb &= rb - 1;
+      float* p = tile + r * C + c;
+      const float score = (kProbs || !kWrite) ? *p : *p * aux[r].y;
       const u32 sk = kProbs ? key32(score) : (__float_as_uint(score) | 0x80000000u);   // softmax scores are >= +0
-      *dst++ = ((u64)sk << 32) | (u64)(((u32)c << kABitsD) | (u32)a);
+      *dst++ = ((u64)sk << 32) | (u64)(((u32)c << kABitsD) | (u32)(j * 32 + r));
     }
   };
-  emit(bits0, 0); emit(bits1, 32); emit(bits2, 64);
+  emit(t0, lane); emit(t1, 32 + lane); emit(t2, 64 + lane);
   if (valid)
     for (int c = 96; c < nfg; ++c) {
       const float score = kProbs ? row[c] : row[c] * inv_s;
       if (score > thr) *dst++ = ((u64)key32(score) << 32) | (u64)(((u32)c << kABitsD) | (u32)a);
     }
   if (kProbs || !valid) return;
-  if (P.head_score || P.head_cls || P.head_mask) {
+  if (kWrite && (P.head_score || P.head_cls || P.head_mask)) {
     // models/ssd_model.py:481-488: max foreground probability, arg-max over all classes (first max)
     float best = row[0];
     int arg = 0;
@@ -205,11 +240,11 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
     if (P.head_mask) P.head_mask[n] = (score > P.head_thresh && !(pbg > P.head_thresh)) ? 1 : 0;
   }
   if (P.boxes) reinterpret_cast<float4*>(P.boxes)[n] = decode_row<TP>(tbox, P.priors, a);
-  if (P.probs)
+  if (kWrite && P.probs)
     for (int c = 0; c < C; ++c) row[c] *= inv_s;
 }
 
-template <typename TP, bool kProbs>
+template <typename TP, bool kProbs, bool kWrite>
 __global__ void __launch_bounds__(kFThreads, 2) filter_kernel(DetectParams P, int warps_per_cta) {   // <= 64 registers: leaves room for a matcher CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int C = P.C, A = P.A, tpi = P.tpi;
@@ -217,6 +252,7 @@ __global__ void __launch_bounds__(kFThreads, 2) filter_kernel(DetectParams P, in
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* bufs = reinterpret_cast<float*>(smem_raw);
   u64* bars = reinterpret_cast<u64*>(smem_raw + (size_t)warps_per_cta * tile_floats * 4);
+  float2* aux = reinterpret_cast<float2*>(bars + kFWarps) + 32 * warp;   // per row: -max*log2e, 1/sum
   if (tid == 0) {
     for (int i = 0; i < warps_per_cta; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
@@ -254,9 +290,11 @@ __global__ void __launch_bounds__(kFThreads, 2) filter_kernel(DetectParams P, in
       for (int i = lane; i < rows * C; i += 32) tile[i] = g[i];
       __syncwarp();
     }
-    filter_tile<TP, kProbs>(P, b, j, rows, tile, lane);
+    filter_tile<TP, kProbs, kWrite>(P, b, j, rows, tile, aux, lane);
+    // the next bulk copy (async proxy) overwrites rows this warp has just written
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
-    if (!kProbs && P.probs) {  // the tile layout in shared memory equals the layout in global memory
+    if (!kProbs && kWrite && P.probs) {  // the tile layout in shared memory equals the layout in global memory
       float* dst = P.probs + ((size_t)b * A + (size_t)j * 32) * C;
       for (int i = lane; i < rows * C; i += 32) __stcs(&dst[i], tile[i]);
       __syncwarp();
@@ -710,7 +748,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
 
 static int f_warps_for(int C) {
   const size_t budget = 220 * 1024;
-  int w = (int)(budget / ((size_t)32 * C * 4 + 8));
+  int w = (int)((budget - (size_t)kFWarps * 32 * 8) / ((size_t)32 * C * 4 + 8));
   return w > kFWarps ? kFWarps : w;
 }
 static int next_pow2(int v) {
@@ -752,20 +790,24 @@ template <bool kProbs>
 static int run_filter(DetectParams& P, int prior_dtype, cudaStream_t st) {
   const int warps = f_warps_for(P.C);
   if (warps < 1) return SSDG_ERR_LIMIT;
-  const size_t smem = (size_t)warps * 32 * P.C * 4 + kFWarps * 8 + 128;
+  const size_t smem = (size_t)warps * 32 * P.C * 4 + kFWarps * 8 + (size_t)kFWarps * 32 * 8 + 128;
   int grid = sm_count();
   const long long tiles = (long long)P.B * P.tpi;
   const long long need = (tiles + warps - 1) / warps;
   if (need < grid) grid = (int)need;
   P.tma_ok = (((long long)P.A * P.C) % 4 == 0) && (((uintptr_t)P.pred_cls & 15) == 0);
   prof_begin(SSDG_PROF_FILTER, st);
-  if (prior_dtype == SSDG_F64) {
-    SSDG_CUDA_TRY(cudaFuncSetAttribute(filter_kernel<double, kProbs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    filter_kernel<double, kProbs><<<grid, kFThreads, smem, st>>>(P, warps);
-  } else {
-    SSDG_CUDA_TRY(cudaFuncSetAttribute(filter_kernel<float, kProbs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    filter_kernel<float, kProbs><<<grid, kFThreads, smem, st>>>(P, warps);
-  }
+  // kWrite: the rows must hold exp(x - max) after the pass (probabilities output, score head)
+  const bool wr = !kProbs && (P.probs || P.head_score || P.head_cls || P.head_mask);
+  auto go = [&](auto kern) -> int {
+    SSDG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kFThreads, smem, st>>>(P, warps);
+    return SSDG_OK;
+  };
+  int rc;
+  if (prior_dtype == SSDG_F64) rc = wr ? go(filter_kernel<double, kProbs, true>) : go(filter_kernel<double, kProbs, false>);
+  else rc = wr ? go(filter_kernel<float, kProbs, true>) : go(filter_kernel<float, kProbs, false>);
+  if (rc != SSDG_OK) return rc;
   prof_end(SSDG_PROF_FILTER, st);
   SSDG_LAUNCH_CHECK();
   SSDG_CUDA_TRY(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
