@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--cpu-images", type=int, default=0, help="images in the CPU-baseline sample (0 = host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mining", default="shard", choices=["shard", "global"],
+                    help="hard-negative threshold over this rank's batch (reference split-batch semantics) or "
+                         "over all ranks' batches (exact-global, 5 small all-reduces)")
     return ap.parse_args()
 
 
@@ -137,7 +140,8 @@ def base_line(args, value, ms, n_gpus):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "global_batch": args.batch * n_gpus, "priors": None,
-                       "l2": "inputs larger than L2 (logits %.0f MB per GPU)" % 0.0, "parallelism": "dp%d" % n_gpus}}
+                       "l2": "inputs larger than L2 (logits %.0f MB per GPU)" % 0.0, "parallelism": "dp%d" % n_gpus,
+                       "mining": "per-shard" if getattr(args, "mining", "shard") == "shard" else "exact-global"}}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -223,7 +227,20 @@ def run_ours(args):
     table = synth.TABLES[args.table]
     b = args.batch
     boxes, cls, off = synth.make_gt(100 + rank, b, args.max_gt, args.gt_mode)
-    hp = HotPath(table, batch=b, max_gt=int(np.diff(off).max()), total_gt=boxes.shape[0])
+    tviews = {}
+
+    def allreduce_on(buf, stream):   # exchange words of the cross-shard mining: NCCL, ordered on the loss stream
+        key = (buf.ptr, stream.handle)
+        if key not in tviews:
+            tviews[key] = (torch.as_tensor(buf, device="cuda"), torch.cuda.ExternalStream(stream.handle))
+        t, ts = tviews[key]
+        if world > 1:
+            with torch.cuda.stream(ts):
+                dist.all_reduce(t)
+
+    hp = HotPath(table, batch=b, max_gt=int(np.diff(off).max()), total_gt=boxes.shape[0], mining=args.mining,
+                 global_priors=b * world * synth.num_priors(table) if args.mining == "global" else None,
+                 allreduce=allreduce_on if args.mining == "global" else None)
     a, c = hp.A, hp.classes
     # pinned host copies of one batch (also the source of the resident copy)
     h = {"gt_boxes": D.PinnedArray(boxes.shape, np.float32), "gt_cls": D.PinnedArray(cls.shape, np.float32),
@@ -247,7 +264,7 @@ def run_ours(args):
     res_t = torch.as_tensor(hp.loss["result"], device="cuda")
 
     def exchange():
-        if world > 1:
+        if world > 1 and args.mining == "shard":
             with torch.cuda.stream(s_main_t):
                 dist.all_reduce(res_t[4:11])
 
@@ -374,7 +391,10 @@ def run_ours(args):
              "match_pairs_per_s": (float(np.diff(off).sum()) * a) / (kernel_ms.get(N.PROF_MATCH, 0) * 1e-3)
              if kernel_ms.get(N.PROF_MATCH) else None,
              "chain_bytes_per_image": a * (c * 4 * 2 + 16 * 3 + 4 + 1 + 4 + 16 + 1),
-             "loss": {"total": res[0], "num_pos": res[4], "num_neg": res[5], "status": res[7]}}
+             "loss": ({"total": res[0], "num_pos": res[4], "num_neg": res[5], "status": res[7], "scope": "this rank"}
+                      if args.mining == "shard" else
+                      {"total": (res[8] + res[10]) / res[11] + res[9] / res[5], "num_pos": res[11], "num_neg": res[5],
+                       "status": res[7], "scope": "all ranks (exact-global mining)"})}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -180,7 +180,7 @@ SSDG_API int ssdg_iou_pairs(const void* boxes_1, int32_t dtype_1, const void* bo
  *   [7] status: 0 OK, SSDG_ERR_NO_POSITIVE, SSDG_ERR_TOPK_RANGE, SSDG_ERR_POS_NEG_OVERLAP
  *       (then [0..3] are NaN)
  *   [8] sum of positive CE [9] sum of mined-negative CE [10] sum of positive L1 (the separable
- *   sums a data-parallel caller all-reduces together with [4],[5])
+ *   sums a data-parallel caller all-reduces together with [4],[5]) [11] this shard's own positives
  * out_neg_mask (optional) uint8 [B,A]: the mined negative mask.
  * out_neg_ce   (optional) float [B,A]: per-prior background CE * (1-pos) (the mining input).
  * grad_box / grad_cls (optional, both or neither): d total / d pred_box, d total / d pred_cls --
@@ -193,6 +193,26 @@ SSDG_API int ssdg_multibox_loss(const int32_t* gt_cls, const float* gt_box, cons
                        int32_t n_priors, int32_t n_classes, int32_t neg_ratio, double* out_result,
                        uint8_t* out_neg_mask, float* out_neg_ce, float* grad_box, float* grad_cls,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Cross-shard (exact batch-global) mining: the same loss when the batch of models/ssd_model.py:341-396 is
+ * split over several devices and the threshold of :368-372 must still be the k-th largest background CE
+ * of the WHOLE batch ("exact-global option").  The loss runs in four stages; between
+ * them the caller sums one exchange buffer over the shards (ncclAllReduce / torch.distributed, in place):
+ *   stage 0  CE pass                 then sum  exchange 3 (int64 x1: positives) and exchange 0 (int32 x2048)
+ *   stage 1  radix level 1           then sum  exchange 1 (int32 x2048)
+ *   stage 2  radix level 2           then sum  exchange 2 (int32 x2048)
+ *   stage 3  mask, sums, result      then sum  out_result[8..11] and [5]:  loss = ([8] + [10]) / sum[11] + [9] / sum[5]
+ * Every stage takes the arguments of ssdg_multibox_loss (same buffers each time) plus global_priors =
+ * sum over shards of batch * n_priors.  After stage 3 out_result[4] is the global positive count, [11] the
+ * shard's own, [6] the global threshold, and out_neg_mask equals the single-device mask of the whole batch.
+ */
+SSDG_API int ssdg_multibox_loss_stage(int32_t stage, int64_t global_priors, const int32_t* gt_cls,
+                       const float* gt_box, const uint8_t* gt_mask, const float* pred_box,
+                       const float* pred_cls, int64_t batch, int32_t n_priors, int32_t n_classes,
+                       int32_t neg_ratio, double* out_result, uint8_t* out_neg_mask, float* out_neg_ce,
+                       float* grad_box, float* grad_cls, void* workspace, size_t workspace_bytes,
+                       void* stream);
+SSDG_API int ssdg_loss_exchange(void* workspace, int32_t which, void** out_ptr, int64_t* out_count);
 
 /* ---- A7+A8+A9: post-processing ------------------------------------------------------------------------
  * Replaces the head of SSDObjectDetectionModel.visualize            models/ssd_model.py:477-490

@@ -12,6 +12,7 @@
 //                  (:375), deterministic reduction of the per-CTA partials, result block.
 //   grad_kernel    optional second pass: d total / d logits and d total / d pred_box (:248).
 #include <math_constants.h>
+#include <cstddef>
 #include "common.cuh"
 
 namespace ssdg {
@@ -29,6 +30,8 @@ struct LossWs {
   u32 hist[3][kBins];       // the three radix levels
   u32 ticket[4];            // last-block-done counters
   u32 nparts[4];            // grid sizes used
+  unsigned long long xnpos; // number of positives as an integer: the exchange word of the cross-shard mining
+  unsigned long long xpad;
 };
 
 struct LossParams {
@@ -45,6 +48,8 @@ struct LossParams {
   LossWs* ws;
   float* grad_box;
   float* grad_cls;
+  long long N_all;      // priors of the whole (cross-shard) batch; == N for single-shard mining
+  int global;           // 1: num_pos and the histograms in the workspace are cross-shard sums
 };
 
 __device__ __forceinline__ u64 make_evict_first_policy() {
@@ -177,6 +182,7 @@ __global__ void __launch_bounds__(kCeThreads, 1) ce_kernel(LossParams P, int war
     for (int w = 0; w < kCeWarps; ++w) { sa += red[w]; sb += red[kCeWarps + w]; sc += red[2 * kCeWarps + w]; }
     P.ws->part[blockIdx.x][0] = sa; P.ws->part[blockIdx.x][1] = sb; P.ws->part[blockIdx.x][2] = sc;
     if (blockIdx.x == 0) P.ws->nparts[0] = gridDim.x;
+    atomicAdd(&P.ws->xnpos, (unsigned long long)sc);   // integer, order-independent
   }
   for (int i = tid; i < kBins; i += kCeThreads) {
     u32 v = hist[i];
@@ -242,12 +248,12 @@ __device__ void derive_state(const LossParams& P, int levels_done, SelectState& 
     if (tid == 0) { *sh_np = np; *sh_bin = 0; *sh_above = 0; }
   }
   __syncthreads();
-  st.num_pos = *sh_np;
+  st.num_pos = P.global ? (double)P.ws->xnpos : *sh_np;
   st.k = (long long)P.ratio * (long long)st.num_pos;
   st.prefix = 0;
   st.status = 0;
   if (st.num_pos <= 0 || P.ratio <= 0) { st.status = SSDG_ERR_NO_POSITIVE; return; }
-  if (st.k > P.N) { st.status = SSDG_ERR_TOPK_RANGE; return; }
+  if (st.k > P.N_all) { st.status = SSDG_ERR_TOPK_RANGE; return; }
   if (levels_done >= 1) st.prefix = (u32)scan_level(P.ws->hist[0], kBins, st.k, sh, tid, nthreads, sh_bin, sh_above) << 21;
   if (levels_done >= 2) st.prefix |= (u32)scan_level(P.ws->hist[1], kBins, st.k, sh, tid, nthreads, sh_bin, sh_above) << 10;
   if (levels_done >= 3) st.prefix |= (u32)scan_level(P.ws->hist[2], 1024, st.k, sh, tid, nthreads, sh_bin, sh_above);
@@ -387,7 +393,8 @@ __global__ void __launch_bounds__(256) final_kernel(LossParams P) {
   r[6] = status ? nan : (double)unkey32(kth);
   r[7] = (double)status;
   r[8] = s_pos; r[9] = s_neg; r[10] = s_l1;
-  for (int i = 11; i < SSDG_LOSS_RESULT_LEN; ++i) r[i] = 0;
+  r[11] = sh_np;   // this shard's own positives (== r[4] unless the mining is cross-shard)
+  for (int i = 12; i < SSDG_LOSS_RESULT_LEN; ++i) r[i] = 0;
 }
 
 // ---- gradient (models/ssd_model.py:248 through :355-386) ---------------------------------------------
@@ -463,11 +470,13 @@ extern "C" size_t ssdg_loss_workspace_bytes(int64_t batch, int32_t n_priors, int
   return align_up(sizeof(LossWs), 256) + align_up((size_t)batch * n_priors * 4, 256);
 }
 
-extern "C" int ssdg_multibox_loss(const int32_t* gt_cls, const float* gt_box, const uint8_t* gt_mask,
-                                  const float* pred_box, const float* pred_cls, int64_t batch, int32_t n_priors,
-                                  int32_t n_classes, int32_t neg_ratio, double* out_result, uint8_t* out_neg_mask,
-                                  float* out_neg_ce, float* grad_box, float* grad_cls, void* workspace,
-                                  size_t workspace_bytes, void* stream) {
+// stages: 1 = CE pass (+ level-0 histogram, positives count), 2 / 4 = radix levels 1 / 2, 8 = mask, sums, result
+// (+ gradient).  Between the stages of a cross-shard run the caller sums the exchange words over the shards.
+static int loss_run(int stages, int global, long long n_all, const int32_t* gt_cls, const float* gt_box,
+                    const uint8_t* gt_mask, const float* pred_box, const float* pred_cls, int64_t batch,
+                    int32_t n_priors, int32_t n_classes, int32_t neg_ratio, double* out_result, uint8_t* out_neg_mask,
+                    float* out_neg_ce, float* grad_box, float* grad_cls, void* workspace, size_t workspace_bytes,
+                    void* stream) {
   if (!gt_cls || !gt_box || !gt_mask || !pred_box || !pred_cls || !out_result) return SSDG_ERR_ARG;
   if (batch <= 0 || n_priors <= 0 || n_classes < 2 || neg_ratio <= 0) return SSDG_ERR_ARG;
   if ((grad_box == nullptr) != (grad_cls == nullptr)) return SSDG_ERR_ARG;
@@ -480,35 +489,73 @@ extern "C" int ssdg_multibox_loss(const int32_t* gt_cls, const float* gt_box, co
   LossParams P;
   P.gt_cls = gt_cls; P.gt_box = gt_box; P.gt_mask = gt_mask; P.pred_box = pred_box; P.pred_cls = pred_cls;
   P.N = (long long)batch * n_priors; P.C = n_classes; P.ratio = neg_ratio;
+  P.N_all = global ? n_all : P.N; P.global = global;
+  if (P.N_all < P.N) return SSDG_ERR_ARG;
   P.ws = (LossWs*)workspace;
   P.neg_ce = out_neg_ce ? out_neg_ce : (float*)((unsigned char*)workspace + align_up(sizeof(LossWs), 256));
   P.neg_mask = out_neg_mask; P.result = out_result; P.grad_box = grad_box; P.grad_cls = grad_cls;
-  SSDG_CUDA_TRY(cudaMemsetAsync(&P.ws->hist[0][0], 0, sizeof(P.ws->hist) + sizeof(P.ws->ticket) + sizeof(P.ws->nparts), st));
-  const size_t smem = ce_smem_bytes(n_classes, warps);
-  SSDG_CUDA_TRY(cudaFuncSetAttribute(ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = sm_count();
-  if (grid > 256) grid = 256;
-  const long long tiles = (P.N + 31) / 32;
-  const long long need = (tiles + warps - 1) / warps;
-  if (need < grid) grid = (int)need;
-  prof_begin(SSDG_PROF_CE, st);
-  ce_kernel<<<grid, kCeThreads, smem, st>>>(P, warps);
-  prof_end(SSDG_PROF_CE, st);
-  SSDG_LAUNCH_CHECK();
+  if (stages & 1) {
+    SSDG_CUDA_TRY(cudaMemsetAsync(&P.ws->hist[0][0], 0, sizeof(LossWs) - offsetof(LossWs, hist), st));
+    const size_t smem = ce_smem_bytes(n_classes, warps);
+    SSDG_CUDA_TRY(cudaFuncSetAttribute(ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = sm_count();
+    if (grid > 256) grid = 256;
+    const long long tiles = (P.N + 31) / 32;
+    const long long need = (tiles + warps - 1) / warps;
+    if (need < grid) grid = (int)need;
+    prof_begin(SSDG_PROF_CE, st);
+    ce_kernel<<<grid, kCeThreads, smem, st>>>(P, warps);
+    prof_end(SSDG_PROF_CE, st);
+    SSDG_LAUNCH_CHECK();
+  }
   int sgrid = sm_count() * 4;
   const long long sneed = (P.N / 4 + 255) / 256;
   if (sneed < sgrid) sgrid = (int)(sneed > 0 ? sneed : 1);
   if (sgrid > 1024) sgrid = 1024;
-  SSDG_CUDA_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  SSDG_CUDA_TRY(cudaFuncSetAttribute(final_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  select_kernel<<<sgrid, 256, 0, st>>>(P, 1);
-  select_kernel<<<sgrid, 256, 0, st>>>(P, 2);
-  final_kernel<<<sgrid, 256, 0, st>>>(P);
-  SSDG_LAUNCH_CHECK();
-  if (grad_cls) {
-    int ggrid = sm_count() * 8;
-    grad_kernel<<<ggrid, 256, 0, st>>>(P);
+  if (stages & 6) {
+    SSDG_CUDA_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (stages & 2) select_kernel<<<sgrid, 256, 0, st>>>(P, 1);
+    if (stages & 4) select_kernel<<<sgrid, 256, 0, st>>>(P, 2);
     SSDG_LAUNCH_CHECK();
   }
+  if (stages & 8) {
+    SSDG_CUDA_TRY(cudaFuncSetAttribute(final_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    final_kernel<<<sgrid, 256, 0, st>>>(P);
+    SSDG_LAUNCH_CHECK();
+    if (grad_cls) {
+      int ggrid = sm_count() * 8;
+      grad_kernel<<<ggrid, 256, 0, st>>>(P);
+      SSDG_LAUNCH_CHECK();
+    }
+  }
+  return SSDG_OK;
+}
+
+extern "C" int ssdg_multibox_loss(const int32_t* gt_cls, const float* gt_box, const uint8_t* gt_mask,
+                                  const float* pred_box, const float* pred_cls, int64_t batch, int32_t n_priors,
+                                  int32_t n_classes, int32_t neg_ratio, double* out_result, uint8_t* out_neg_mask,
+                                  float* out_neg_ce, float* grad_box, float* grad_cls, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  return loss_run(15, 0, 0, gt_cls, gt_box, gt_mask, pred_box, pred_cls, batch, n_priors, n_classes, neg_ratio,
+                  out_result, out_neg_mask, out_neg_ce, grad_box, grad_cls, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ssdg_multibox_loss_stage(int32_t stage, int64_t global_priors, const int32_t* gt_cls,
+                                        const float* gt_box, const uint8_t* gt_mask, const float* pred_box,
+                                        const float* pred_cls, int64_t batch, int32_t n_priors, int32_t n_classes,
+                                        int32_t neg_ratio, double* out_result, uint8_t* out_neg_mask,
+                                        float* out_neg_ce, float* grad_box, float* grad_cls, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  if (stage < 0 || stage > 3 || global_priors <= 0) return SSDG_ERR_ARG;
+  return loss_run(1 << stage, 1, global_priors, gt_cls, gt_box, gt_mask, pred_box, pred_cls, batch, n_priors,
+                  n_classes, neg_ratio, out_result, out_neg_mask, out_neg_ce, grad_box, grad_cls, workspace,
+                  workspace_bytes, stream);
+}
+
+extern "C" int ssdg_loss_exchange(void* workspace, int32_t which, void** out_ptr, int64_t* out_count) {
+  if (!workspace || !out_ptr || !out_count || which < 0 || which > 3) return SSDG_ERR_ARG;
+  LossWs* ws = (LossWs*)workspace;
+  if (which < 3) { *out_ptr = &ws->hist[which][0]; *out_count = kBins; }     // int32 counts
+  else { *out_ptr = &ws->xnpos; *out_count = 1; }                           // int64 count
   return SSDG_OK;
 }

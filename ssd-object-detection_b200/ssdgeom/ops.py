@@ -198,6 +198,97 @@ def multibox_loss(gt_cls, gt_box, gt_mask, pred_box, pred_cls, neg_ratio: int = 
     return out
 
 
+class StagedLoss:
+    """The multibox loss of one shard of a batch whose hard-negative threshold is mined over ALL shards
+    (include/ssdgeom.h, ssdg_multibox_loss_stage).  Usage, on every shard:
+
+        sl = StagedLoss(gt_cls, gt_box, gt_mask, pred_box, pred_cls, global_priors=sum of b*A over shards)
+        for stage in range(4):
+            sl.run(stage)
+            for buf in sl.exchange(stage):      # device buffers (int32 / int64 / float64)
+                <sum buf over the shards, in place>
+        total, info = sl.finish()
+
+    The buffers are DeviceArrays over the workspace / result block, so a torch.distributed all_reduce on
+    torch.as_tensor(buf) works in place without a copy."""
+
+    def __init__(self, gt_cls, gt_box, gt_mask, pred_box, pred_cls, global_priors: int, neg_ratio: int = 3,
+                 want_neg_mask=False, want_neg_ce=False, want_grad=False, stream=None, ws_kind="loss_staged", out=None):
+        self.gt_cls = D.as_device(gt_cls, np.int32)
+        self.gt_box = D.as_device(gt_box, np.float32)
+        self.gt_mask = D.as_device(gt_mask, np.uint8)
+        self.pred_box = D.as_device(pred_box, np.float32)
+        self.pred_cls = D.as_device(pred_cls, np.float32)
+        if len(self.pred_cls.shape) != 3:
+            raise AssertionError("pred_cls must be [B,A,C]")
+        b, a, c = self.pred_cls.shape
+        if not (self.gt_cls.size == b * a and self.gt_mask.size == b * a and self.gt_box.size == b * a * 4
+                and self.pred_box.size == b * a * 4):
+            raise AssertionError("y_true / y_pred disagree in shape")
+        self.shape = (b, a, c)
+        self.global_priors = int(global_priors)
+        self.neg_ratio = int(neg_ratio)
+        self.stream = stream
+        self.out = dict(out or {})
+        if "result" not in self.out:
+            self.out["result"] = D.empty((N.LOSS_RESULT_LEN,), np.float64)
+        self._xb = {}
+        if want_neg_mask:
+            self.out["neg_mask"] = D.empty((b, a), np.uint8)
+        if want_neg_ce:
+            self.out["neg_ce"] = D.empty((b, a), np.float32)
+        if want_grad:
+            self.out["grad_box"] = D.empty((b, a, 4), np.float32)
+            self.out["grad_cls"] = D.empty((b, a, c), np.float32)
+        lib = N.lib()
+        self.ws = POOL.get(ws_kind, lib.ssdg_loss_workspace_bytes(b, a, c))
+
+    def run(self, stage: int):
+        b, a, c = self.shape
+        o = self.out
+        N.check(N.lib().ssdg_multibox_loss_stage(
+            int(stage), self.global_priors, self.gt_cls.ptr, self.gt_box.ptr, self.gt_mask.ptr, self.pred_box.ptr,
+            self.pred_cls.ptr, b, a, c, self.neg_ratio, o["result"].ptr, _p(o.get("neg_mask")), _p(o.get("neg_ce")),
+            _p(o.get("grad_box")), _p(o.get("grad_cls")), self.ws.ptr, self.ws.nbytes,
+            D.stream_handle(self.stream)), "multibox_loss_stage")
+
+    def _xbuf(self, which: int, dtype):
+        import ctypes as C
+        ptr, cnt = C.c_void_p(), C.c_int64()
+        N.check(N.lib().ssdg_loss_exchange(self.ws.ptr, which, C.byref(ptr), C.byref(cnt)), "loss_exchange")
+        return D.DeviceArray((int(cnt.value),), dtype, ptr=ptr.value, owner=self.ws)
+
+    def exchange(self, stage: int):
+        """Buffers to sum over the shards after `stage` (in place)."""
+        if stage not in self._xb:
+            self._xb[stage] = self._exchange(stage)
+        return self._xb[stage]
+
+    def _exchange(self, stage: int):
+        if stage == 0:
+            return [self._xbuf(3, np.int64), self._xbuf(0, np.int32)]
+        if stage in (1, 2):
+            return [self._xbuf(stage, np.int32)]
+        r = self.out["result"]
+        # the separable sums [8..10], the shard's own positives [11] and its mined negatives [5]
+        return [D.DeviceArray((4,), np.float64, ptr=r.ptr + 8 * 8, owner=r),
+                D.DeviceArray((1,), np.float64, ptr=r.ptr + 5 * 8, owner=r)]
+
+    def finish(self) -> tuple:
+        """After the stage-3 exchange: (total, info) of the whole batch, identical on every shard."""
+        r = self.out["result"].to_host(self.stream)
+        status = int(r[7])
+        if status == N.ERR_NO_POSITIVE:
+            raise IndexError("no positive prior in the batch: hard-negative top-k is empty (models/ssd_model.py:369)")
+        if status == N.ERR_TOPK_RANGE:
+            raise ValueError("3*num_pos exceeds the number of priors in the batch (tf.math.top_k, models/ssd_model.py:368)")
+        N.check(status, "multibox_loss_stage")
+        s_pos, s_neg, s_l1, n_pos, n_neg = r[8], r[9], r[10], r[11], r[5]
+        l_pos, l_neg, l_loc = s_pos / n_pos, s_neg / n_neg, s_l1 / n_pos
+        return (l_loc + l_pos) + l_neg, {"cls loss pos": l_pos, "cls loss neg": l_neg, "loc loss": l_loc,
+                                          "num_pos": int(n_pos), "num_neg": int(n_neg), "kth": r[6]}
+
+
 def loss_result_to_host(result: D.DeviceArray, stream=None) -> dict:
     """One synchronising read of the result block; raises like the reference on the device-side
     guards (num_pos == 0 -> IndexError at models/ssd_model.py:369; k out of range -> top_k error)."""

@@ -9,6 +9,11 @@ and calls ``_ssd_loss`` per slice (models/ssd_model.py:235-256).  ``combine_loss
 normalisations: ``pooled`` (sums and counts pooled over all shards) and ``mean_of_shards`` (the
 reference's accumulate-and-average of per-slice losses, :251-256).
 
+``global_mining_loss`` is the exact alternative: the threshold of :368-372 is the
+k-th largest background CE of the WHOLE batch, found by a radix select whose three 2048-bin histograms are
+summed over the shards between the stages of ``ops.StagedLoss`` -- five small all-reduces, after which the
+mined mask of every shard equals the corresponding slice of the single-device mask, bit for bit.
+
 torch is imported lazily: only callers that use torch.distributed need it."""
 from __future__ import annotations
 
@@ -87,3 +92,33 @@ def distributed_loss(result_block_tensor, group=None, mode="pooled"):
         v = (vec.double().cpu().numpy()) / world
         return float(v[0]), {"cls loss pos": float(v[1]), "cls loss neg": float(v[2]), "loc loss": float(v[3])}
     raise ValueError("mode must be 'pooled' or 'mean_of_shards'")
+
+
+def global_mining_loss(staged, allreduce):
+    """Drive a staged loss (``ops.StagedLoss`` or anything with run / exchange / finish) through the four
+    stages of the cross-shard mining protocol.  ``allreduce(buf)`` sums one exchange buffer over the shards
+    in place; every shard must call this function collectively.  Returns (total, info) of the whole batch."""
+    for stage in range(4):
+        staged.run(stage)
+        for buf in staged.exchange(stage):
+            allreduce(buf)
+    return staged.finish()
+
+
+def torch_allreduce(group=None, device="cuda"):
+    """allreduce callable for ``global_mining_loss``: zero-copy torch view of a device buffer (anything with
+    __cuda_array_interface__) or of a NumPy array (gloo), summed over ``group``."""
+    import torch
+    import torch.distributed as dist
+
+    def run(buf):
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return buf
+        if isinstance(buf, np.ndarray):
+            t = torch.from_numpy(buf)
+        else:
+            t = torch.as_tensor(buf, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return buf
+
+    return run

@@ -14,7 +14,12 @@ from .models.ssd_model import SSD300
 
 class HotPath:
     def __init__(self, table=None, batch=256, max_gt=100, classes=81, thresh=0.5, neg_ratio=3,
-                 score_thresh=0.01, top_k=200, iou_thresh=0.45, total_gt=None):
+                 score_thresh=0.01, top_k=200, iou_thresh=0.45, total_gt=None, mining="shard", global_priors=None,
+                 allreduce=None):
+        """mining: "shard" -- the hard-negative threshold is mined over this process's batch (what the reference
+        does per slice under split_batch); "global" -- over the batches of all data-parallel processes
+        (ops.StagedLoss; ``allreduce(buf, stream)`` must sum a device buffer over the processes in stream order
+        and ``global_priors`` is the total number of priors over all of them)."""
         table = SSD300 if table is None else table
         self.batch, self.max_gt, self.classes = int(batch), int(max_gt), int(classes)
         self.thresh, self.neg_ratio = float(thresh), int(neg_ratio)
@@ -37,6 +42,15 @@ class HotPath:
         # branch fills the gaps
         self.s_main, self.s_a, self.s_d = D.Stream(), D.Stream("low"), D.Stream("high")
         self.ev_begin, self.ev_a, self.ev_d, self.ev_mid = D.Event(), D.Event(), D.Event(), D.Event()
+        if mining not in ("shard", "global"):
+            raise ValueError("mining must be 'shard' or 'global'")
+        self.mining, self.allreduce = mining, allreduce
+        self.staged = None
+        if mining == "global":
+            if allreduce is None or not global_priors:
+                raise ValueError("global mining needs allreduce and global_priors")
+            self.staged = ops.StagedLoss(self.tgt["cls"], self.tgt["loc"], self.tgt["mask"], self.pred_box, self.pred_cls,
+                                         int(global_priors), self.neg_ratio, out=self.loss)
         self.stagger = False   # measured: co-running the matcher with nms_kernel is slower than with the filter pass
         self.kernel_launches_per_step = 8   # match | ce, select x2, final | filter, bucket, nms
         self.h2d_bytes = (self.gt_boxes.nbytes + self.gt_cls.nbytes + self.gt_off.nbytes + self.pred_cls.nbytes +
@@ -49,6 +63,13 @@ class HotPath:
                          want=(), out=self.tgt, stream=stream)
 
     def loss_stage(self, stream):
+        if self.staged is not None:
+            self.staged.stream = stream
+            for stage in range(4):
+                self.staged.run(stage)
+                for buf in self.staged.exchange(stage):
+                    self.allreduce(buf, stream)
+            return
         ops.multibox_loss(self.tgt["cls"], self.tgt["loc"], self.tgt["mask"], self.pred_box, self.pred_cls,
                           self.neg_ratio, out=self.loss, stream=stream)
 
