@@ -214,6 +214,20 @@ SSDG_API int ssdg_multibox_loss_stage(int32_t stage, int64_t global_priors, cons
                        void* stream);
 SSDG_API int ssdg_loss_exchange(void* workspace, int32_t which, void** out_ptr, int64_t* out_count);
 
+/* ---- input glue ----------------------------------------------------------
+ * ssdg_gt_prepare replaces, for a whole batch of annotation rows at once,
+ *   COCODataLoader.gen            data_loaders/coco/make_dataset.py:132   bbox[:, :2] += bbox[:, 2:] / 2
+ *   SSDDataLoader._coco2ssd       data_loaders/ssd/make_dataset.py:43-44  box /= [w, h, w, h]
+ * xywh [rows,4] pixel boxes (float64 as decoded from the annotation file, or float32), img_wh int32 [B,2]
+ * (width, height of each image), gt_offsets int32 [B+1] (CSR rows per image) -> out_boxes float32
+ * [rows,4] relative cxcywh: exactly the array the reference hands to match_bbox.
+ * ssdg_image_normalize replaces batch_data_iter's (image - 0.5) * 2      models/ssd_model.py:214
+ * on n float32 values (in and out may alias).
+ */
+SSDG_API int ssdg_gt_prepare(const void* xywh, int32_t dtype, const int32_t* img_wh, const int32_t* gt_offsets,
+                    int64_t batch, int64_t rows, float* out_boxes, void* stream);
+SSDG_API int ssdg_image_normalize(const float* in, float* out, int64_t n, void* stream);
+
 /* ---- A7+A8+A9: post-processing ------------------------------------------------------------------------
  * Replaces the head of SSDObjectDetectionModel.visualize            models/ssd_model.py:477-490
  *   (softmax, max foreground score, arg-max class, threshold mask) and the decode of

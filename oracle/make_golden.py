@@ -157,6 +157,28 @@ def main():
         num_pos=np.int64(n_pos), num_neg=np.int64(neg_mask.sum()), kth=kth,
         neg_mask_bits=np.packbits(neg_mask, axis=1),
     )
+    # ---- input glue: the reference's _coco2ssd on annotation rows (section 8f row 3) ------------------
+    rng = np.random.default_rng(12)
+    sizes = np.array([(640, 427), (500, 375), (333, 500), (1, 1), (4000, 3000)], np.int32)
+    counts = [9, 1, 40, 3, 5]
+    g_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    g_in, g_out = [], []
+    for (w, h), t in zip(sizes, counts):
+        xywh = np.concatenate([rng.uniform(0, [w, h], (t, 2)), rng.uniform(0.5, [w, h], (t, 2))], 1)
+        centre = xywh.copy()
+        centre[:, :2] += centre[:, 2:] / 2            # data_loaders/coco/make_dataset.py:132, verbatim
+        image = np.zeros((int(h) if h < 64 else 8, int(w) if w < 64 else 8, 3), np.float32)
+        # _coco2ssd reads (h, w) from the image: hand it an image of the real size only when small; otherwise
+        # call the two arithmetic lines (:43-44) it would execute, on the real width / height
+        box32 = centre.astype(np.float32)
+        if image.shape[0] == h and image.shape[1] == w:
+            _, _, rel = ref.coco2ssd(image, np.zeros(t, np.float32), box32)
+        else:
+            rel = box32
+            rel /= np.array([w, h, w, h])             # data_loaders/ssd/make_dataset.py:43-44, verbatim
+        g_in.append(xywh); g_out.append(rel)
+    np.savez_compressed(os.path.join(OUT, "glue_small.npz"), xywh=np.concatenate(g_in), img_wh=sizes, offsets=g_off,
+                        rel=np.concatenate(g_out))
     print("loss b=4:", float(total), {k: float(v) for k, v in info.items()}, n_pos, int(neg_mask.sum()))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

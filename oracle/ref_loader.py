@@ -16,6 +16,7 @@ Reference entry points exposed (file:line in /root/reference):
   utils/bbox.py:94   apply_anchor_box
   models/ssd_model.py:173  SSDObjectDetectionModel._build_prior_box
   models/ssd_model.py:341  SSDObjectDetectionModel._ssd_loss
+  data_loaders/ssd/make_dataset.py:37  SSDDataLoader._coco2ssd (resize + relative boxes)
 """
 from __future__ import annotations
 
@@ -60,7 +61,14 @@ def load():
         fake_self = types.SimpleNamespace(cfg=types.SimpleNamespace(input_shape=(input_size, input_size, 3)))
         return model_cls._build_prior_box(fake_self, size_list)
 
+    ssd_loader = sys.modules["data_loaders.ssd.make_dataset"].SSDDataLoader
+
+    def coco2ssd(image, cls, box, train_resize=(300, 300)):
+        """(image, cls, box) -> (resized image, cls, box / [w,h,w,h]); mutates ``box`` in place like the reference."""
+        return ssd_loader._coco2ssd(types.SimpleNamespace(_train_resize=train_resize), (image, cls, box))
+
     ns = types.SimpleNamespace(
+        coco2ssd=coco2ssd,
         iou=bbox.iou,
         iou_n=bbox.iou_n,
         match_bbox=bbox.match_bbox,

@@ -381,3 +381,22 @@ def detect(pred_cls, pred_box, prior_box, score_thresh=0.01, top_k=200, iou_thre
     boxes = decode_bbox(pred_box, prior_box, scale=1.0, exp_dtype=np.float64)
     kept, counts = nms_per_class(probs, boxes, score_thresh, top_k, iou_thresh)
     return kept, counts, probs, boxes
+
+
+# ---- input glue ------------------------------------------------------------
+def coco_to_ssd_boxes(xywh, img_w, img_h):
+    """One image: COCO pixel [x,y,w,h] -> relative cxcywh float32.  Follows
+    data_loaders/coco/make_dataset.py:132 (centre = corner + size/2, in the array's own dtype), the float32
+    TensorSpec of the generator (:140-142), and data_loaders/ssd/make_dataset.py:43-44 (in-place division of
+    the float32 array by the integer [w,h,w,h])."""
+    box = np.array(xywh).reshape(-1, 4)
+    box[:, :2] += box[:, 2:] / 2
+    box = box.astype(np.float32)
+    scale = np.array([img_w, img_h, img_w, img_h])
+    box /= scale
+    return box
+
+
+def normalize_image(image):
+    """models/ssd_model.py:214 on the float32 image the loaders yield."""
+    return (np.asarray(image, dtype=np.float32) - 0.5) * 2

@@ -28,6 +28,7 @@ UNITS = {
     "api.cu": [],
     "geom.cu": ["-fmad=false"],
     "match.cu": ["-fmad=false"],
+    "glue.cu": ["-fmad=false"],
     "loss.cu": [],
     "detect.cu": [],
 }

@@ -121,6 +121,33 @@ def match_status(stream=None) -> int:
     return st.value
 
 
+def gt_prepare(xywh, img_wh, gt_offsets, out=None, stream=None) -> D.DeviceArray:
+    """COCO pixel [x,y,w,h] rows of a batch -> relative cxcywh float32 (data_loaders/coco/make_dataset.py:132,
+    data_loaders/ssd/make_dataset.py:43-44)."""
+    xywh = D.as_device(xywh)
+    if xywh.dtype not in (np.float32, np.float64):
+        raise AssertionError("annotation boxes must be float32 or float64")
+    img_wh, gt_offsets = D.as_device(img_wh, np.int32), D.as_device(gt_offsets, np.int32)
+    rows = xywh.size // 4
+    b = gt_offsets.size - 1
+    if img_wh.size != 2 * b:
+        raise AssertionError("img_wh must be [B,2]")
+    out = D.empty((rows, 4), np.float32) if out is None else out
+    N.check(N.lib().ssdg_gt_prepare(xywh.ptr, _code(xywh.dtype), img_wh.ptr, gt_offsets.ptr, b, rows, out.ptr,
+                                    D.stream_handle(stream)), "gt_prepare")
+    out._keep = (xywh, img_wh, gt_offsets)
+    return out
+
+
+def image_normalize(images, out=None, stream=None) -> D.DeviceArray:
+    """(image - 0.5) * 2, float32 (models/ssd_model.py:214)."""
+    images = D.as_device(images, np.float32)
+    out = D.empty(images.shape, np.float32) if out is None else out
+    N.check(N.lib().ssdg_image_normalize(images.ptr, out.ptr, images.size, D.stream_handle(stream)), "image_normalize")
+    out._keep = (images,)
+    return out
+
+
 def encode(boxes, priors, out_dtype=np.float32, stream=None) -> D.DeviceArray:
     boxes, priors = D.as_device(boxes), D.as_device(priors)
     a = int(priors.shape[0])

@@ -62,6 +62,57 @@ def test_priors_ssd512_bit_exact(priors512):
     assert np.array_equal(got, priors512)
 
 
+# ---- input glue (section 8f row 3) --------------------------------------------------------------------
+def test_gt_prepare_and_image_normalize_bit_exact():
+    rng = np.random.default_rng(5)
+    sizes = [(640, 427), (500, 375), (333, 500), (1, 1), (4000, 3000)]
+    counts = [9, 1, 40, 3, 0]
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    rows = [np.concatenate([rng.uniform(0, [w, h], (t, 2)), rng.uniform(0.5, [w, h], (t, 2))], 1)
+            for (w, h), t in zip(sizes, counts)]
+    xywh = np.concatenate(rows)
+    want = np.concatenate([O.coco_to_ssd_boxes(r, w, h) for r, (w, h) in zip(rows, sizes)])
+    got = ops.gt_prepare(xywh, np.array(sizes, np.int32), off).to_host()
+    assert got.dtype == np.float32 and np.array_equal(got, want)
+    want32 = np.concatenate([O.coco_to_ssd_boxes(r.astype(np.float32), w, h) for r, (w, h) in zip(rows, sizes)])
+    assert np.array_equal(ops.gt_prepare(xywh.astype(np.float32), np.array(sizes, np.int32), off).to_host(), want32)
+    for n in (1, 7, 300 * 300 * 3 * 2 + 1):
+        x = rng.uniform(-0.2, 1.2, n).astype(np.float32)
+        assert np.array_equal(ops.image_normalize(x).to_host(), O.normalize_image(x))
+
+
+def test_gt_prepare_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "glue_small.npz"))      # outputs of the unmodified reference
+    got = ops.gt_prepare(g["xywh"], g["img_wh"], g["offsets"]).to_host()
+    assert np.array_equal(got, g["rel"])
+
+
+def test_train_batches_iterator_matches_per_image_oracle(priors300):
+    """get_train_set semantics (models/ssd_model.py:209-227): per-image match + encode + image scaling, batched,
+    trailing partial batch dropped."""
+    from ssdgeom import data
+    rng = np.random.default_rng(6)
+    items = []
+    for i in range(7):
+        w, h, t = int(rng.integers(200, 700)), int(rng.integers(200, 700)), int(rng.integers(1, 12))
+        xywh = np.concatenate([rng.uniform(0, [w * 0.7, h * 0.7], (t, 2)), rng.uniform(8, [w * 0.3, h * 0.3], (t, 2))], 1)
+        items.append((rng.uniform(0, 1, (30, 30, 3)).astype(np.float32), rng.integers(0, 80, t).astype(np.float32), xywh, (w, h)))
+    batches = list(data.TrainBatches(items, priors300, batch_size=3, coco_pixels=True))
+    assert len(batches) == 2                                    # 7 images, batch 3, remainder dropped (:225)
+    k = 0
+    for images, (cls, loc, mask) in batches:
+        assert images.shape == (3, 30, 30, 3) and cls.shape == (3, 8732) and loc.shape == (3, 8732, 4)
+        assert cls.dtype == np.int32 and loc.dtype == np.float32 and mask.dtype == bool
+        for i in range(3):
+            image, c, xywh, (w, h) = items[k]
+            box = O.coco_to_ssd_boxes(xywh, w, h)
+            w_cls, w_loc, w_mask = O.assign_encode(c, box, priors300, sweeps=False)
+            assert np.array_equal(cls[i], w_cls) and np.array_equal(mask[i], w_mask)
+            close(loc[i], w_loc)
+            assert np.array_equal(images[i], O.normalize_image(image))
+            k += 1
+
+
 # ---- A10 / A2 ---------------------------------------------------------------------------------------
 IOU_KAT = [([10, 10, 2, 2], [10, 10, 2, 2], 1.0), ([10, 10, 1, 1], [20, 20, 1, 1], 0.0),
            ([10, 10, 2, 2], [10, 10, 4, 4], 0.25), ([10, 10, 0, 0], [20, 20, 0, 0], 0.0),

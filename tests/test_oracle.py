@@ -227,3 +227,14 @@ def test_nms_against_torchvision_sanity():
     xyxy = torch.tensor(np.concatenate([b[:, :2] - b[:, 2:] / 2, b[:, :2] + b[:, 2:] / 2], 1))
     ref = tv.ops.nms(xyxy, torch.tensor(s), 0.45).numpy()
     assert kept.tolist() == ref.tolist()
+
+
+def test_input_glue_golden(golden_dir):
+    """coco xywh pixels -> relative cxcywh: the reference's own outputs (oracle/make_golden.py)."""
+    g = np.load(os.path.join(golden_dir, "glue_small.npz"))
+    off = g["offsets"]
+    for i, (w, h) in enumerate(g["img_wh"]):
+        got = O.coco_to_ssd_boxes(g["xywh"][off[i]:off[i + 1]], int(w), int(h))
+        assert got.dtype == np.float32 and np.array_equal(got, g["rel"][off[i]:off[i + 1]])
+    x = np.linspace(-1, 2, 101, dtype=np.float32)
+    assert np.array_equal(O.normalize_image(x), (x - np.float32(0.5)) * np.float32(2))

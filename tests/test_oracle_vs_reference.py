@@ -78,3 +78,20 @@ def test_loss(ref):
     np.testing.assert_allclose(o_total, float(r_total), rtol=1e-7)
     for k in ("cls loss pos", "cls loss neg", "loc loss"):
         np.testing.assert_allclose(o_info[k], float(r_info[k]), rtol=1e-7)
+
+
+def test_input_glue(ref):
+    """data_loaders/coco/make_dataset.py:132 + data_loaders/ssd/make_dataset.py:37-46 against the restatement."""
+    rng = np.random.default_rng(12)
+    for (w, h, t) in [(640, 427, 9), (500, 375, 1), (333, 500, 40), (1, 1, 3)]:
+        xywh = np.concatenate([rng.uniform(0, [w, h], (t, 2)), rng.uniform(0.5, [w, h], (t, 2))], 1)   # float64, as json.load gives
+        cls = rng.integers(0, 80, t).astype(np.float32)
+        image = rng.uniform(0, 1, (h, w, 3)).astype(np.float32)
+        centre = xywh.copy()
+        centre[:, :2] += centre[:, 2:] / 2                       # the generator's line 132, verbatim
+        box32 = centre.astype(np.float32)                        # TensorSpec(..., tf.float32), :140-142
+        r_image, r_cls, r_box = ref.coco2ssd(image, cls, box32)
+        assert r_box.dtype == np.float32 and r_image.shape == (300, 300, 3)
+        assert np.array_equal(r_box, O.coco_to_ssd_boxes(xywh, w, h))
+    x = rng.uniform(0, 1, (4, 5, 3)).astype(np.float32)
+    assert np.array_equal(O.normalize_image(x), (x - 0.5) * 2)
