@@ -26,7 +26,7 @@ constexpr int kFWarps = kFThreads / 32;
 constexpr int kNmsThreads = 128;
 constexpr int kNmsWarps = kNmsThreads / 32;
 constexpr int kSlabs = 32;   // slabs per axis of the NMS candidate join
-constexpr int kBucketThreads = 1024;
+constexpr int kBucketThreads = 512;
 constexpr int kABitsD = 21;     // prior index bits in a staged candidate (A < 2^21, C <= 2048)
 
 struct DetectParams {
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(kFThreads, 2) filter_kernel(DetectParams P, in
 }
 
 // Counting sort of one image's candidates by class (shared-memory histogram, scan, scatter).
-__global__ void __launch_bounds__(kBucketThreads) bucket_kernel(DetectParams P) {
+__global__ void __launch_bounds__(kBucketThreads, 2) bucket_kernel(DetectParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nfg = P.C - 1, tpi = P.tpi, b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
