@@ -201,34 +201,43 @@ struct SelectState {
 };
 
 // Scan one histogram from the top: find bin with  count(bins above) < k <= count(bins >= bin).
+// 256 threads, each owns nbins/256 consecutive bins (from the top) in registers: one round of global loads,
+// a shuffle scan per warp and an 8-entry cross-warp prefix.
 __device__ int scan_level(const u32* __restrict__ ghist, int nbins, long long& k, u32* sh /*[kBins]*/, int tid,
                           int nthreads, int* sh_bin, long long* sh_above) {
-  for (int i = tid; i < nbins; i += nthreads) sh[i] = ghist[i];
-  __syncthreads();
-  if (tid < 32) {
-    // 32 lanes, each owns a contiguous chunk (from the top)
-    const int per = nbins / 32;
-    const int hi = nbins - 1 - tid * per;
-    long long mine = 0;
-    for (int j = 0; j < per; ++j) mine += sh[hi - j];
-    long long incl = mine;
+  (void)nthreads;   // launch bounds of the callers: 256
+  const int per = nbins >> 8;   // 8 or 4
+  const int hi = nbins - 1 - tid * per;
+  u32 c[8];
+  long long mine = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      long long v = __shfl_up_sync(SSDG_FULL, incl, o);
-      if (tid >= o) incl += v;
-    }
-    const long long above = incl - mine;
-    if (above < k && k <= incl) {
-      long long run = above;
-      int bin = hi;
-      for (int j = 0; j < per; ++j) {
-        long long cnt = sh[hi - j];
-        if (run + cnt >= k) { bin = hi - j; break; }
-        run += cnt;
+  for (int j = 0; j < 8; ++j) {
+    c[j] = j < per ? ghist[hi - j] : 0u;
+    mine += c[j];
+  }
+  long long incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long v = __shfl_up_sync(SSDG_FULL, incl, o);
+    if ((tid & 31) >= o) incl += v;
+  }
+  long long* wtot = reinterpret_cast<long long*>(sh);   // [8] warp totals
+  if ((tid & 31) == 31) wtot[tid >> 5] = incl;
+  __syncthreads();
+  long long above = incl - mine;
+  for (int w = 0; w < (tid >> 5); ++w) above += wtot[w];
+  if (above < k && k <= above + mine) {   // exactly one thread
+    long long run = above;
+    int bin = hi;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < per) {
+        if (run + (long long)c[j] >= k) { bin = hi - j; break; }
+        run += c[j];
       }
-      *sh_bin = bin;
-      *sh_above = run;
     }
+    *sh_bin = bin;
+    *sh_above = run;
   }
   __syncthreads();
   const int bin = *sh_bin;
