@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--cpu-images", type=int, default=0, help="images in the CPU-baseline sample (0 = host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pipeline", default="split", choices=["split", "two-stream"],
+                    help="split: NMS and loss on their own streams (loss outranks NMS); two-stream: one stream per branch")
     ap.add_argument("--mining", default="shard", choices=["shard", "global"],
                     help="hard-negative threshold over this rank's batch (reference split-batch semantics) or "
                          "over all ranks' batches (exact-global, 5 small all-reduces)")
@@ -241,6 +243,7 @@ def run_ours(args):
     hp = HotPath(table, batch=b, max_gt=int(np.diff(off).max()), total_gt=boxes.shape[0], mining=args.mining,
                  global_priors=b * world * synth.num_priors(table) if args.mining == "global" else None,
                  allreduce=allreduce_on if args.mining == "global" else None)
+    hp.split = args.pipeline == "split"
     a, c = hp.A, hp.classes
     # pinned host copies of one batch (also the source of the resident copy)
     h = {"gt_boxes": D.PinnedArray(boxes.shape, np.float32), "gt_cls": D.PinnedArray(cls.shape, np.float32),

@@ -251,6 +251,16 @@ SSDG_API int ssdg_detect(const float* pred_cls, const float* pred_box, const voi
                 int32_t* out_count, float* out_kept_score, float* out_boxes, float* out_probs,
                 float head_thresh, float* head_score, int32_t* head_cls, uint8_t* head_mask,
                 void* workspace, size_t workspace_bytes, void* stream);
+/* The same call in two stream-ordered stages sharing the workspace: stage 0 = softmax filter, decode and
+ * candidate bucketing (the pass over the logits, HBM-bound), stage 1 = per-class NMS (instruction-bound).  A
+ * pipeline can enqueue them on different streams -- ordered by an event -- so that the NMS shares the SMs
+ * with an HBM-bound kernel of another branch (ssdgeom/pipeline.py). */
+SSDG_API int ssdg_detect_stage(int32_t stage, const float* pred_cls, const float* pred_box, const void* priors,
+                int32_t prior_dtype, int64_t batch, int32_t n_priors, int32_t n_classes,
+                float score_thresh, int32_t top_k, float iou_thresh, int32_t* out_kept,
+                int32_t* out_count, float* out_kept_score, float* out_boxes, float* out_probs,
+                float head_thresh, float* head_score, int32_t* head_cls, uint8_t* head_mask,
+                void* workspace, size_t workspace_bytes, void* stream);
 
 /* Per-class NMS on caller-supplied scores and decoded boxes (the second stage alone):
  *   probs float [B,A,C] (16-byte aligned), boxes float [B,A,4]. */

@@ -860,12 +860,13 @@ extern "C" size_t ssdg_detect_workspace_bytes(int64_t batch, int32_t n_priors, i
   return detect_ws_layout(batch, n_priors, n_classes, nullptr, nullptr);
 }
 
-extern "C" int ssdg_detect(const float* pred_cls, const float* pred_box, const void* priors, int32_t prior_dtype,
-                           int64_t batch, int32_t n_priors, int32_t n_classes, float score_thresh, int32_t top_k,
-                           float iou_thresh, int32_t* out_kept, int32_t* out_count, float* out_kept_score,
-                           float* out_boxes, float* out_probs, float head_thresh, float* head_score,
-                           int32_t* head_cls, uint8_t* head_mask, void* workspace, size_t workspace_bytes,
-                           void* stream) {
+// stages: 1 = softmax filter + decode + candidate bucketing, 2 = per-class NMS (reads what stage 1 left in the workspace)
+static int detect_run(int stages, const float* pred_cls, const float* pred_box, const void* priors, int32_t prior_dtype,
+                      int64_t batch, int32_t n_priors, int32_t n_classes, float score_thresh, int32_t top_k,
+                      float iou_thresh, int32_t* out_kept, int32_t* out_count, float* out_kept_score,
+                      float* out_boxes, float* out_probs, float head_thresh, float* head_score,
+                      int32_t* head_cls, uint8_t* head_mask, void* workspace, size_t workspace_bytes,
+                      void* stream) {
   if (!pred_cls || !pred_box || !priors || !out_kept || !out_count) return SSDG_ERR_ARG;
   if (batch <= 0 || n_priors <= 0 || n_classes < 2 || top_k <= 0) return SSDG_ERR_ARG;
   if (prior_dtype != SSDG_F32 && prior_dtype != SSDG_F64) return SSDG_ERR_ARG;
@@ -883,9 +884,36 @@ extern "C" int ssdg_detect(const float* pred_cls, const float* pred_box, const v
   P.pred_cls = pred_cls; P.pred_box = pred_box; P.priors = priors; P.score_thresh = score_thresh;
   P.boxes = out_boxes ? out_boxes : ws.boxes; P.probs = out_probs;
   P.head_thresh = head_thresh; P.head_score = head_score; P.head_cls = head_cls; P.head_mask = head_mask;
-  int rc = run_filter<false>(P, prior_dtype, st);
-  if (rc) return rc;
-  return run_nms(ws, P.boxes, batch, n_priors, n_classes, top_k, iou_thresh, out_kept, out_count, out_kept_score, st);
+  if (stages & 1) {
+    const int rc = run_filter<false>(P, prior_dtype, st);
+    if (rc) return rc;
+  }
+  if (stages & 2)
+    return run_nms(ws, P.boxes, batch, n_priors, n_classes, top_k, iou_thresh, out_kept, out_count, out_kept_score, st);
+  return SSDG_OK;
+}
+
+extern "C" int ssdg_detect(const float* pred_cls, const float* pred_box, const void* priors, int32_t prior_dtype,
+                           int64_t batch, int32_t n_priors, int32_t n_classes, float score_thresh, int32_t top_k,
+                           float iou_thresh, int32_t* out_kept, int32_t* out_count, float* out_kept_score,
+                           float* out_boxes, float* out_probs, float head_thresh, float* head_score,
+                           int32_t* head_cls, uint8_t* head_mask, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  return detect_run(3, pred_cls, pred_box, priors, prior_dtype, batch, n_priors, n_classes, score_thresh, top_k,
+                    iou_thresh, out_kept, out_count, out_kept_score, out_boxes, out_probs, head_thresh, head_score,
+                    head_cls, head_mask, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ssdg_detect_stage(int32_t stage, const float* pred_cls, const float* pred_box, const void* priors,
+                                 int32_t prior_dtype, int64_t batch, int32_t n_priors, int32_t n_classes,
+                                 float score_thresh, int32_t top_k, float iou_thresh, int32_t* out_kept,
+                                 int32_t* out_count, float* out_kept_score, float* out_boxes, float* out_probs,
+                                 float head_thresh, float* head_score, int32_t* head_cls, uint8_t* head_mask,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (stage != 0 && stage != 1) return SSDG_ERR_ARG;
+  return detect_run(1 << stage, pred_cls, pred_box, priors, prior_dtype, batch, n_priors, n_classes, score_thresh,
+                    top_k, iou_thresh, out_kept, out_count, out_kept_score, out_boxes, out_probs, head_thresh,
+                    head_score, head_cls, head_mask, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ssdg_nms(const float* probs, const float* boxes, int64_t batch, int32_t n_priors, int32_t n_classes,

@@ -13,6 +13,7 @@
 //   grad_kernel    optional second pass: d total / d logits and d total / d pred_box (:248).
 #include <math_constants.h>
 #include <cstddef>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace ssdg {
@@ -459,7 +460,8 @@ __global__ void __launch_bounds__(256) grad_kernel(LossParams P) {
 }
 
 static int ce_warps_for(int C) {
-  const size_t budget = 200 * 1024;
+  static const char* env = getenv("SSDG_CE_SMEM_KB");   // experiment knob
+  const size_t budget = (env ? (size_t)atoi(env) : 200) * 1024;
   size_t per_warp = (size_t)kStages * 32 * C * 4;
   int w = (int)(budget / per_warp);
   if (w > kCeWarps) w = kCeWarps;

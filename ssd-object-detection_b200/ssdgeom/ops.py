@@ -332,7 +332,9 @@ def loss_result_to_host(result: D.DeviceArray, stream=None) -> dict:
 
 # ---- A7 + A8 + A9 ---------------------------------------------------------------------------------------
 def detect(pred_cls, pred_box, priors, score_thresh=0.01, top_k=200, iou_thresh=0.45, want_scores=False,
-           want_boxes=False, want_probs=False, head_thresh=None, out=None, stream=None) -> dict:
+           want_boxes=False, want_probs=False, head_thresh=None, out=None, stream=None, stage=None) -> dict:
+    """stage: None = the whole post-processing; 0 = filter + decode + bucketing only; 1 = the NMS of a previous
+    stage-0 call with the same arguments (include/ssdgeom.h, ssdg_detect_stage)."""
     pred_cls = D.as_device(pred_cls, np.float32)
     pred_box = D.as_device(pred_box, np.float32)
     priors = D.as_device(priors)
@@ -359,12 +361,15 @@ def detect(pred_cls, pred_box, priors, score_thresh=0.01, top_k=200, iou_thresh=
         need("head_mask", (b, a), np.uint8)
     lib = N.lib()
     ws = POOL.get("detect", lib.ssdg_detect_workspace_bytes(b, a, c, top_k))
-    N.check(lib.ssdg_detect(pred_cls.ptr, pred_box.ptr, priors.ptr, _code(priors.dtype), b, a, c, float(score_thresh),
-                            int(top_k), float(iou_thresh), out["kept"].ptr, out["count"].ptr, _p(out.get("kept_score")),
-                            _p(out.get("boxes")), _p(out.get("probs")),
-                            float(head_thresh if head_thresh is not None else 0.0), _p(out.get("head_score")),
-                            _p(out.get("head_cls")), _p(out.get("head_mask")), ws.ptr, ws.nbytes,
-                            D.stream_handle(stream)), "detect")
+    args = (pred_cls.ptr, pred_box.ptr, priors.ptr, _code(priors.dtype), b, a, c, float(score_thresh),
+            int(top_k), float(iou_thresh), out["kept"].ptr, out["count"].ptr, _p(out.get("kept_score")),
+            _p(out.get("boxes")), _p(out.get("probs")),
+            float(head_thresh if head_thresh is not None else 0.0), _p(out.get("head_score")),
+            _p(out.get("head_cls")), _p(out.get("head_mask")), ws.ptr, ws.nbytes, D.stream_handle(stream))
+    if stage is None:
+        N.check(lib.ssdg_detect(*args), "detect")
+    else:
+        N.check(lib.ssdg_detect_stage(int(stage), *args), "detect_stage")
     out["_keep"] = (pred_cls, pred_box, priors, ws)
     return out
 

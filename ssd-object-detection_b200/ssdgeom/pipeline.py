@@ -41,7 +41,9 @@ class HotPath:
         # the post-processing branch is the longer one: its CTAs are scheduled first, the assignment/loss
         # branch fills the gaps
         self.s_main, self.s_a, self.s_d = D.Stream(), D.Stream("low"), D.Stream("high")
-        self.ev_begin, self.ev_a, self.ev_d, self.ev_mid = D.Event(), D.Event(), D.Event(), D.Event()
+        self.s_n, self.s_l = D.Stream("low"), D.Stream("high")
+        self.ev_begin, self.ev_a, self.ev_d, self.ev_mid, self.ev_m = (D.Event() for _ in range(5))
+        self.split = True
         if mining not in ("shard", "global"):
             raise ValueError("mining must be 'shard' or 'global'")
         self.mining, self.allreduce = mining, allreduce
@@ -51,7 +53,6 @@ class HotPath:
                 raise ValueError("global mining needs allreduce and global_priors")
             self.staged = ops.StagedLoss(self.tgt["cls"], self.tgt["loc"], self.tgt["mask"], self.pred_box, self.pred_cls,
                                          int(global_priors), self.neg_ratio, out=self.loss)
-        self.stagger = False   # measured: co-running the matcher with nms_kernel is slower than with the filter pass
         self.kernel_launches_per_step = 8   # match | ce, select x2, final | filter, bucket, nms
         self.h2d_bytes = (self.gt_boxes.nbytes + self.gt_cls.nbytes + self.gt_off.nbytes + self.pred_cls.nbytes +
                           self.pred_box.nbytes)
@@ -73,30 +74,37 @@ class HotPath:
         ops.multibox_loss(self.tgt["cls"], self.tgt["loc"], self.tgt["mask"], self.pred_box, self.pred_cls,
                           self.neg_ratio, out=self.loss, stream=stream)
 
-    def detect_stage(self, stream):
+    def detect_stage(self, stream, stage=None):
         ops.detect(self.pred_cls, self.pred_box, self.priors, self.score_thresh, self.top_k, self.iou_thresh,
-                   out=self.det, stream=stream)
+                   out=self.det, stream=stream, stage=stage)
 
     def step(self):
-        """One pass of the chain over the resident batch; work is ordered on ``s_main``."""
+        """One pass of the chain over the resident batch; work is ordered on ``s_main``.
+
+        Four streams so that kernels bound by different resources share the SMs:
+          phase A   filter + bucketing (HBM-bound, s_d, high priority)  with  the matcher (latency-bound, s_a, low)
+          phase B   NMS (instruction-bound, s_n, low)                   with  the loss (HBM-bound, s_l, high)
+        The loss must outrank the NMS or its 148 large-shared-memory CTAs starve behind 20 480 small NMS CTAs."""
         self.ev_begin.record(self.s_main)
         D.stream_wait_event(self.s_a, self.ev_begin)
         D.stream_wait_event(self.s_d, self.ev_begin)
-        # enqueue the long, high-priority branch first: its CTAs own the SMs from the start and the
-        # latency-bound matcher then shares them with the small NMS CTAs instead of blocking the filter
-        if self.stagger:
-            # The filter pass is HBM-bound and owns the SMs' registers and shared memory; the matcher is
-            # latency-bound and shares an SM best with the small, ALU-bound NMS CTAs: start it when they start.
-            N.lib().ssdg_detect_set_mid_event(self.ev_mid.handle)
-            self.detect_stage(self.s_d)
-            N.lib().ssdg_detect_set_mid_event(None)
-            D.stream_wait_event(self.s_a, self.ev_mid)
+        if self.split:
+            self.detect_stage(self.s_d, stage=0)
+            self.ev_mid.record(self.s_d)
+            self.assign(self.s_a)
+            self.ev_m.record(self.s_a)
+            D.stream_wait_event(self.s_n, self.ev_mid)
+            self.detect_stage(self.s_n, stage=1)
+            D.stream_wait_event(self.s_l, self.ev_m)
+            self.loss_stage(self.s_l)
+            self.ev_a.record(self.s_l)
+            self.ev_d.record(self.s_n)
         else:
             self.detect_stage(self.s_d)
-        self.assign(self.s_a)
-        self.loss_stage(self.s_a)
-        self.ev_a.record(self.s_a)
-        self.ev_d.record(self.s_d)
+            self.assign(self.s_a)
+            self.loss_stage(self.s_a)
+            self.ev_a.record(self.s_a)
+            self.ev_d.record(self.s_d)
         D.stream_wait_event(self.s_main, self.ev_a)
         D.stream_wait_event(self.s_main, self.ev_d)
 
