@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--pipeline", default="split", choices=["split", "two-stream"],
                     help="split: NMS and loss on their own streams (loss outranks NMS); two-stream: one stream per branch")
+    ap.add_argument("--no-fused", action="store_true",
+                    help="loss streams the logits itself (ce_kernel) instead of reusing the filter pass's row statistics")
     ap.add_argument("--mining", default="shard", choices=["shard", "global"],
                     help="hard-negative threshold over this rank's batch (reference split-batch semantics) or "
                          "over all ranks' batches (exact-global, 5 small all-reduces)")
@@ -244,6 +246,7 @@ def run_ours(args):
                  global_priors=b * world * synth.num_priors(table) if args.mining == "global" else None,
                  allreduce=allreduce_on if args.mining == "global" else None)
     hp.split = args.pipeline == "split"
+    hp.fused = not args.no_fused and hp.split and args.mining == "shard"
     a, c = hp.A, hp.classes
     # pinned host copies of one batch (also the source of the resident copy)
     h = {"gt_boxes": D.PinnedArray(boxes.shape, np.float32), "gt_cls": D.PinnedArray(cls.shape, np.float32),
@@ -336,6 +339,10 @@ def run_ours(args):
     time_stage("assign_ms", hp.assign, [N.PROF_MATCH])
     time_stage("loss_ms", hp.loss_stage, [N.PROF_CE])
     time_stage("detect_ms", hp.detect_stage, [N.PROF_FILTER, N.PROF_NMS])
+    ce_alone_ms, filter_alone_ms = kernel_ms.get(N.PROF_CE, 0.0), kernel_ms.get(N.PROF_FILTER, 0.0)
+    if hp.fused:   # the variants the chained step actually launches
+        time_stage("detect_with_row_stats_ms", lambda s: hp.detect_stage(s, stats=True), [N.PROF_FILTER, N.PROF_NMS])
+        time_stage("loss_from_row_stats_ms", lambda s: hp.loss_stage(s, stats=True), [N.PROF_CE])
     N.lib().ssdg_profile_enable(0)
     clocks = sampler.summary(t0, t1, t_load0, time.perf_counter())
 
@@ -371,29 +378,41 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
-    loss_bytes_img = a * (c * 4 + 16 + 16 + 4 + 1)            # logits + pred_box + gt_box + gt_cls + mask
-    ce_bytes = b * loss_bytes_img                              # algorithmic bytes of one ce_kernel launch
-    ce_ms = kernel_ms.get(N.PROF_CE, 0.0)
-    achieved = ce_bytes / (ce_ms * 1e-3) / 1e9 if ce_ms > 0 else 0.0
-    traffic = None
-    try:      # dram__bytes_read.sum + dram__bytes_write.sum of one ce_kernel launch (ncu --set full), same shape only
-        cap = json.load(open(os.path.join(ROOT, "profiles", "ce_kernel_traffic.json")))
-        if cap.get("batch") == b and cap.get("priors") == a and cap.get("classes") == c:
-            traffic = cap["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    roof = {"bound": "hbm", "kernel": "ce_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": ce_ms,
-            "algorithmic_bytes_per_launch": ce_bytes}
+    def traffic_of(name):   # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full), same shape only
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if cap.get("batch") == b and cap.get("priors") == a and cap.get("classes") == c:
+                return cap["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        return None
+
+    if hp.fused:
+        # the one pass over the logits: in logits + pred_box, out decoded boxes (16 B) + row statistics (12 B) per prior
+        k_name, k_ms = "filter_kernel (softmax filter + decode + loss row statistics)", kernel_ms.get(N.PROF_FILTER, 0.0)
+        k_bytes = b * a * (c * 4 + 16 + 16 + 12)
+        traffic = traffic_of("filter_kernel_traffic.json")
+    else:
+        k_name, k_ms = "ce_kernel", ce_alone_ms
+        k_bytes = b * a * (c * 4 + 16 + 16 + 4 + 1)            # logits + pred_box + gt_box + gt_cls + mask
+        traffic = traffic_of("ce_kernel_traffic.json")
+    achieved = k_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    roof = {"bound": "hbm", "kernel": k_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms,
+            "algorithmic_bytes_per_launch": k_bytes}
+    ce_ms = ce_alone_ms
     filt_bytes = b * a * (c * 4 + 16)
-    f_ms = kernel_ms.get(N.PROF_FILTER, 0.0)
-    extra = {"stages_ms": stages,
+    f_ms = filter_alone_ms
+    extra = {"stages_ms": stages, "fused_logits_pass": bool(hp.fused),
+             "ce_kernel_gbs_standalone": b * a * (c * 4 + 16 + 16 + 4 + 1) / (ce_ms * 1e-3) / 1e9 if ce_ms > 0 else None,
              "kernels_ms": {"match_kernel": kernel_ms.get(N.PROF_MATCH), "ce_kernel": ce_ms, "filter_kernel": f_ms,
-                            "nms_kernel": kernel_ms.get(N.PROF_NMS)},
+                            "nms_kernel": kernel_ms.get(N.PROF_NMS),
+                            "filter_kernel_with_row_stats": kernel_ms.get(N.PROF_FILTER) if hp.fused else None,
+                            "lossprep_kernel": kernel_ms.get(N.PROF_CE) if hp.fused else None},
              "filter_kernel_gbs": filt_bytes / (f_ms * 1e-3) / 1e9 if f_ms > 0 else None,
              "match_pairs_per_s": (float(np.diff(off).sum()) * a) / (kernel_ms.get(N.PROF_MATCH, 0) * 1e-3)
              if kernel_ms.get(N.PROF_MATCH) else None,
-             "chain_bytes_per_image": a * (c * 4 * 2 + 16 * 3 + 4 + 1 + 4 + 16 + 1),
+             "chain_bytes_per_image": a * (c * 4 * (1 if hp.fused else 2) + 16 * 3 + 4 + 1 + 4 + 16 + 1),
              "loss": ({"total": res[0], "num_pos": res[4], "num_neg": res[5], "status": res[7], "scope": "this rank"}
                       if args.mining == "shard" else
                       {"total": (res[8] + res[10]) / res[11] + res[9] / res[5], "num_pos": res[11], "num_neg": res[5],

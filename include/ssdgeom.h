@@ -214,6 +214,17 @@ SSDG_API int ssdg_multibox_loss_stage(int32_t stage, int64_t global_priors, cons
                        void* stream);
 SSDG_API int ssdg_loss_exchange(void* workspace, int32_t which, void** out_ptr, int64_t* out_count);
 
+/* The same loss when the post-processing branch has already streamed the same logits: ssdg_detect_stage(0, ...)
+ * with out_row_ml / out_row_negbg leaves per prior (row max, log sum exp(x - max)) and the background CE; this
+ * entry point then needs no second pass over pred_cls -- positives gather their one ground-truth logit.
+ * row_ml float [B*A,2], row_negbg float [B*A]; everything else as ssdg_multibox_loss. */
+SSDG_API int ssdg_multibox_loss_fused(const float* row_ml, const float* row_negbg, const int32_t* gt_cls,
+                       const float* gt_box, const uint8_t* gt_mask, const float* pred_box,
+                       const float* pred_cls, int64_t batch, int32_t n_priors, int32_t n_classes,
+                       int32_t neg_ratio, double* out_result, uint8_t* out_neg_mask, float* out_neg_ce,
+                       float* grad_box, float* grad_cls, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
 /* ---- input glue ----------------------------------------------------------
  * ssdg_gt_prepare replaces, for a whole batch of annotation rows at once,
  *   COCODataLoader.gen            data_loaders/coco/make_dataset.py:132   bbox[:, :2] += bbox[:, 2:] / 2
@@ -254,13 +265,15 @@ SSDG_API int ssdg_detect(const float* pred_cls, const float* pred_box, const voi
 /* The same call in two stream-ordered stages sharing the workspace: stage 0 = softmax filter, decode and
  * candidate bucketing (the pass over the logits, HBM-bound), stage 1 = per-class NMS (instruction-bound).  A
  * pipeline can enqueue them on different streams -- ordered by an event -- so that the NMS shares the SMs
- * with an HBM-bound kernel of another branch (ssdgeom/pipeline.py). */
+ * with an HBM-bound kernel of another branch (ssdgeom/pipeline.py).  out_row_ml float [B*A,2] / out_row_negbg
+ * float [B*A] (both or neither, stage 0): per-prior softmax statistics for ssdg_multibox_loss_fused. */
 SSDG_API int ssdg_detect_stage(int32_t stage, const float* pred_cls, const float* pred_box, const void* priors,
                 int32_t prior_dtype, int64_t batch, int32_t n_priors, int32_t n_classes,
                 float score_thresh, int32_t top_k, float iou_thresh, int32_t* out_kept,
                 int32_t* out_count, float* out_kept_score, float* out_boxes, float* out_probs,
                 float head_thresh, float* head_score, int32_t* head_cls, uint8_t* head_mask,
-                void* workspace, size_t workspace_bytes, void* stream);
+                float* out_row_ml, float* out_row_negbg, void* workspace, size_t workspace_bytes,
+                void* stream);
 
 /* Per-class NMS on caller-supplied scores and decoded boxes (the second stage alone):
  *   probs float [B,A,C] (16-byte aligned), boxes float [B,A,4]. */

@@ -47,6 +47,8 @@ struct DetectParams {
   float* head_score;
   int* head_cls;
   uint8_t* head_mask;
+  float2* row_ml;          // optional [B*A] (row max, log sum exp(x - max)): what the loss needs of this pass
+  float* row_negbg;        // optional [B*A] background CE  log-sum - (x_bg - max)   (models/ssd_model.py:362-367)
 };
 
 __device__ __forceinline__ u64 evict_first_policy() {
@@ -126,7 +128,9 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
         m0 = fmaxf(m0, row[c]); m1 = fmaxf(m1, row[c + 1]); m2 = fmaxf(m2, row[c + 2]); m3 = fmaxf(m3, row[c + 3]);
       }
       for (; c < C; ++c) m0 = fmaxf(m0, row[c]);
-      kexp = -fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * SSDG_LOG2E;
+      const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      const float xbg = row[C - 1];
+      kexp = -mx * SSDG_LOG2E;
       float s0 = 0.f, s1 = 0.f;
       auto chunk32 = [&](int c0) {   // a full word of 32 classes, fully unrolled: the bit positions are immediates
         u32 bits = 0u;
@@ -159,6 +163,11 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
         row[c] = e0; s0 += e0;
       }
       inv_s = __frcp_rn(s0 + s1);
+      if (P.row_ml) {   // the loss of the same predictions reuses this pass instead of streaming the logits again
+        const float lg = logf(s0 + s1);
+        P.row_ml[n] = make_float2(mx, lg);
+        P.row_negbg[n] = lg - (xbg - mx);
+      }
     } else {
       const int lim = min(nfg, 96);
       for (int c = 0; c < lim; ++c) {
@@ -865,8 +874,10 @@ static int detect_run(int stages, const float* pred_cls, const float* pred_box, 
                       int64_t batch, int32_t n_priors, int32_t n_classes, float score_thresh, int32_t top_k,
                       float iou_thresh, int32_t* out_kept, int32_t* out_count, float* out_kept_score,
                       float* out_boxes, float* out_probs, float head_thresh, float* head_score,
-                      int32_t* head_cls, uint8_t* head_mask, void* workspace, size_t workspace_bytes,
-                      void* stream) {
+                      int32_t* head_cls, uint8_t* head_mask, float* out_row_ml, float* out_row_negbg, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if ((out_row_ml == nullptr) != (out_row_negbg == nullptr)) return SSDG_ERR_ARG;
+  if (((uintptr_t)out_row_ml & 7) || ((uintptr_t)out_row_negbg & 3)) return SSDG_ERR_ALIGN;
   if (!pred_cls || !pred_box || !priors || !out_kept || !out_count) return SSDG_ERR_ARG;
   if (batch <= 0 || n_priors <= 0 || n_classes < 2 || top_k <= 0) return SSDG_ERR_ARG;
   if (prior_dtype != SSDG_F32 && prior_dtype != SSDG_F64) return SSDG_ERR_ARG;
@@ -884,6 +895,7 @@ static int detect_run(int stages, const float* pred_cls, const float* pred_box, 
   P.pred_cls = pred_cls; P.pred_box = pred_box; P.priors = priors; P.score_thresh = score_thresh;
   P.boxes = out_boxes ? out_boxes : ws.boxes; P.probs = out_probs;
   P.head_thresh = head_thresh; P.head_score = head_score; P.head_cls = head_cls; P.head_mask = head_mask;
+  P.row_ml = reinterpret_cast<float2*>(out_row_ml); P.row_negbg = out_row_negbg;
   if (stages & 1) {
     const int rc = run_filter<false>(P, prior_dtype, st);
     if (rc) return rc;
@@ -901,7 +913,7 @@ extern "C" int ssdg_detect(const float* pred_cls, const float* pred_box, const v
                            void* stream) {
   return detect_run(3, pred_cls, pred_box, priors, prior_dtype, batch, n_priors, n_classes, score_thresh, top_k,
                     iou_thresh, out_kept, out_count, out_kept_score, out_boxes, out_probs, head_thresh, head_score,
-                    head_cls, head_mask, workspace, workspace_bytes, stream);
+                    head_cls, head_mask, nullptr, nullptr, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ssdg_detect_stage(int32_t stage, const float* pred_cls, const float* pred_box, const void* priors,
@@ -909,11 +921,12 @@ extern "C" int ssdg_detect_stage(int32_t stage, const float* pred_cls, const flo
                                  float score_thresh, int32_t top_k, float iou_thresh, int32_t* out_kept,
                                  int32_t* out_count, float* out_kept_score, float* out_boxes, float* out_probs,
                                  float head_thresh, float* head_score, int32_t* head_cls, uint8_t* head_mask,
-                                 void* workspace, size_t workspace_bytes, void* stream) {
+                                 float* out_row_ml, float* out_row_negbg, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
   if (stage != 0 && stage != 1) return SSDG_ERR_ARG;
   return detect_run(1 << stage, pred_cls, pred_box, priors, prior_dtype, batch, n_priors, n_classes, score_thresh,
                     top_k, iou_thresh, out_kept, out_count, out_kept_score, out_boxes, out_probs, head_thresh,
-                    head_score, head_cls, head_mask, workspace, workspace_bytes, stream);
+                    head_score, head_cls, head_mask, out_row_ml, out_row_negbg, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ssdg_nms(const float* probs, const float* boxes, int64_t batch, int32_t n_priors, int32_t n_classes,
@@ -935,6 +948,7 @@ extern "C" int ssdg_nms(const float* probs, const float* boxes, int64_t batch, i
   P.pred_cls = probs; P.pred_box = nullptr; P.priors = nullptr; P.score_thresh = score_thresh;
   P.boxes = nullptr; P.probs = nullptr;
   P.head_thresh = 0.f; P.head_score = nullptr; P.head_cls = nullptr; P.head_mask = nullptr;
+  P.row_ml = nullptr; P.row_negbg = nullptr;
   int rc = run_filter<true>(P, SSDG_F32, st);
   if (rc) return rc;
   return run_nms(ws, boxes, batch, n_priors, n_classes, top_k, iou_thresh, out_kept, out_count, out_kept_score, st);

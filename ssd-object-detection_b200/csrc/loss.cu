@@ -49,6 +49,8 @@ struct LossParams {
   LossWs* ws;
   float* grad_box;
   float* grad_cls;
+  const float2* row_ml; // optional: per-prior (max, log-sum) left by the filter pass of the same logits
+  const float* row_negbg;   // optional: per-prior background CE from the same pass
   long long N_all;      // priors of the whole (cross-shard) batch; == N for single-shard mining
   int global;           // 1: num_pos and the histograms in the workspace are cross-shard sums
 };
@@ -187,6 +189,70 @@ __global__ void __launch_bounds__(kCeThreads, 1) ce_kernel(LossParams P, int war
   }
   for (int i = tid; i < kBins; i += kCeThreads) {
     u32 v = hist[i];
+    if (v) atomicAdd(&P.ws->hist[0][i], v);
+  }
+}
+
+// ---- the CE pass without the logits ----------------------------------------------------------------------
+// When the softmax filter of the post-processing branch has already streamed the same logits (ssdg_detect_stage
+// with row statistics), the loss needs no second pass over them: the background CE is there, and the positives
+// (a few percent of the priors) gather their one ground-truth logit.  Same outputs as ce_kernel: the mining
+// vector, its level-0 histogram, the per-CTA partial sums, the positives count.
+__global__ void __launch_bounds__(256) lossprep_kernel(LossParams P) {
+  __shared__ u32 hist[kBins];
+  __shared__ double red[3][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kBins; i += 256) hist[i] = 0u;
+  __syncthreads();
+  CeAcc acc;
+  acc.pos_ce = 0.f; acc.l1 = 0.f; acc.npos = 0;
+  const int C = P.C;
+  auto one = [&](long long n, bool pos, float negbg) -> float {
+    if (!pos) return negbg;
+    int lab = P.gt_cls[n];
+    lab = lab < 0 ? 0 : (lab >= C ? C - 1 : lab);
+    const float2 ml = P.row_ml[n];
+    acc.pos_ce += ml.y - (__ldg(P.pred_cls + (size_t)n * C + lab) - ml.x);
+    const float4 pb = __ldg(reinterpret_cast<const float4*>(P.pred_box) + n);
+    const float4 gb = __ldg(reinterpret_cast<const float4*>(P.gt_box) + n);
+    acc.l1 += (fabsf(pb.x - gb.x) + fabsf(pb.y - gb.y)) + (fabsf(pb.z - gb.z) + fabsf(pb.w - gb.w));
+    acc.npos += 1;
+    return 0.f;
+  };
+  const long long gtid = (long long)blockIdx.x * 256 + tid, gstride = (long long)gridDim.x * 256;
+  const bool vec = (((uintptr_t)P.gt_mask) & 3) == 0 && (((uintptr_t)P.row_negbg | (uintptr_t)P.neg_ce) & 15) == 0;
+  long long done = 0;
+  if (vec) {
+    const long long n4 = P.N >> 2;
+    for (long long i = gtid; i < n4; i += gstride) {
+      const uchar4 mk = reinterpret_cast<const uchar4*>(P.gt_mask)[i];
+      const float4 nb = reinterpret_cast<const float4*>(P.row_negbg)[i];
+      float4 o;
+      o.x = one(4 * i, mk.x != 0, nb.x); o.y = one(4 * i + 1, mk.y != 0, nb.y);
+      o.z = one(4 * i + 2, mk.z != 0, nb.z); o.w = one(4 * i + 3, mk.w != 0, nb.w);
+      reinterpret_cast<float4*>(P.neg_ce)[i] = o;
+      atomicAdd(&hist[key32(o.x) >> 21], 1u); atomicAdd(&hist[key32(o.y) >> 21], 1u);
+      atomicAdd(&hist[key32(o.z) >> 21], 1u); atomicAdd(&hist[key32(o.w) >> 21], 1u);
+    }
+    done = n4 << 2;
+  }
+  for (long long n = done + gtid; n < P.N; n += gstride) {
+    const float v = one(n, P.gt_mask[n] != 0, P.row_negbg[n]);
+    P.neg_ce[n] = v;
+    atomicAdd(&hist[key32(v) >> 21], 1u);
+  }
+  double a = warp_sum((double)acc.pos_ce), b = warp_sum((double)acc.l1), c = warp_sum((double)acc.npos);
+  if (lane == 0) { red[0][warp] = a; red[1][warp] = b; red[2][warp] = c; }
+  __syncthreads();
+  if (tid == 0) {
+    double sa = 0, sb = 0, sc = 0;
+    for (int w = 0; w < 8; ++w) { sa += red[0][w]; sb += red[1][w]; sc += red[2][w]; }
+    P.ws->part[blockIdx.x][0] = sa; P.ws->part[blockIdx.x][1] = sb; P.ws->part[blockIdx.x][2] = sc;
+    if (blockIdx.x == 0) P.ws->nparts[0] = gridDim.x;
+    atomicAdd(&P.ws->xnpos, (unsigned long long)sc);
+  }
+  for (int i = tid; i < kBins; i += 256) {
+    const u32 v = hist[i];
     if (v) atomicAdd(&P.ws->hist[0][i], v);
   }
 }
@@ -483,7 +549,8 @@ extern "C" size_t ssdg_loss_workspace_bytes(int64_t batch, int32_t n_priors, int
 
 // stages: 1 = CE pass (+ level-0 histogram, positives count), 2 / 4 = radix levels 1 / 2, 8 = mask, sums, result
 // (+ gradient).  Between the stages of a cross-shard run the caller sums the exchange words over the shards.
-static int loss_run(int stages, int global, long long n_all, const int32_t* gt_cls, const float* gt_box,
+static int loss_run(int stages, int global, long long n_all, const float* row_ml, const float* row_negbg,
+                    const int32_t* gt_cls, const float* gt_box,
                     const uint8_t* gt_mask, const float* pred_box, const float* pred_cls, int64_t batch,
                     int32_t n_priors, int32_t n_classes, int32_t neg_ratio, double* out_result, uint8_t* out_neg_mask,
                     float* out_neg_ce, float* grad_box, float* grad_cls, void* workspace, size_t workspace_bytes,
@@ -501,21 +568,32 @@ static int loss_run(int stages, int global, long long n_all, const int32_t* gt_c
   P.gt_cls = gt_cls; P.gt_box = gt_box; P.gt_mask = gt_mask; P.pred_box = pred_box; P.pred_cls = pred_cls;
   P.N = (long long)batch * n_priors; P.C = n_classes; P.ratio = neg_ratio;
   P.N_all = global ? n_all : P.N; P.global = global;
+  if ((row_ml == nullptr) != (row_negbg == nullptr)) return SSDG_ERR_ARG;
+  if (((uintptr_t)row_ml & 7) || ((uintptr_t)row_negbg & 3)) return SSDG_ERR_ALIGN;
+  P.row_ml = reinterpret_cast<const float2*>(row_ml); P.row_negbg = row_negbg;
   if (P.N_all < P.N) return SSDG_ERR_ARG;
   P.ws = (LossWs*)workspace;
   P.neg_ce = out_neg_ce ? out_neg_ce : (float*)((unsigned char*)workspace + align_up(sizeof(LossWs), 256));
   P.neg_mask = out_neg_mask; P.result = out_result; P.grad_box = grad_box; P.grad_cls = grad_cls;
   if (stages & 1) {
     SSDG_CUDA_TRY(cudaMemsetAsync(&P.ws->hist[0][0], 0, sizeof(LossWs) - offsetof(LossWs, hist), st));
-    const size_t smem = ce_smem_bytes(n_classes, warps);
-    SSDG_CUDA_TRY(cudaFuncSetAttribute(ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = sm_count();
-    if (grid > 256) grid = 256;
-    const long long tiles = (P.N + 31) / 32;
-    const long long need = (tiles + warps - 1) / warps;
-    if (need < grid) grid = (int)need;
     prof_begin(SSDG_PROF_CE, st);
-    ce_kernel<<<grid, kCeThreads, smem, st>>>(P, warps);
+    if (row_ml) {
+      int grid = (int)((P.N / 4 + 255) / 256);
+      if (grid > 256) grid = 256;   // LossWs::part
+      if (grid < 1) grid = 1;
+      SSDG_CUDA_TRY(cudaFuncSetAttribute(lossprep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      lossprep_kernel<<<grid, 256, 0, st>>>(P);
+    } else {
+      const size_t smem = ce_smem_bytes(n_classes, warps);
+      SSDG_CUDA_TRY(cudaFuncSetAttribute(ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int grid = sm_count();
+      if (grid > 256) grid = 256;
+      const long long tiles = (P.N + 31) / 32;
+      const long long need = (tiles + warps - 1) / warps;
+      if (need < grid) grid = (int)need;
+      ce_kernel<<<grid, kCeThreads, smem, st>>>(P, warps);
+    }
     prof_end(SSDG_PROF_CE, st);
     SSDG_LAUNCH_CHECK();
   }
@@ -547,7 +625,7 @@ extern "C" int ssdg_multibox_loss(const int32_t* gt_cls, const float* gt_box, co
                                   int32_t n_classes, int32_t neg_ratio, double* out_result, uint8_t* out_neg_mask,
                                   float* out_neg_ce, float* grad_box, float* grad_cls, void* workspace,
                                   size_t workspace_bytes, void* stream) {
-  return loss_run(15, 0, 0, gt_cls, gt_box, gt_mask, pred_box, pred_cls, batch, n_priors, n_classes, neg_ratio,
+  return loss_run(15, 0, 0, nullptr, nullptr, gt_cls, gt_box, gt_mask, pred_box, pred_cls, batch, n_priors, n_classes, neg_ratio,
                   out_result, out_neg_mask, out_neg_ce, grad_box, grad_cls, workspace, workspace_bytes, stream);
 }
 
@@ -558,9 +636,20 @@ extern "C" int ssdg_multibox_loss_stage(int32_t stage, int64_t global_priors, co
                                         float* out_neg_ce, float* grad_box, float* grad_cls, void* workspace,
                                         size_t workspace_bytes, void* stream) {
   if (stage < 0 || stage > 3 || global_priors <= 0) return SSDG_ERR_ARG;
-  return loss_run(1 << stage, 1, global_priors, gt_cls, gt_box, gt_mask, pred_box, pred_cls, batch, n_priors,
+  return loss_run(1 << stage, 1, global_priors, nullptr, nullptr, gt_cls, gt_box, gt_mask, pred_box, pred_cls, batch, n_priors,
                   n_classes, neg_ratio, out_result, out_neg_mask, out_neg_ce, grad_box, grad_cls, workspace,
                   workspace_bytes, stream);
+}
+
+extern "C" int ssdg_multibox_loss_fused(const float* row_ml, const float* row_negbg, const int32_t* gt_cls,
+                                        const float* gt_box, const uint8_t* gt_mask, const float* pred_box,
+                                        const float* pred_cls, int64_t batch, int32_t n_priors, int32_t n_classes,
+                                        int32_t neg_ratio, double* out_result, uint8_t* out_neg_mask,
+                                        float* out_neg_ce, float* grad_box, float* grad_cls, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  if (!row_ml || !row_negbg) return SSDG_ERR_ARG;
+  return loss_run(15, 0, 0, row_ml, row_negbg, gt_cls, gt_box, gt_mask, pred_box, pred_cls, batch, n_priors, n_classes,
+                  neg_ratio, out_result, out_neg_mask, out_neg_ce, grad_box, grad_cls, workspace, workspace_bytes, stream);
 }
 
 extern "C" int ssdg_loss_exchange(void* workspace, int32_t which, void** out_ptr, int64_t* out_count) {

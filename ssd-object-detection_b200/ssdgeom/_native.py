@@ -66,7 +66,9 @@ PROTOTYPES = {
     "ssdg_detect": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp, _vp,
                               _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ssdg_detect_stage": (C.c_int, [_i32, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp,
-                                    _vp, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
+                                    _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ssdg_multibox_loss_fused": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp,
+                                           _vp, _vp, _vp, _sz, _vp]),
     "ssdg_nms": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 

@@ -189,9 +189,10 @@ def iou_pairs(boxes_1, boxes_2, use_eps_clamp: bool, stream=None) -> D.DeviceArr
 
 # ---- A6 ----------------------------------------------------------------------------------------------
 def multibox_loss(gt_cls, gt_box, gt_mask, pred_box, pred_cls, neg_ratio: int = 3, want_neg_mask=False,
-                  want_neg_ce=False, want_grad=False, out=None, stream=None, ws_kind="loss") -> dict:
+                  want_neg_ce=False, want_grad=False, out=None, stream=None, ws_kind="loss", row_stats=None) -> dict:
     """models/ssd_model.py:341-396.  Returns {'result': float64[16] device block, ...}; see
-    include/ssdgeom.h for the block layout."""
+    include/ssdgeom.h for the block layout.  row_stats = (row_ml, row_negbg) from ``detect(..., want_row_stats=True)``
+    on the same pred_cls: the loss then skips its own pass over the logits (ssdg_multibox_loss_fused)."""
     gt_cls = D.as_device(gt_cls, np.int32)
     gt_box = D.as_device(gt_box, np.float32)
     gt_mask = D.as_device(gt_mask, np.uint8)
@@ -217,10 +218,16 @@ def multibox_loss(gt_cls, gt_box, gt_mask, pred_box, pred_cls, neg_ratio: int = 
             out["grad_cls"] = D.empty((b, a, c), np.float32)
     lib = N.lib()
     ws = POOL.get(ws_kind, lib.ssdg_loss_workspace_bytes(b, a, c))
-    N.check(lib.ssdg_multibox_loss(gt_cls.ptr, gt_box.ptr, gt_mask.ptr, pred_box.ptr, pred_cls.ptr, b, a, c,
-                                   int(neg_ratio), out["result"].ptr, _p(out.get("neg_mask")), _p(out.get("neg_ce")),
-                                   _p(out.get("grad_box")), _p(out.get("grad_cls")), ws.ptr, ws.nbytes,
-                                   D.stream_handle(stream)), "multibox_loss")
+    args = (gt_cls.ptr, gt_box.ptr, gt_mask.ptr, pred_box.ptr, pred_cls.ptr, b, a, c,
+            int(neg_ratio), out["result"].ptr, _p(out.get("neg_mask")), _p(out.get("neg_ce")),
+            _p(out.get("grad_box")), _p(out.get("grad_cls")), ws.ptr, ws.nbytes, D.stream_handle(stream))
+    if row_stats is None:
+        N.check(lib.ssdg_multibox_loss(*args), "multibox_loss")
+    else:
+        row_ml, row_negbg = row_stats
+        if row_ml.size != 2 * b * a or row_negbg.size != b * a:
+            raise AssertionError("row statistics disagree with pred_cls in shape")
+        N.check(lib.ssdg_multibox_loss_fused(row_ml.ptr, row_negbg.ptr, *args), "multibox_loss_fused")
     out["_keep"] = (gt_cls, gt_box, gt_mask, pred_box, pred_cls, ws)
     return out
 
@@ -332,7 +339,8 @@ def loss_result_to_host(result: D.DeviceArray, stream=None) -> dict:
 
 # ---- A7 + A8 + A9 ---------------------------------------------------------------------------------------
 def detect(pred_cls, pred_box, priors, score_thresh=0.01, top_k=200, iou_thresh=0.45, want_scores=False,
-           want_boxes=False, want_probs=False, head_thresh=None, out=None, stream=None, stage=None) -> dict:
+           want_boxes=False, want_probs=False, head_thresh=None, out=None, stream=None, stage=None,
+           want_row_stats=False) -> dict:
     """stage: None = the whole post-processing; 0 = filter + decode + bucketing only; 1 = the NMS of a previous
     stage-0 call with the same arguments (include/ssdgeom.h, ssdg_detect_stage)."""
     pred_cls = D.as_device(pred_cls, np.float32)
@@ -355,6 +363,9 @@ def detect(pred_cls, pred_box, priors, score_thresh=0.01, top_k=200, iou_thresh=
         need("boxes", (b, a, 4), np.float32)
     if want_probs:
         need("probs", (b, a, c), np.float32)
+    if want_row_stats:           # per-prior softmax statistics for multibox_loss(row_stats=...)
+        need("row_ml", (b, a, 2), np.float32)
+        need("row_negbg", (b, a), np.float32)
     if head_thresh is not None:
         need("head_score", (b, a), np.float32)
         need("head_cls", (b, a), np.int32)
@@ -365,11 +376,14 @@ def detect(pred_cls, pred_box, priors, score_thresh=0.01, top_k=200, iou_thresh=
             int(top_k), float(iou_thresh), out["kept"].ptr, out["count"].ptr, _p(out.get("kept_score")),
             _p(out.get("boxes")), _p(out.get("probs")),
             float(head_thresh if head_thresh is not None else 0.0), _p(out.get("head_score")),
-            _p(out.get("head_cls")), _p(out.get("head_mask")), ws.ptr, ws.nbytes, D.stream_handle(stream))
-    if stage is None:
-        N.check(lib.ssdg_detect(*args), "detect")
+            _p(out.get("head_cls")), _p(out.get("head_mask")))
+    tail = (ws.ptr, ws.nbytes, D.stream_handle(stream))
+    if stage is None and not want_row_stats:
+        N.check(lib.ssdg_detect(*args, *tail), "detect")
     else:
-        N.check(lib.ssdg_detect_stage(int(stage), *args), "detect_stage")
+        stats = (_p(out.get("row_ml")), _p(out.get("row_negbg"))) if want_row_stats else (None, None)
+        for st in ((0, 1) if stage is None else (int(stage),)):
+            N.check(lib.ssdg_detect_stage(st, *args, *stats, *tail), "detect_stage")
     out["_keep"] = (pred_cls, pred_box, priors, ws)
     return out
 

@@ -618,3 +618,32 @@ def test_detect_full_batch_properties(priors300):
     k1 = h1["kept"].to_host()
     h2 = ops.detect(pred_cls[32:], pred_box[32:], priors300)
     assert np.array_equal(np.concatenate([k1, h2["kept"].to_host()]), kept)
+
+
+def test_loss_from_filter_row_statistics(priors300):
+    """The chained step's single pass over the logits: the softmax filter leaves per-prior (max, log-sum) and the
+    background CE, and ssdg_multibox_loss_fused must give the loss of the standalone path -- per-prior CE within
+    tolerance of the float64 oracle, the mask bit-exact on its own CE vector (two-stage contract), same counts."""
+    batch = 5
+    boxes, cls, off = synth.make_gt(41, batch, 100, "coco")
+    y_true = _targets(boxes, cls, off, priors300, batch)
+    for bias in (7.0, 0.0):
+        pred_cls, pred_box = synth.make_predictions(41, batch, 8732, bg_bias=bias)
+        d_cls = D.to_device(pred_cls)
+        det = ops.detect(d_cls, pred_box, priors300, want_row_stats=True)
+        plain = ops.detect(d_cls, pred_box, priors300)
+        assert np.array_equal(det["kept"].to_host(), plain["kept"].to_host())          # the statistics are a by-product
+        assert np.array_equal(det["count"].to_host(), plain["count"].to_host())
+        fused = ops.multibox_loss(y_true[0], y_true[1], y_true[2], pred_box, d_cls, want_neg_mask=True, want_neg_ce=True,
+                                  row_stats=(det["row_ml"], det["row_negbg"]), ws_kind="loss_fused")
+        r = ops.loss_result_to_host(fused["result"])
+        w_total, w_info, w_aux = O.ssd_loss(y_true, (pred_box, pred_cls), return_masks=True)
+        close(r["total"], w_total)
+        for k in ("cls loss pos", "cls loss neg", "loc loss"):
+            close(r[k], w_info[k])
+        neg_ce, neg_mask = fused["neg_ce"].to_host(), fused["neg_mask"].to_host().astype(bool)
+        close(neg_ce, w_aux["neg_ce"], rtol=RTOL, atol=1e-6)
+        kth, want_mask = O.hard_negative_select(neg_ce, r["num_pos"], 3)
+        assert np.array_equal(neg_mask, want_mask) and np.float32(r["kth"]) == kth
+        assert r["num_pos"] == w_aux["num_pos"] and r["num_neg"] == int(want_mask.sum())
+        assert int(np.sum(neg_mask != w_aux["neg_mask"])) <= 2      # end to end vs the float64 oracle (reported)
