@@ -76,8 +76,11 @@ struct MatchParams {
   float* out_loc;
   uint8_t* out_mask;
   int* out_match;
-  u32* ws_head;             // [0] next image, [1] status bits
-  Cand* ws_cand;            // per CTA kCandCap
+  u32* ws_head;             // [0] next image, [1] status bits, [2] next row of the search kernel
+  u32* ws_ncand;            // [B] listed pairs of the image
+  u64* ws_rowkey;           // [B*tm] row maximum (key64) found by the search kernel
+  int* ws_rowcol;           // [B*tm] its first arg-max prior
+  Cand* ws_cand;            // per image kCandCap
   u64* ws_colkey;           // per CTA A
   int* ws_colt;             // per CTA A
   u32* ws_bits;             // per CTA 2*elim_words (knocked-out columns, touched columns) when not in smem
@@ -228,7 +231,6 @@ struct MatchSmem {
   int* red_idx;
   int* ctl;                          // control words, see enum
   TileStat* tiles_s;                 // staged tile statistics (when they fit)
-  float* ub_s;                       // [warps][ntiles_s] per-warp cache of the rows' tile bounds
   u32 *elim_s, *touch_s;             // bitmaps (when they fit)
   __device__ void carve(unsigned char* base, int tm, int ntiles_s, int bit_words) {
     size_t o = 0;
@@ -240,7 +242,6 @@ struct MatchSmem {
     o = (o + 15) & ~(size_t)15;
     cbox = (float4*)(base + o); o += 16 * (size_t)tm;
     tiles_s = (TileStat*)(base + o); o += sizeof(TileStat) * (size_t)ntiles_s;
-    ub_s = (float*)(base + o); o += 4 * (size_t)ntiles_s * (SSDG_MATCH_THREADS / 32);
     rowkey = (u64*)(base + o); o += 8 * (size_t)tm;
     galo = (float*)(base + o); o += 4 * (size_t)tm;
     rowcol = (int*)(base + o); o += 4 * (size_t)tm;
@@ -256,8 +257,142 @@ struct MatchSmem {
   }
 };
 static size_t match_smem_bytes(int tm, int ntiles_s, int bit_words) {
-  return (size_t)tm * (5 * 8 + 16 + 8 + 4 + 20 + 1) + (size_t)ntiles_s * (sizeof(TileStat) + 4 * (SSDG_MATCH_THREADS / 32)) +
+  return (size_t)tm * (5 * 8 + 16 + 8 + 4 + 20 + 1) + (size_t)ntiles_s * sizeof(TileStat) +
          (size_t)bit_words * 8 + 16 + 64 + 96;
+}
+
+// ---- search: the row maxima of the whole batch --------------------------------------------------------------
+// One warp per ground-truth ROW, rows handed out dynamically over the whole batch (they differ in cost and the
+// images in row count): small CTAs that fill every SM evenly and fit beside the streaming kernels of the other
+// branch.  Per row: the first arg-max prior (exact formula) and every pair above the threshold, appended to the
+// image's list.  The per-image kernel below consumes both.
+constexpr int kSearchThreads = 128;
+constexpr int kSearchWarps = kSearchThreads / 32;
+
+template <typename TG, typename TP>
+__global__ void __launch_bounds__(kSearchThreads, 8) search_kernel(MatchParams P) {
+  typedef typename Promote<TG, TP>::type R;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int A = P.A, ntiles = P.ntiles;
+  const bool cached = ntiles <= kTileSmemMax;   // per-warp cache of the row's tile bounds
+  float* ubw = reinterpret_cast<float*>(smem_raw) + (size_t)warp * (cached ? ntiles : 0);
+  const TileStat* tiles = P.tiles;
+  const R EPS = (R)1e-10;
+  const u64 thr_key = key64((double)(R)P.thresh);
+  const float thr_lo = f_down((double)(R)P.thresh);
+  const int total_rows = P.gt_off[P.B];
+  for (;;) {
+    int gr = 0;
+    if (lane == 0) gr = (int)atomicAdd(&P.ws_head[2], 1u);
+    gr = __shfl_sync(SSDG_FULL, gr, 0);
+    if (gr >= total_rows) break;
+    // image of the row: last b with gt_off[b] <= gr
+    int lo = 0, hi = P.B;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(P.gt_off + mid) <= gr) lo = mid; else hi = mid;
+    }
+    const int img = lo, g0 = __ldg(P.gt_off + img);
+    const int T = __ldg(P.gt_off + img + 1) - g0, t = gr - g0;
+    if (t < 0 || t >= T || T > P.max_gt || T > A) continue;   // malformed offsets / flagged images: no rows
+    Corners<R> g;
+    float4 gb;
+    float galo;
+    {
+      TG cx, cy, w, h;
+      Vec4<TG>::load(P.gt_boxes, gr, cx, cy, w, h);
+      const Corners<TG> c = corners_of<TG>(cx, cy, w, h);
+      g.x1 = (R)c.x1; g.y1 = (R)c.y1; g.x2 = (R)c.x2; g.y2 = (R)c.y2; g.area = (R)c.area;
+      const bool ok = finite4((double)g.x1, (double)g.y1, (double)g.x2, (double)g.y2) && isfinite((double)g.area);
+      gb = make_float4(f_down((double)g.x1), f_down((double)g.y1), f_up((double)g.x2), f_up((double)g.y2));
+      galo = ok ? f_down((double)g.area) : CUDART_NAN_F;
+    }
+    Cand* cand = P.ws_cand + (size_t)img * kCandCap;
+    u64 best_key = 0ull;
+    int best_a = 0x7fffffff;
+    float rowlo = 0.f;
+    // exact evaluation of one tile for this row (all lanes)
+    auto evaluate = [&](int tile) {
+      const int slot = (tile << 5) + lane;
+      const int a = P.perm ? __ldg(P.perm + slot) : slot;
+      const bool valid = a >= 0 && a < A;
+      u64 key = 0ull;
+      if (valid) {
+        Corners<R> p;
+        TP dx, dy, dw, dh;
+        Vec4<TP>::load(P.pprior ? P.pprior : P.priors, P.pprior ? slot : a, dx, dy, dw, dh);
+        const Corners<TP> c = corners_of<TP>(dx, dy, dw, dh);
+        p.x1 = (R)c.x1; p.y1 = (R)c.y1; p.x2 = (R)c.x2; p.y2 = (R)c.y2; p.area = (R)c.area;
+        key = key64((double)iou_corners<R>(g, p, EPS));
+      }
+      const bool listed = key > thr_key;   // phase-2 candidate; one counter update per warp
+      const u32 lm = __ballot_sync(SSDG_FULL, listed);
+      if (lm) {
+        const int leader = __ffs(lm) - 1;
+        int base = 0;
+        if (lane == leader) base = (int)atomicAdd(&P.ws_ncand[img], (u32)__popc(lm));
+        base = __shfl_sync(SSDG_FULL, base, leader);
+        if (listed) {
+          const int pos = base + __popc(lm & ((1u << lane) - 1u));
+          if (pos < kCandCap) { Cand c; c.key = key; c.a = a; c.t = t; cand[pos] = c; }
+        }
+      }
+      u64 wk = key;
+      int wa = valid ? a : 0x7fffffff;
+      warp_argmax_u64(wk, wa);
+      if (wk > best_key || (wk == best_key && wa < best_a)) {
+        best_key = wk; best_a = wa;
+        rowlo = fmaxf(f_down(unkey64(wk)), 0.f);
+      }
+    };
+    // pass 1: bound every tile; the highest bound seeds the running maximum
+    float sub = -1.f;
+    int stile = 0x7fffffff;
+#pragma unroll 4
+    for (int tb = 0; tb < ntiles; tb += 32) {
+      const int tile = tb + lane;
+      if (tile < ntiles) {
+        const TileStat ts = tiles[tile];
+        float iub, dlb;
+        iou_bound(gb, galo, ts, iub, dlb);
+        const float ub = (ts.safe && dlb > 0.f) ? __fdividef(iub, dlb) * 1.0002f : CUDART_INF_F;
+        if (cached) ubw[tile] = ub;
+        if (ub > sub) { sub = ub; stile = tile; }
+      }
+    }
+    {
+      const u32 m = __reduce_max_sync(SSDG_FULL, key32(sub));
+      stile = (int)__reduce_min_sync(SSDG_FULL, key32(sub) == m ? (u32)stile : 0x7fffffffu);
+    }
+    __syncwarp();
+    evaluate(stile);
+    // pass 2: every other tile whose bound still reaches min(thresh, running maximum)
+    for (int tb = 0; tb < ntiles; tb += 32) {
+      const int tile = tb + lane;
+      bool pending = tile < ntiles && tile != stile;
+      float ub = 0.f;
+      TileStat ts;
+      ts.x1 = ts.y1 = ts.x2 = ts.y2 = ts.wmax = ts.hmax = ts.amin = ts.cx1 = ts.cy1 = ts.cx2 = ts.cy2 = 0.f; ts.safe = 1u;
+      if (pending) {
+        if (cached) ub = ubw[tile]; else ts = tiles[tile];
+      }
+      for (;;) {
+        const float bound = fminf(thr_lo, rowlo);
+        const bool reach = pending && (cached ? !(ub < bound) : may_reach(gb, galo, ts, bound));
+        const u32 m = __ballot_sync(SSDG_FULL, reach);
+        if (!m) break;
+        const int l = __ffs(m) - 1;
+        if (lane == l) pending = false;
+        evaluate(tb + l);
+      }
+    }
+    if (lane == 0) {
+      P.ws_rowkey[(size_t)img * P.tm + t] = best_key;
+      P.ws_rowcol[(size_t)img * P.tm + t] = best_a;
+    }
+    __syncwarp();
+  }
 }
 
 enum { C_IMG = 0, C_NCAND, C_NRS, C_DONE, C_ROUND, C_DEGEN, C_MINELIM, C_NEXTROW, C_RLO, C_RA, C_RKEY_LO, C_RKEY_HI, C_GENERIC, C_HEAD, C_NLIVE };
@@ -276,7 +411,6 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
   const TileStat* tiles = tiles_in_smem ? S.tiles_s : P.tiles;
   u32* elim = P.bits_in_smem ? S.elim_s : P.ws_bits + (size_t)blockIdx.x * 2 * P.elim_words;
   u32* touch = P.bits_in_smem ? S.touch_s : elim + P.elim_words;
-  Cand* cand = P.ws_cand + (size_t)blockIdx.x * kCandCap;
   u64* colkey = P.ws_colkey + (size_t)blockIdx.x * A;
   int* colt = P.ws_colt + (size_t)blockIdx.x * A;
   const u64 thr_key = key64((double)(R)P.thresh);
@@ -322,6 +456,7 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
     if (T > A) { if (tid == 0) atomicOr(&P.ws_head[1], 2u); bad = true; }
     if (bad) T = 0;  // outputs for the image are still fully written (all unmatched)
     const size_t obase = (size_t)img * A;
+    const Cand* cand = P.ws_cand + (size_t)img * kCandCap;
 
     // ---- per-image setup -------------------------------------------------------------------
     for (int t = tid; t < T; t += kMatchThreads) {
@@ -333,8 +468,8 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
       const bool ok = finite4((double)x1, (double)y1, (double)x2, (double)y2) && isfinite((double)ar);
       S.cbox[t] = make_float4(f_down((double)x1), f_down((double)y1), f_up((double)x2), f_up((double)y2));
       S.galo[t] = ok ? f_down((double)ar) : CUDART_NAN_F;
-      S.rowkey[t] = 0ull;
-      S.rowcol[t] = 0x7fffffff;
+      S.rowkey[t] = P.ws_rowkey[(size_t)img * P.tm + t];     // the search kernel's result for this row
+      S.rowcol[t] = P.ws_rowcol[(size_t)img * P.tm + t];
       S.dead[t] = 0;
     }
     for (int w = tid; w < P.elim_words; w += kMatchThreads) { elim[w] = 0u; touch[w] = 0u; }
@@ -343,113 +478,6 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
       S.ctl[C_MINELIM] = 0x7fffffff; S.ctl[C_NEXTROW] = 0; S.ctl[C_GENERIC] = 0; S.ctl[C_HEAD] = 0; S.ctl[C_NLIVE] = -1;
     }
     __syncthreads();
-
-    // ---- search: one warp per row; `subset`: only the rows in rs_list, over the live columns ---------
-    auto search = [&](const bool subset) {
-      const int nrow = subset ? S.ctl[C_NRS] : T;
-      for (;;) {
-        int k = 0;
-        if (lane == 0) k = atomicAdd(&S.ctl[C_NEXTROW], 1);    // rows differ in cost: hand them out dynamically
-        k = __shfl_sync(SSDG_FULL, k, 0);
-        if (k >= nrow) break;
-        const int t = subset ? S.rs_list[k] : k;
-        const Corners<R> g = load_gt(t);
-        const float4 gb = S.cbox[t];
-        const float galo = S.galo[t];
-        u64 best_key = 0ull;
-        int best_a = 0x7fffffff;
-        float rowlo = 0.f;
-        // exact evaluation of one tile for this row (all lanes)
-        auto evaluate = [&](int tile) {
-          const int slot = (tile << 5) + lane;
-          const int a = P.perm ? __ldg(P.perm + slot) : slot;
-          bool valid = a >= 0 && a < A;
-          if (subset && valid && bit_test(elim, a)) valid = false;
-          u64 key = 0ull;
-          if (valid) {
-            Corners<R> p; TP dx, dy, dw, dh;
-            if (P.pprior) {   // slot-ordered copy: no dependent load behind the permutation
-              Vec4<TP>::load(P.pprior, slot, dx, dy, dw, dh);
-              Corners<TP> c = corners_of<TP>(dx, dy, dw, dh);
-              p.x1 = (R)c.x1; p.y1 = (R)c.y1; p.x2 = (R)c.x2; p.y2 = (R)c.y2; p.area = (R)c.area;
-            } else {
-              load_prior(a, p, dx, dy, dw, dh);
-            }
-            key = key64((double)iou_corners<R>(g, p, EPS));
-            if (!subset && key > thr_key) {   // phase-2 candidate
-              const int pos = atomicAdd(&S.ctl[C_NCAND], 1);
-              if (pos < kCandCap) { Cand c; c.key = key; c.a = a; c.t = t; cand[pos] = c; }
-            }
-          }
-          u64 wk = key;
-          int wa = valid ? a : 0x7fffffff;
-          warp_argmax_u64(wk, wa);
-          if (wk > best_key || (wk == best_key && wa < best_a)) {
-            best_key = wk; best_a = wa;
-            rowlo = fmaxf(f_down(unkey64(wk)), 0.f);
-          }
-        };
-#ifdef SSDG_MATCH_TIMING
-        long long w0 = clock64(), wev = 0, w1 = 0; int nev = 0;
-#define EVAL(x) do { long long e0_ = clock64(); evaluate(x); wev += clock64() - e0_; ++nev; } while (0)
-#else
-#define EVAL(x) evaluate(x)
-#endif
-        // pass 1: bound every tile (cached per warp when the tiles are staged); the highest seeds the maximum
-        float sub = -1.f;
-        int stile = 0x7fffffff;
-        float* ubw = S.ub_s + (size_t)warp * ntiles;
-#pragma unroll 4
-        for (int tb = 0; tb < ntiles; tb += 32) {
-          const int tile = tb + lane;
-          if (tile < ntiles) {
-            const TileStat ts = tiles[tile];
-            float iub, dlb;
-            iou_bound(gb, galo, ts, iub, dlb);
-            const float ub = (ts.safe && dlb > 0.f) ? __fdividef(iub, dlb) * 1.0002f : CUDART_INF_F;
-            if (tiles_in_smem) ubw[tile] = ub;
-            if (ub > sub) { sub = ub; stile = tile; }
-          }
-        }
-        {
-          const u32 m = __reduce_max_sync(SSDG_FULL, key32(sub));
-          stile = (int)__reduce_min_sync(SSDG_FULL, key32(sub) == m ? (u32)stile : 0x7fffffffu);
-        }
-#ifdef SSDG_MATCH_TIMING
-        w1 = clock64();
-#endif
-        EVAL(stile);
-        // pass 2: every other tile whose bound still reaches min(thresh, running maximum)
-        for (int tb = 0; tb < ntiles; tb += 32) {
-          const int tile = tb + lane;
-          bool pending = tile < ntiles && tile != stile;
-          float ub = 0.f;
-          TileStat ts;
-          ts.x1 = ts.y1 = ts.x2 = ts.y2 = ts.wmax = ts.hmax = ts.amin = ts.cx1 = ts.cy1 = ts.cx2 = ts.cy2 = 0.f; ts.safe = 1u;
-          if (pending) {
-            if (tiles_in_smem) ub = ubw[tile]; else ts = tiles[tile];
-          }
-          for (;;) {
-            const float bound = fminf(thr_lo, rowlo);
-            const bool reach = pending && (tiles_in_smem ? !(ub < bound) : may_reach(gb, galo, ts, bound));
-            const u32 m = __ballot_sync(SSDG_FULL, reach);
-            if (!m) break;
-            const int l = __ffs(m) - 1;
-            if (lane == l) pending = false;
-            EVAL(tb + l);
-          }
-        }
-        if (lane == 0) { S.rowkey[t] = best_key; S.rowcol[t] = best_a; }
-#ifdef SSDG_MATCH_TIMING
-        if (lane == 0 && !subset) {
-          atomicAdd((unsigned long long*)&P.ws_head[24], (unsigned long long)(w1 - w0));                 // pass 1
-          atomicAdd((unsigned long long*)&P.ws_head[26], (unsigned long long)wev);                       // evaluations
-          atomicAdd((unsigned long long*)&P.ws_head[28], (unsigned long long)(clock64() - w1 - wev));    // pass 2 tests
-          atomicAdd((unsigned long long*)&P.ws_head[30], (unsigned long long)nev);
-        }
-#endif
-      }
-    };
 
     TICK(0);
     // Re-search of ONE row over the live columns by the whole CTA (a row whose cached column was taken):
@@ -514,13 +542,10 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
       __syncthreads();
     };
 
-    search(false);
-    __syncthreads();
-    if (tid == 0) S.ctl[C_NEXTROW] = 0;
     TICK(1);
 
     // ---- phase 2: first-arg-max row of every listed prior ---------------------------------------------
-    const int ncand_raw = S.ctl[C_NCAND];
+    const int ncand_raw = bad ? 0 : (int)P.ws_ncand[img];
     const bool cand_overflow = ncand_raw > kCandCap;
     const int ncand = cand_overflow ? 0 : ncand_raw;
     if (cand_overflow) {
@@ -793,6 +818,15 @@ static int launch_match(const MatchParams& P, int grid, size_t smem, cudaStream_
   // same shared-memory carve-out as the streaming kernels so CTAs of both can share an SM
   SSDG_CUDA_TRY(cudaFuncSetAttribute(match_kernel<TG, TP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   prof_begin(SSDG_PROF_MATCH, st);
+  {
+    const size_t ssm = P.ntiles <= kTileSmemMax ? (size_t)kSearchWarps * P.ntiles * 4 : 0;
+    SSDG_CUDA_TRY(cudaFuncSetAttribute(search_kernel<TG, TP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    long long sgrid = (long long)sm_count() * 8;
+    const long long want = ((long long)P.B * (P.max_gt > 0 ? P.max_gt : 1) + kSearchWarps - 1) / kSearchWarps;
+    if (want < sgrid) sgrid = want;
+    search_kernel<TG, TP><<<(unsigned)sgrid, kSearchThreads, ssm, st>>>(P);
+    SSDG_LAUNCH_CHECK();
+  }
   match_kernel<TG, TP><<<grid, kMatchThreads, smem, st>>>(P);
   prof_end(SSDG_PROF_MATCH, st);
   SSDG_LAUNCH_CHECK();
@@ -808,19 +842,33 @@ static int match_grid(int batch) {
 
 struct MatchWs {
   u32* head;
+  u32* ncand;
+  u64* rowkey;
+  int* rowcol;
   Cand* cand;
   u64* colkey;
   int* colt;
   u32* bits;
   TileStat* tiles;
 };
-static size_t match_ws_layout(int n_priors, int ctas, MatchWs* out, unsigned char* base) {
+static int match_tm(int max_gt) {
+  const int tm = ((max_gt + 31) / 32) * 32;
+  return tm == 0 ? 32 : tm;
+}
+static size_t match_ws_layout(int batch, int n_priors, int max_gt, int ctas, MatchWs* out, unsigned char* base) {
   size_t o = 0;
   const size_t words = ((size_t)n_priors + 31) / 32;
+  const size_t rows = (size_t)batch * match_tm(max_gt);
   if (out) out->head = (u32*)(base + o);
   o += 256;
+  if (out) out->ncand = (u32*)(base + o);          // directly behind the head: cleared by the same memset
+  o += align_up((size_t)batch * 4, 256);
+  if (out) out->rowkey = (u64*)(base + o);
+  o += align_up(rows * 8, 256);
+  if (out) out->rowcol = (int*)(base + o);
+  o += align_up(rows * 4, 256);
   if (out) out->cand = (Cand*)(base + o);
-  o += align_up((size_t)ctas * kCandCap * sizeof(Cand), 256);
+  o += align_up((size_t)batch * kCandCap * sizeof(Cand), 256);
   if (out) out->colkey = (u64*)(base + o);
   o += align_up((size_t)ctas * n_priors * 8, 256);
   if (out) out->colt = (int*)(base + o);
@@ -945,9 +993,9 @@ extern "C" int ssdg_prior_index_build(const void* priors, int32_t prior_dtype, i
 }
 
 extern "C" size_t ssdg_match_workspace_bytes(int32_t batch, int32_t n_priors, int32_t max_gt) {
-  (void)max_gt;
-  if (batch <= 0 || n_priors <= 0) return 0;
-  return match_ws_layout(n_priors, match_ws_ctas(batch), nullptr, nullptr);
+  if (batch <= 0 || n_priors <= 0 || max_gt < 0) return 0;
+  if (max_gt > n_priors) max_gt = n_priors;
+  return match_ws_layout(batch, n_priors, max_gt, match_ws_ctas(batch), nullptr, nullptr);
 }
 
 extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const float* gt_cls,
@@ -967,15 +1015,14 @@ extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const f
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = match_grid(batch);
   MatchWs ws;
-  match_ws_layout(n_priors, match_ws_ctas(batch), &ws, (unsigned char*)workspace);
+  match_ws_layout(batch, n_priors, max_gt, match_ws_ctas(batch), &ws, (unsigned char*)workspace);
   MatchParams P;
   P.gt_boxes = gt_boxes; P.gt_cls = gt_cls; P.gt_off = gt_offsets; P.priors = priors;
-  P.B = batch; P.A = n_priors; P.max_gt = max_gt; P.tm = ((max_gt + 31) / 32) * 32;
-  if (P.tm == 0) P.tm = 32;
+  P.B = batch; P.A = n_priors; P.max_gt = max_gt; P.tm = match_tm(max_gt);
   P.thresh = thresh;
   P.out_cls = out_cls; P.out_box = out_box; P.out_loc = out_loc; P.out_mask = out_mask; P.out_match = out_match;
   P.elim_words = (n_priors + 31) / 32;
-  P.ws_head = ws.head; P.ws_cand = ws.cand; P.ws_colkey = ws.colkey; P.ws_colt = ws.colt; P.ws_bits = ws.bits;
+  P.ws_head = ws.head; P.ws_ncand = ws.ncand; P.ws_rowkey = ws.rowkey; P.ws_rowcol = ws.rowcol; P.ws_cand = ws.cand; P.ws_colkey = ws.colkey; P.ws_colt = ws.colt; P.ws_bits = ws.bits;
   P.tiles = ws.tiles; P.perm = nullptr; P.unmatched = nullptr; P.pprior = nullptr; P.ntiles = (n_priors + 31) / 32;
   if (prior_index) {
     IndexInfo info;
@@ -993,7 +1040,7 @@ extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const f
     P.pprior = ib + index_pprior_offset(n_priors);
     P.ntiles = info.ntiles;
   }
-  SSDG_CUDA_TRY(cudaMemsetAsync(P.ws_head, 0, 256, st));
+  SSDG_CUDA_TRY(cudaMemsetAsync(P.ws_head, 0, 256 + align_up((size_t)batch * 4, 256), st));
   P.bits_in_smem = P.elim_words <= kElimSmemWords ? 1 : 0;
   const size_t smem = match_smem_bytes(P.tm, P.ntiles <= kTileSmemMax ? P.ntiles : 0, P.bits_in_smem ? P.elim_words : 0);
   if ((int)smem > max_smem_optin()) return SSDG_ERR_LIMIT;
