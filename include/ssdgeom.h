@@ -87,12 +87,17 @@ SSDG_API int ssdg_event_elapsed_ms(void* start, void* stop, float* ms); /* synch
 #define SSDG_PROF_CE 1
 #define SSDG_PROF_FILTER 2
 #define SSDG_PROF_NMS 3
+#define SSDG_PROF_BUCKET 4      /* bucket_kernel */
+#define SSDG_PROF_SEARCH 5      /* search_kernel (SSDG_PROF_MATCH covers search + per-image kernel) */
+#define SSDG_PROF_LOSS_TAIL 6   /* select_kernel x2 + final_kernel */
 SSDG_API int ssdg_profile_enable(int enable);
 /* Scheduling hook: when set (non-NULL), ssdg_detect / ssdg_nms record this cudaEvent_t on their stream right
  * after the HBM-bound filter + bucket kernels and before the ALU-bound nms_kernel, so a caller can start
  * latency-bound work (the matcher) on another stream exactly when it overlaps best.  NULL clears it. */
 SSDG_API int ssdg_detect_set_mid_event(void* event);
 SSDG_API int ssdg_profile_last_ms(int which, float* ms);
+/* Begin / end of the bracketed kernel relative to a caller-recorded event (ms): a timeline of one step. */
+SSDG_API int ssdg_profile_span_ms(int32_t which, void* ref_event, float* begin_ms, float* end_ms);
 
 /* ---- A1: anchors -------------------------------------------------------------------------------
  * Replaces SSDObjectDetectionModel._build_prior_box(size_list)      models/ssd_model.py:173-194

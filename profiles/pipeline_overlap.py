@@ -36,15 +36,24 @@ def timed(label, branches, reps=15):
         ts.append(e0.elapsed_ms(e1) * 1e3)
     print("%-34s %8.1f us" % (label, statistics.median(ts[3:])), flush=True)
 
-filt = lambda s: hp.detect_stage(s, stage=0)
-nms = lambda s: hp.detect_stage(s, stage=1)
+filt = lambda s: hp.detect_stage(s, stage=0, stats=True)
+nms = lambda s: hp.detect_stage(s, stage=1, stats=True)
+loss = lambda s: hp.loss_stage(s, stats=True)
 timed("filter+bucket", [(hp.s_d, [filt])])
 timed("match", [(hp.s_a, [hp.assign])])
 timed("filter+bucket || match", [(hp.s_d, [filt]), (hp.s_a, [hp.assign])])
 timed("nms", [(hp.s_n, [nms])])
-timed("loss", [(hp.s_l, [hp.loss_stage])])
-timed("nms(low) || loss(high)", [(hp.s_n, [nms]), (hp.s_l, [hp.loss_stage])])
-timed("nms(high) || loss(low)", [(hp.s_d, [nms]), (hp.s_a, [hp.loss_stage])])
+timed("loss", [(hp.s_l, [loss])])
+timed("nms(low) || loss(high)", [(hp.s_n, [nms]), (hp.s_l, [loss])])
+timed("nms(high) || loss(low)", [(hp.s_d, [nms]), (hp.s_a, [loss])])
 timed("nms || match", [(hp.s_n, [nms]), (hp.s_a, [hp.assign])])
-timed("filter+bucket || loss", [(hp.s_d, [filt]), (hp.s_l, [hp.loss_stage])])
-timed("filter+bucket+nms || match+loss", [(hp.s_d, [filt, nms]), (hp.s_a, [hp.assign, hp.loss_stage])])
+timed("filter+bucket || loss", [(hp.s_d, [filt]), (hp.s_l, [loss])])
+timed("filter+bucket+nms || match+loss", [(hp.s_d, [filt, nms]), (hp.s_a, [hp.assign, loss])])
+
+def full():
+    e0, e1 = D.Event(), D.Event()
+    ts = []
+    for _ in range(15):
+        e0.record(hp.s_main); hp.step(); e1.record(hp.s_main); hp.s_main.sync(); ts.append(e0.elapsed_ms(e1) * 1e3)
+    return statistics.median(ts[3:])
+print("%-34s %8.1f us" % ("HotPath.step (split, fused)", full()))

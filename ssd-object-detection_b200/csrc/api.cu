@@ -57,6 +57,15 @@ int ssdg_profile_enable(int enable) {
   ssdg::g_prof = enable != 0;
   return SSDG_OK;
 }
+int ssdg_profile_span_ms(int32_t which, void* ref_event, float* begin_ms, float* end_ms) {
+  if (which < 0 || which >= 8 || !ref_event || !begin_ms || !end_ms) return SSDG_ERR_ARG;
+  if (!ssdg::g_prof_have[which]) return SSDG_ERR_ARG;
+  cudaError_t e = cudaEventSynchronize(ssdg::g_prof_ev[which][1]);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaEventElapsedTime(begin_ms, (cudaEvent_t)ref_event, ssdg::g_prof_ev[which][0]);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaEventElapsedTime(end_ms, (cudaEvent_t)ref_event, ssdg::g_prof_ev[which][1]);
+}
 int ssdg_profile_last_ms(int which, float* ms) {
   if (which < 0 || which >= 8 || !ms) return SSDG_ERR_ARG;
   if (!ssdg::g_prof_have[which]) { *ms = 0.f; return SSDG_ERR_ARG; }

@@ -825,7 +825,9 @@ static int run_filter(DetectParams& P, int prior_dtype, cudaStream_t st) {
     if ((int)bsm > max_smem_optin()) return SSDG_ERR_LIMIT;
     if (bsm > 48 * 1024)
       SSDG_CUDA_TRY(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    prof_begin(SSDG_PROF_BUCKET, st);
     bucket_kernel<<<P.B, kBucketThreads, bsm, st>>>(P);
+    prof_end(SSDG_PROF_BUCKET, st);
   }
   SSDG_LAUNCH_CHECK();
   if (detect_mid_event()) SSDG_CUDA_TRY(cudaEventRecord(detect_mid_event(), st));

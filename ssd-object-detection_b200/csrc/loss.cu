@@ -601,6 +601,7 @@ static int loss_run(int stages, int global, long long n_all, const float* row_ml
   const long long sneed = (P.N / 4 + 255) / 256;
   if (sneed < sgrid) sgrid = (int)(sneed > 0 ? sneed : 1);
   if (sgrid > 1024) sgrid = 1024;
+  if (stages & 6) prof_begin(SSDG_PROF_LOSS_TAIL, st);
   if (stages & 6) {
     SSDG_CUDA_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (stages & 2) select_kernel<<<sgrid, 256, 0, st>>>(P, 1);
@@ -610,6 +611,7 @@ static int loss_run(int stages, int global, long long n_all, const float* row_ml
   if (stages & 8) {
     SSDG_CUDA_TRY(cudaFuncSetAttribute(final_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     final_kernel<<<sgrid, 256, 0, st>>>(P);
+    prof_end(SSDG_PROF_LOSS_TAIL, st);
     SSDG_LAUNCH_CHECK();
     if (grad_cls) {
       int ggrid = sm_count() * 8;

@@ -276,8 +276,13 @@ __global__ void __launch_bounds__(kSearchThreads, 8) search_kernel(MatchParams P
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int A = P.A, ntiles = P.ntiles;
   const bool cached = ntiles <= kTileSmemMax;   // per-warp cache of the row's tile bounds
-  float* ubw = reinterpret_cast<float*>(smem_raw) + (size_t)warp * (cached ? ntiles : 0);
-  const TileStat* tiles = P.tiles;
+  TileStat* tiles_s = reinterpret_cast<TileStat*>(smem_raw);            // staged once per (persistent) CTA
+  float* ubw = reinterpret_cast<float*>(tiles_s + (cached ? ntiles : 0)) + (size_t)warp * (cached ? ntiles : 0);
+  if (cached) {
+    for (int i = tid; i < ntiles; i += kSearchThreads) tiles_s[i] = P.tiles[i];
+    __syncthreads();
+  }
+  const TileStat* tiles = cached ? tiles_s : P.tiles;
   const R EPS = (R)1e-10;
   const u64 thr_key = key64((double)(R)P.thresh);
   const float thr_lo = f_down((double)(R)P.thresh);
@@ -819,12 +824,16 @@ static int launch_match(const MatchParams& P, int grid, size_t smem, cudaStream_
   SSDG_CUDA_TRY(cudaFuncSetAttribute(match_kernel<TG, TP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   prof_begin(SSDG_PROF_MATCH, st);
   {
-    const size_t ssm = P.ntiles <= kTileSmemMax ? (size_t)kSearchWarps * P.ntiles * 4 : 0;
+    const size_t ssm = P.ntiles <= kTileSmemMax ? (size_t)P.ntiles * (sizeof(TileStat) + kSearchWarps * 4) : 0;
+    if (ssm > 48 * 1024)
+      SSDG_CUDA_TRY(cudaFuncSetAttribute(search_kernel<TG, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
     SSDG_CUDA_TRY(cudaFuncSetAttribute(search_kernel<TG, TP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     long long sgrid = (long long)sm_count() * 8;
     const long long want = ((long long)P.B * (P.max_gt > 0 ? P.max_gt : 1) + kSearchWarps - 1) / kSearchWarps;
     if (want < sgrid) sgrid = want;
+    prof_begin(SSDG_PROF_SEARCH, st);
     search_kernel<TG, TP><<<(unsigned)sgrid, kSearchThreads, ssm, st>>>(P);
+    prof_end(SSDG_PROF_SEARCH, st);
     SSDG_LAUNCH_CHECK();
   }
   match_kernel<TG, TP><<<grid, kMatchThreads, smem, st>>>(P);

@@ -14,6 +14,7 @@ ERR_TOPK_RANGE, ERR_WORKSPACE, ERR_ALIGN, ERR_LIMIT, ERR_POS_NEG_OVERLAP = -6, -
 F32, F64 = 0, 1
 LOSS_RESULT_LEN = 16
 PROF_MATCH, PROF_CE, PROF_FILTER, PROF_NMS = 0, 1, 2, 3
+PROF_BUCKET, PROF_SEARCH, PROF_LOSS_TAIL = 4, 5, 6
 
 _vp, _i32, _i64, _f32, _f64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_size_t
 _pi32, _pf64 = C.POINTER(C.c_int32), C.POINTER(C.c_double)
@@ -43,6 +44,7 @@ PROTOTYPES = {
     "ssdg_profile_enable": (C.c_int, [C.c_int]),
     "ssdg_detect_set_mid_event": (C.c_int, [_vp]),
     "ssdg_profile_last_ms": (C.c_int, [C.c_int, C.POINTER(_f32)]),
+    "ssdg_profile_span_ms": (C.c_int, [_i32, _vp, C.POINTER(_f32), C.POINTER(_f32)]),
     "ssdg_prior_count": (_i64, [_pi32, _pi32, _pi32, _i32]),
     "ssdg_prior_boxes": (C.c_int, [_pi32, _pi32, _pf64, _pi32, _pf64, _i32, _f64, _vp, _i64, _vp]),
     "ssdg_match_workspace_bytes": (_sz, [_i32, _i32, _i32]),
