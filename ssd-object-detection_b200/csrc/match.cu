@@ -276,13 +276,10 @@ __global__ void __launch_bounds__(kSearchThreads, 8) search_kernel(MatchParams P
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int A = P.A, ntiles = P.ntiles;
   const bool cached = ntiles <= kTileSmemMax;   // per-warp cache of the row's tile bounds
-  TileStat* tiles_s = reinterpret_cast<TileStat*>(smem_raw);            // staged once per (persistent) CTA
-  float* ubw = reinterpret_cast<float*>(tiles_s + (cached ? ntiles : 0)) + (size_t)warp * (cached ? ntiles : 0);
-  if (cached) {
-    for (int i = tid; i < ntiles; i += kSearchThreads) tiles_s[i] = P.tiles[i];
-    __syncthreads();
-  }
-  const TileStat* tiles = cached ? tiles_s : P.tiles;
+  // the tile statistics stay in global memory (L1/L2-resident, 14 KB for SSD300): staging them per CTA costs
+  // shared memory that decides how many of these CTAs fit beside a streaming kernel of the other branch
+  float* ubw = reinterpret_cast<float*>(smem_raw) + (size_t)warp * (cached ? ntiles : 0);
+  const TileStat* tiles = P.tiles;
   const R EPS = (R)1e-10;
   const u64 thr_key = key64((double)(R)P.thresh);
   const float thr_lo = f_down((double)(R)P.thresh);
@@ -589,7 +586,7 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
       // rounds walk the rows in descending (key, then ascending row) order -- a priority queue with lazy
       // re-evaluation: a row whose cached column has been taken in the meantime only gives an upper
       // bound, so it is re-searched (with every other stale row) and the order is rebuilt.
-      const bool fast = T <= 128 && !S.ctl[C_GENERIC];
+      const bool fast = !S.ctl[C_GENERIC];
       if (fast && S.ctl[C_NLIVE] < 0) {
         // (re)build the order of the live rows by rank counting: one warp per row, lanes split the others
         for (int t = warp; t < T; t += kMatchThreads / 32) {
@@ -646,8 +643,7 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
         if (stop && round < T) {
           // every live row whose cached column is gone is re-searched now; the order is rebuilt afterwards
           __syncwarp();
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
+          for (int r = 0; r * 32 < T; ++r) {
             const int t = lane + 32 * r;
             const bool need = t < T && !S.dead[t] && bit_test(elim, S.rowcol[t]);
             const u32 nm = __ballot_sync(SSDG_FULL, need);
@@ -824,7 +820,7 @@ static int launch_match(const MatchParams& P, int grid, size_t smem, cudaStream_
   SSDG_CUDA_TRY(cudaFuncSetAttribute(match_kernel<TG, TP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   prof_begin(SSDG_PROF_MATCH, st);
   {
-    const size_t ssm = P.ntiles <= kTileSmemMax ? (size_t)P.ntiles * (sizeof(TileStat) + kSearchWarps * 4) : 0;
+    const size_t ssm = P.ntiles <= kTileSmemMax ? (size_t)P.ntiles * kSearchWarps * 4 : 0;
     if (ssm > 48 * 1024)
       SSDG_CUDA_TRY(cudaFuncSetAttribute(search_kernel<TG, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
     SSDG_CUDA_TRY(cudaFuncSetAttribute(search_kernel<TG, TP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
