@@ -32,6 +32,7 @@
 #include <unordered_map>
 #include <utility>
 #include <vector>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace ssdg {
@@ -824,7 +825,8 @@ static int launch_match(const MatchParams& P, int grid, size_t smem, cudaStream_
     if (ssm > 48 * 1024)
       SSDG_CUDA_TRY(cudaFuncSetAttribute(search_kernel<TG, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
     SSDG_CUDA_TRY(cudaFuncSetAttribute(search_kernel<TG, TP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    long long sgrid = (long long)sm_count() * 8;
+    static const char* env = getenv("SSDG_SEARCH_CTAS_PER_SM");   // experiment knob
+    long long sgrid = (long long)sm_count() * (env ? atoi(env) : 8);
     const long long want = ((long long)P.B * (P.max_gt > 0 ? P.max_gt : 1) + kSearchWarps - 1) / kSearchWarps;
     if (want < sgrid) sgrid = want;
     prof_begin(SSDG_PROF_SEARCH, st);
