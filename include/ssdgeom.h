@@ -69,7 +69,7 @@ SSDG_API int ssdg_memcpy_h2d(void* dst, const void* src_host, size_t bytes, void
 SSDG_API int ssdg_memcpy_d2h(void* dst_host, const void* src, size_t bytes, void* stream);
 SSDG_API int ssdg_memset(void* dst, int value, size_t bytes, void* stream);
 SSDG_API int ssdg_stream_create(void** stream);
-SSDG_API int ssdg_stream_create_priority(void** stream, int high_priority); /* non-blocking; highest / lowest device priority */
+SSDG_API int ssdg_stream_create_priority(void** stream, int high_priority); /* non-blocking; 0: lowest device priority, 1: highest, k >= 2: k-1 levels below the highest */
 SSDG_API int ssdg_stream_destroy(void* stream);
 SSDG_API int ssdg_stream_sync(void* stream);
 SSDG_API int ssdg_event_create(void** event);

@@ -134,7 +134,10 @@ int ssdg_stream_create_priority(void** stream, int high_priority) {
   cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
   if (e != cudaSuccess) return (int)e;
   cudaStream_t s;
-  e = cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo);
+  // 0: lowest, 1: highest, k >= 2: k-1 levels below the highest (clamped to the lowest)
+  int pr = high_priority == 0 ? lo : hi + (high_priority - 1);
+  if (pr > lo) pr = lo;
+  e = cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, pr);
   *stream = (void*)s;
   return (int)e;
 }
