@@ -246,7 +246,7 @@ def run_ours(args):
                  global_priors=b * world * synth.num_priors(table) if args.mining == "global" else None,
                  allreduce=allreduce_on if args.mining == "global" else None)
     hp.split = args.pipeline == "split"
-    hp.fused = not args.no_fused and hp.split and args.mining == "shard"
+    hp.fused = not args.no_fused and hp.split
     a, c = hp.A, hp.classes
     # pinned host copies of one batch (also the source of the resident copy)
     h = {"gt_boxes": D.PinnedArray(boxes.shape, np.float32), "gt_cls": D.PinnedArray(cls.shape, np.float32),

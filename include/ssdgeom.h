@@ -208,10 +208,12 @@ SSDG_API int ssdg_multibox_loss(const int32_t* gt_cls, const float* gt_box, cons
  *   stage 2  radix level 2           then sum  exchange 2 (int32 x2048)
  *   stage 3  mask, sums, result      then sum  out_result[8..11] and [5]:  loss = ([8] + [10]) / sum[11] + [9] / sum[5]
  * Every stage takes the arguments of ssdg_multibox_loss (same buffers each time) plus global_priors =
- * sum over shards of batch * n_priors.  After stage 3 out_result[4] is the global positive count, [11] the
+ * sum over shards of batch * n_priors, and optionally (both or neither, else NULL) the per-prior softmax statistics
+ * of ssdg_detect_stage so that stage 0 skips its own pass over the logits (see ssdg_multibox_loss_fused).  After stage 3 out_result[4] is the global positive count, [11] the
  * shard's own, [6] the global threshold, and out_neg_mask equals the single-device mask of the whole batch.
  */
-SSDG_API int ssdg_multibox_loss_stage(int32_t stage, int64_t global_priors, const int32_t* gt_cls,
+SSDG_API int ssdg_multibox_loss_stage(int32_t stage, int64_t global_priors, const float* row_ml,
+                       const float* row_negbg, const int32_t* gt_cls,
                        const float* gt_box, const uint8_t* gt_mask, const float* pred_box,
                        const float* pred_cls, int64_t batch, int32_t n_priors, int32_t n_classes,
                        int32_t neg_ratio, double* out_result, uint8_t* out_neg_mask, float* out_neg_ce,

@@ -631,14 +631,15 @@ extern "C" int ssdg_multibox_loss(const int32_t* gt_cls, const float* gt_box, co
                   out_result, out_neg_mask, out_neg_ce, grad_box, grad_cls, workspace, workspace_bytes, stream);
 }
 
-extern "C" int ssdg_multibox_loss_stage(int32_t stage, int64_t global_priors, const int32_t* gt_cls,
+extern "C" int ssdg_multibox_loss_stage(int32_t stage, int64_t global_priors, const float* row_ml,
+                                        const float* row_negbg, const int32_t* gt_cls,
                                         const float* gt_box, const uint8_t* gt_mask, const float* pred_box,
                                         const float* pred_cls, int64_t batch, int32_t n_priors, int32_t n_classes,
                                         int32_t neg_ratio, double* out_result, uint8_t* out_neg_mask,
                                         float* out_neg_ce, float* grad_box, float* grad_cls, void* workspace,
                                         size_t workspace_bytes, void* stream) {
   if (stage < 0 || stage > 3 || global_priors <= 0) return SSDG_ERR_ARG;
-  return loss_run(1 << stage, 1, global_priors, nullptr, nullptr, gt_cls, gt_box, gt_mask, pred_box, pred_cls, batch, n_priors,
+  return loss_run(1 << stage, 1, global_priors, row_ml, row_negbg, gt_cls, gt_box, gt_mask, pred_box, pred_cls, batch, n_priors,
                   n_classes, neg_ratio, out_result, out_neg_mask, out_neg_ce, grad_box, grad_cls, workspace,
                   workspace_bytes, stream);
 }

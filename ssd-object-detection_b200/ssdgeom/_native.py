@@ -59,7 +59,7 @@ PROTOTYPES = {
     "ssdg_loss_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "ssdg_multibox_loss": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
                                      _vp, _sz, _vp]),
-    "ssdg_multibox_loss_stage": (C.c_int, [_i32, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp,
+    "ssdg_multibox_loss_stage": (C.c_int, [_i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp,
                                            _vp, _vp, _vp, _sz, _vp]),
     "ssdg_loss_exchange": (C.c_int, [_vp, _i32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "ssdg_gt_prepare": (C.c_int, [_vp, _i32, _vp, _vp, _i64, _i64, _vp, _vp]),

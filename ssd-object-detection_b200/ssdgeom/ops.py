@@ -247,7 +247,8 @@ class StagedLoss:
     torch.as_tensor(buf) works in place without a copy."""
 
     def __init__(self, gt_cls, gt_box, gt_mask, pred_box, pred_cls, global_priors: int, neg_ratio: int = 3,
-                 want_neg_mask=False, want_neg_ce=False, want_grad=False, stream=None, ws_kind="loss_staged", out=None):
+                 want_neg_mask=False, want_neg_ce=False, want_grad=False, stream=None, ws_kind="loss_staged", out=None,
+                 row_stats=None):
         self.gt_cls = D.as_device(gt_cls, np.int32)
         self.gt_box = D.as_device(gt_box, np.float32)
         self.gt_mask = D.as_device(gt_mask, np.uint8)
@@ -261,6 +262,7 @@ class StagedLoss:
             raise AssertionError("y_true / y_pred disagree in shape")
         self.shape = (b, a, c)
         self.global_priors = int(global_priors)
+        self.row_stats = row_stats          # (row_ml, row_negbg) of detect(..., want_row_stats=True), or None
         self.neg_ratio = int(neg_ratio)
         self.stream = stream
         self.out = dict(out or {})
@@ -281,7 +283,8 @@ class StagedLoss:
         b, a, c = self.shape
         o = self.out
         N.check(N.lib().ssdg_multibox_loss_stage(
-            int(stage), self.global_priors, self.gt_cls.ptr, self.gt_box.ptr, self.gt_mask.ptr, self.pred_box.ptr,
+            int(stage), self.global_priors, _p(self.row_stats[0] if self.row_stats else None),
+            _p(self.row_stats[1] if self.row_stats else None), self.gt_cls.ptr, self.gt_box.ptr, self.gt_mask.ptr, self.pred_box.ptr,
             self.pred_cls.ptr, b, a, c, self.neg_ratio, o["result"].ptr, _p(o.get("neg_mask")), _p(o.get("neg_ce")),
             _p(o.get("grad_box")), _p(o.get("grad_cls")), self.ws.ptr, self.ws.nbytes,
             D.stream_handle(self.stream)), "multibox_loss_stage")

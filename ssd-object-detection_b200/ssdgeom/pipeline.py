@@ -57,7 +57,7 @@ class HotPath:
                 raise ValueError("global mining needs allreduce and global_priors")
             self.staged = ops.StagedLoss(self.tgt["cls"], self.tgt["loc"], self.tgt["mask"], self.pred_box, self.pred_cls,
                                          int(global_priors), self.neg_ratio, out=self.loss)
-        self.kernel_launches_per_step = 8   # match | ce, select x2, final | filter, bucket, nms
+        self.kernel_launches_per_step = 9   # search, match | lossprep (or ce), select x2, final | filter, bucket, nms
         self.h2d_bytes = (self.gt_boxes.nbytes + self.gt_cls.nbytes + self.gt_off.nbytes + self.pred_cls.nbytes +
                           self.pred_box.nbytes)
         self.d2h_bytes = self.loss["result"].nbytes + self.det["kept"].nbytes + self.det["count"].nbytes
@@ -75,6 +75,7 @@ class HotPath:
             return
         if self.staged is not None:
             self.staged.stream = stream
+            self.staged.row_stats = (self.det_stats["row_ml"], self.det_stats["row_negbg"]) if stats else None
             for stage in range(4):
                 self.staged.run(stage)
                 for buf in self.staged.exchange(stage):
@@ -98,7 +99,7 @@ class HotPath:
         self.ev_begin.record(self.s_main)
         D.stream_wait_event(self.s_a, self.ev_begin)
         D.stream_wait_event(self.s_d, self.ev_begin)
-        fused = self.fused and self.staged is None
+        fused = self.fused
         if self.split:
             self.detect_stage(self.s_d, stage=0, stats=fused)
             self.ev_mid.record(self.s_d)
