@@ -138,6 +138,42 @@ class HotPath:
         for src, dst in ((self.loss["result"], out_result), (self.det["kept"], out_kept), (self.det["count"], out_count)):
             N.check(lib.ssdg_memcpy_d2h(dst.ctypes.data, src.ptr, src.nbytes, D.stream_handle(st)), "d2h")
 
+    # Pipelined end to end: two device copies of the inputs, the H2D copy of batch k+1 (PCIe-bound, ~14 ms) runs on
+    # its own stream under the compute and D2H of batch k.
+    def _input_sets(self):
+        if getattr(self, "_sets", None) is None:
+            names = ("gt_boxes", "gt_cls", "gt_off", "pred_cls", "pred_box")
+            first = {k: getattr(self, k) for k in names}
+            second = {k: D.empty(v.shape, v.dtype) for k, v in first.items()}
+            self._sets, self._n_sub = [first, second], 0
+            self.s_copy = D.Stream()
+            self.ev_up, self.ev_done, self._done_valid = [D.Event(), D.Event()], [D.Event(), D.Event()], [False, False]
+        return self._sets
+
+    def submit(self, host_in, host_out):
+        """Enqueue one end-to-end step (host inputs -> host results) and return without waiting; call ``drain()``
+        before reading ``host_out``.  Results of consecutive submits must go to different host buffers if they are
+        to be kept.  Not available with cross-process mining (the staged loss holds its input buffers)."""
+        if self.staged is not None:
+            raise RuntimeError("submit() is not available with mining='global'; use step_host()")
+        sets = self._input_sets()
+        slot = self._n_sub % 2
+        if self._done_valid[slot]:      # the slot's inputs were read by the step two submits ago
+            D.stream_wait_event(self.s_copy, self.ev_done[slot])
+        for k, v in sets[slot].items():
+            setattr(self, k, v)
+        self.upload(*host_in, stream=self.s_copy)
+        self.ev_up[slot].record(self.s_copy)
+        D.stream_wait_event(self.s_main, self.ev_up[slot])
+        self.step()
+        self.download(*host_out)
+        self.ev_done[slot].record(self.s_main)
+        self._done_valid[slot] = True
+        self._n_sub += 1
+
+    def drain(self):
+        self.s_main.sync()
+
     def step_host(self, gt_boxes, gt_cls, gt_off, pred_cls, pred_box, out_result, out_kept, out_count):
         """End to end: host inputs in, host results out (synchronises)."""
         self.upload(gt_boxes, gt_cls, gt_off, pred_cls, pred_box)

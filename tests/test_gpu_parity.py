@@ -647,3 +647,31 @@ def test_loss_from_filter_row_statistics(priors300):
         assert np.array_equal(neg_mask, want_mask) and np.float32(r["kth"]) == kth
         assert r["num_pos"] == w_aux["num_pos"] and r["num_neg"] == int(want_mask.sum())
         assert int(np.sum(neg_mask != w_aux["neg_mask"])) <= 2      # end to end vs the float64 oracle (reported)
+
+
+def test_pipelined_host_steps_match_serial(priors300):
+    """HotPath.submit (double-buffered inputs, copies overlapped with compute) returns exactly what step_host returns,
+    batch after batch, including when consecutive batches differ."""
+    from ssdgeom.pipeline import HotPath
+    b = 4
+    hp = HotPath(synth.TABLES["ssd300"], batch=b, max_gt=100, total_gt=b * 100)
+    batches = []
+    for seed in (51, 52, 53):
+        boxes, cls, off = synth.make_gt(seed, b, 100, "max")
+        pc, pb = synth.make_predictions(seed, b, 8732)
+        batches.append((boxes, cls, off, pc, pb))
+    def outs():
+        return (np.zeros(16), np.zeros((b, 80, 200), np.int32), np.zeros((b, 80), np.int32))
+    serial = []
+    for inp in batches:
+        o = outs()
+        hp.step_host(*inp, *o)
+        serial.append(o)
+    piped = [outs() for _ in batches]
+    for inp, o in zip(batches, piped):
+        hp.submit(inp, o)
+    hp.drain()
+    for s, p in zip(serial, piped):
+        assert np.array_equal(s[1], p[1]) and np.array_equal(s[2], p[2])
+        close(p[0][:11], s[0][:11], rtol=1e-12)
+    assert not np.array_equal(serial[0][1], serial[1][1])
