@@ -246,6 +246,14 @@ SSDG_API int ssdg_gt_prepare(const void* xywh, int32_t dtype, const int32_t* img
                     int64_t batch, int64_t rows, float* out_boxes, void* stream);
 SSDG_API int ssdg_image_normalize(const float* in, float* out, int64_t n, void* stream);
 
+/* ---- generalised anchor tables --------------------------------------------
+ * The reference's rule (models/ssd_model.py:173-194) neither clips priors nor uses variances; SSD variants do.
+ * ssdg_priors_clip clamps every component of [A,4] cxcywh priors to [0,1] in place.  ssdg_loc_scale multiplies
+ * encoded offsets [rows,4] by (sxy, sxy, swh, swh): 1/variance after ssdg_encode / ssdg_match_encode, variance
+ * before ssdg_decode / ssdg_detect (in and out may alias).  Variance 1 and no clipping reproduce the reference. */
+SSDG_API int ssdg_priors_clip(void* priors, int32_t dtype, int64_t n_priors, void* stream);
+SSDG_API int ssdg_loc_scale(const float* in, float* out, int64_t rows, float scale_xy, float scale_wh, void* stream);
+
 /* ---- A7+A8+A9: post-processing ------------------------------------------------------------------------
  * Replaces the head of SSDObjectDetectionModel.visualize            models/ssd_model.py:477-490
  *   (softmax, max foreground score, arg-max class, threshold mask) and the decode of

@@ -400,3 +400,21 @@ def coco_to_ssd_boxes(xywh, img_w, img_h):
 def normalize_image(image):
     """models/ssd_model.py:214 on the float32 image the loaders yield."""
     return (np.asarray(image, dtype=np.float32) - 0.5) * 2
+
+
+# ---- generalised anchor tables (SURVEY.md section 8f row 4): options the reference's rule does not have -------
+def clip_priors(priors):
+    """Component-wise clamp of cxcywh priors to [0,1] (the `clip` option of SSD variants)."""
+    return np.clip(np.asarray(priors), 0.0, 1.0)
+
+
+def apply_anchor_box_var(origin_bbox, default_box, variances):
+    """utils/bbox.py:94-101 followed by the division by (v_xy, v_xy, v_wh, v_wh) of SSD variants; float64."""
+    enc = apply_anchor_box(origin_bbox, default_box).astype(np.float64)
+    return enc / np.array([variances[0], variances[0], variances[1], variances[1]], dtype=np.float64)
+
+
+def decode_bbox_var(loc, default_box, scale, variances):
+    """models/ssd_model.py:466-467 on offsets multiplied by the variances first (float32 product, like the kernel)."""
+    v = np.array([variances[0], variances[0], variances[1], variances[1]], dtype=np.float32)
+    return decode_bbox(np.asarray(loc, dtype=np.float32) * v, default_box, scale)

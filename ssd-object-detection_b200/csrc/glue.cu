@@ -62,9 +62,49 @@ __global__ void __launch_bounds__(256) image_norm_kernel(const float* __restrict
   for (long long i = done + gtid; i < n; i += gstride) out[i] = __fmul_rn(__fsub_rn(in[i], 0.5f), 2.f);
 }
 
+// Generalised anchor tables: the two options SSD variants add to the reference's rule.
+//   clip_kernel        priors clamped to [0, 1] component-wise (cx, cy, w, h), in place
+//   loc_scale_kernel   encoded offsets times (sxy, sxy, swh, swh): 1/variance after encoding, variance before decoding
+template <typename T>
+__global__ void __launch_bounds__(256) clip_kernel(T* __restrict__ v, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = v[i] < (T)0 ? (T)0 : (v[i] > (T)1 ? (T)1 : v[i]);
+}
+
+__global__ void __launch_bounds__(256) loc_scale_kernel(const float4* __restrict__ in, float4* __restrict__ out, long long rows,
+                                                        float sxy, float swh) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const float4 v = in[i];
+  out[i] = make_float4(__fmul_rn(v.x, sxy), __fmul_rn(v.y, sxy), __fmul_rn(v.z, swh), __fmul_rn(v.w, swh));
+}
+
 }  // namespace ssdg
 
 using namespace ssdg;
+
+extern "C" int ssdg_priors_clip(void* priors, int32_t dtype, int64_t n_priors, void* stream) {
+  if (n_priors < 0 || (dtype != SSDG_F32 && dtype != SSDG_F64)) return SSDG_ERR_ARG;
+  if (n_priors == 0) return SSDG_OK;
+  if (!priors) return SSDG_ERR_ARG;
+  const long long n = n_priors * 4;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (dtype == SSDG_F64) clip_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)priors, n);
+  else clip_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)priors, n);
+  SSDG_LAUNCH_CHECK();
+  return SSDG_OK;
+}
+
+extern "C" int ssdg_loc_scale(const float* in, float* out, int64_t rows, float scale_xy, float scale_wh, void* stream) {
+  if (rows < 0) return SSDG_ERR_ARG;
+  if (rows == 0) return SSDG_OK;
+  if (!in || !out) return SSDG_ERR_ARG;
+  if (((uintptr_t)in | (uintptr_t)out) & 15) return SSDG_ERR_ALIGN;
+  loc_scale_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)in, (float4*)out, rows,
+                                                                                     scale_xy, scale_wh);
+  SSDG_LAUNCH_CHECK();
+  return SSDG_OK;
+}
 
 extern "C" int ssdg_gt_prepare(const void* xywh, int32_t dtype, const int32_t* img_wh, const int32_t* gt_offsets,
                                int64_t batch, int64_t rows, float* out_boxes, void* stream) {

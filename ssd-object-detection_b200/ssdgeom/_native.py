@@ -64,6 +64,8 @@ PROTOTYPES = {
     "ssdg_loss_exchange": (C.c_int, [_vp, _i32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "ssdg_gt_prepare": (C.c_int, [_vp, _i32, _vp, _vp, _i64, _i64, _vp, _vp]),
     "ssdg_image_normalize": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "ssdg_priors_clip": (C.c_int, [_vp, _i32, _i64, _vp]),
+    "ssdg_loc_scale": (C.c_int, [_vp, _vp, _i64, _f32, _f32, _vp]),
     "ssdg_detect_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "ssdg_detect": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp, _vp,
                               _f32, _vp, _vp, _vp, _vp, _sz, _vp]),

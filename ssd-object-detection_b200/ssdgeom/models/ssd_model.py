@@ -19,12 +19,13 @@ SSD512 = dict(input_size=512, sizes=[(64, 64), (32, 32), (16, 16), (8, 8), (4, 4
               aspect_ratio=[[2], [2, 3], [2, 3], [2, 3], [2, 3], [2], [2]])
 
 
-def build_prior_box(size_list, s_k_refer=None, aspect_ratio=None, input_size=300, device_out=False):
-    """``_build_prior_box(size_list)`` (models/ssd_model.py:173-194): float64 [A,4] cxcywh."""
+def build_prior_box(size_list, s_k_refer=None, aspect_ratio=None, input_size=300, device_out=False, clip=False):
+    """``_build_prior_box(size_list)`` (models/ssd_model.py:173-194): float64 [A,4] cxcywh.  ``clip`` (an option
+    the reference does not have) clamps every component to [0,1]."""
     size_list = [tuple(int(v) for v in s) for s in size_list]
     s_k_refer = SSD300["s_k_refer"] if s_k_refer is None else s_k_refer
     aspect_ratio = SSD300["aspect_ratio"] if aspect_ratio is None else aspect_ratio
-    out = ops.prior_boxes(size_list, s_k_refer[:len(size_list) + 1], aspect_ratio[:len(size_list)], input_size)
+    out = ops.prior_boxes(size_list, s_k_refer[:len(size_list) + 1], aspect_ratio[:len(size_list)], input_size, clip=clip)
     return out if device_out else out.to_host()
 
 

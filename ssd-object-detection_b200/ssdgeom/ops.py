@@ -44,8 +44,9 @@ def _p(x):
 
 
 # ---- A1 ------------------------------------------------------------------------------------------
-def prior_boxes(size_list, s_k_refer, aspect_ratio, input_size=300, stream=None) -> D.DeviceArray:
-    """models/ssd_model.py:173-194 with the tables lifted to arguments; float64 [A,4] on the device."""
+def prior_boxes(size_list, s_k_refer, aspect_ratio, input_size=300, stream=None, clip=False) -> D.DeviceArray:
+    """models/ssd_model.py:173-194 with the tables lifted to arguments; float64 [A,4] on the device.
+    clip=True clamps every component to [0,1] (not in the reference)."""
     n = len(size_list)
     if len(s_k_refer) != n + 1 or len(aspect_ratio) != n:
         raise ValueError("need len(s_k_refer) == len(size_list)+1 and one ratio list per level")
@@ -66,6 +67,18 @@ def prior_boxes(size_list, s_k_refer, aspect_ratio, input_size=300, stream=None)
     out = D.empty((count, 4), np.float64)
     N.check(lib.ssdg_prior_boxes(fh, fw, sk, ro, rr, n, float(input_size), out.ptr, count, D.stream_handle(stream)),
             "prior_boxes")
+    if clip:
+        N.check(lib.ssdg_priors_clip(out.ptr, _code(out.dtype), count, D.stream_handle(stream)), "priors_clip")
+    return out
+
+
+def loc_scale(loc, scale_xy, scale_wh, out=None, stream=None) -> D.DeviceArray:
+    """Encoded offsets times (sxy, sxy, swh, swh): 1/variance after encoding, variance before decoding."""
+    loc = D.as_device(loc, np.float32)
+    out = D.empty(loc.shape, np.float32) if out is None else out
+    N.check(N.lib().ssdg_loc_scale(loc.ptr, out.ptr, loc.size // 4, float(scale_xy), float(scale_wh),
+                                   D.stream_handle(stream)), "loc_scale")
+    out._keep = (loc,)
     return out
 
 

@@ -63,15 +63,20 @@ def apply_anchor_box(origin_bbox, default_box):
     return ops.encode(g, d, out_dtype=odt).to_host()
 
 
-def decode_bbox(loc, default_box, scale=300.0):
-    """The inverse the reference applies inline at models/ssd_model.py:466-467 (pixels for scale=300)."""
+def decode_bbox(loc, default_box, scale=300.0, variances=None):
+    """The inverse the reference applies inline at models/ssd_model.py:466-467 (pixels for scale=300).
+    ``variances=(v_xy, v_wh)`` (not in the reference): the offsets are multiplied by them first."""
     t = np.ascontiguousarray(np.asarray(loc, dtype=np.float32))
+    if variances is not None:
+        t = ops.loc_scale(t, variances[0], variances[1])
     return ops.decode(t, _boxes(default_box), scale=scale).to_host()
 
 
-def match_encode_batch(gt_boxes, gt_cls, gt_offsets, default_box, thresh=0.5, device_out=False, stream=None):
+def match_encode_batch(gt_boxes, gt_cls, gt_offsets, default_box, thresh=0.5, device_out=False, stream=None,
+                       variances=None):
     """The reference's per-image generator body (models/ssd_model.py:211-215) for a whole batch:
-    CSR ground truth -> (cls int32[B,A], loc float32[B,A,4], mask bool[B,A])."""
+    CSR ground truth -> (cls int32[B,A], loc float32[B,A,4], mask bool[B,A]).  ``variances=(v_xy, v_wh)`` (not in
+    the reference) divides the encoded offsets."""
     off = np.asarray(gt_offsets, dtype=np.int32)
     counts = np.diff(off)
     priors = default_box if D.is_device(default_box) else _boxes(default_box)
@@ -81,6 +86,8 @@ def match_encode_batch(gt_boxes, gt_cls, gt_offsets, default_box, thresh=0.5, de
     gb = gt_boxes if D.is_device(gt_boxes) else _boxes(gt_boxes)
     gc = gt_cls if D.is_device(gt_cls) else np.trunc(np.asarray(gt_cls, dtype=np.float64)).astype(np.float32)
     out = ops.match_encode(gb, gc, off, priors, int(counts.size), int(counts.max()), float(thresh), stream=stream)
+    if variances is not None:
+        ops.loc_scale(out["loc"], 1.0 / variances[0], 1.0 / variances[1], out=out["loc"], stream=stream)
     if device_out:
         return out["cls"], out["loc"], out["mask"]
     return out["cls"].to_host(stream), out["loc"].to_host(stream), out["mask"].to_host(stream).astype(bool)

@@ -675,3 +675,22 @@ def test_pipelined_host_steps_match_serial(priors300):
         assert np.array_equal(s[1], p[1]) and np.array_equal(s[2], p[2])
         close(p[0][:11], s[0][:11], rtol=1e-12)
     assert not np.array_equal(serial[0][1], serial[1][1])
+
+
+def test_generalised_anchor_options(priors300):
+    """Section 8f row 4: clipping and variances (options the reference lacks) against the oracle's restatement;
+    clip=False / variances=None are the reference's behaviour (covered by every other test)."""
+    t = synth.SSD300
+    got = M.build_prior_box(t["sizes"], clip=True)
+    assert np.array_equal(got, O.clip_priors(priors300)) and got.max() <= 1.0 and (priors300.max() > 1.0)
+    boxes, cls, off = synth.make_gt(61, 3, 20, "max")
+    var = (0.1, 0.2)
+    c0, l0, m0 = bbox.match_encode_batch(boxes, cls, off, priors300, 0.5)
+    c1, l1, m1 = bbox.match_encode_batch(boxes, cls, off, priors300, 0.5, variances=var)
+    assert np.array_equal(c0, c1) and np.array_equal(m0, m1)
+    for i in range(3):
+        w_cls, w_box, w_mask = O.match_bbox(cls[off[i]:off[i + 1]], boxes[off[i]:off[i + 1]], priors300)
+        close(l1[i], O.apply_anchor_box_var(w_box, priors300, var), rtol=RTOL)      # float32 product vs float64 division
+    dec = bbox.decode_bbox(l1[0], priors300, scale=300.0, variances=var)
+    close(dec, O.decode_bbox_var(l1[0], priors300, 300.0, var), rtol=RTOL, atol=1e-6)
+    close(dec[m1[0]], bbox.decode_bbox(l0[0], priors300, scale=300.0)[m0[0]], rtol=1e-4, atol=1e-4)   # round trip
