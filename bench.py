@@ -269,14 +269,22 @@ def run_ours(args):
     s_main_t = torch.cuda.ExternalStream(hp.s_main.handle)
     res_t = torch.as_tensor(hp.loss["result"], device="cuda")
 
+    t_streams = {}
+
+    def exchange_on(stream):     # enqueued by HotPath on its loss stream: hidden under the NMS of the other branch
+        if stream.handle not in t_streams:
+            t_streams[stream.handle] = torch.cuda.ExternalStream(stream.handle)
+        with torch.cuda.stream(t_streams[stream.handle]):
+            dist.all_reduce(res_t[4:11])
+
+    if world > 1 and args.mining == "shard":
+        hp.loss_exchange = exchange_on
+
     def exchange():
-        if world > 1 and args.mining == "shard":
-            with torch.cuda.stream(s_main_t):
-                dist.all_reduce(res_t[4:11])
+        pass
 
     def full_step():
         hp.step()
-        exchange()
 
     sampler = ClockSampler(local_rank)
     sampler.start()

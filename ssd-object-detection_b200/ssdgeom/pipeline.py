@@ -51,6 +51,9 @@ class HotPath:
         if mining not in ("shard", "global"):
             raise ValueError("mining must be 'shard' or 'global'")
         self.mining, self.allreduce = mining, allreduce
+        # optional callable(stream): the data-parallel exchange of the additive loss sums (per-shard mining),
+        # enqueued on the loss stream right behind the loss so that it hides under the NMS of the other branch
+        self.loss_exchange = None
         self.staged = None
         if mining == "global":
             if allreduce is None or not global_priors:
@@ -111,12 +114,16 @@ class HotPath:
             if fused:
                 D.stream_wait_event(self.s_l, self.ev_mid)
             self.loss_stage(self.s_l, stats=fused)
+            if self.loss_exchange is not None:
+                self.loss_exchange(self.s_l)
             self.ev_a.record(self.s_l)
             self.ev_d.record(self.s_n)
         else:
             self.detect_stage(self.s_d)
             self.assign(self.s_a)
             self.loss_stage(self.s_a)
+            if self.loss_exchange is not None:
+                self.loss_exchange(self.s_a)
             self.ev_a.record(self.s_a)
             self.ev_d.record(self.s_d)
         D.stream_wait_event(self.s_main, self.ev_a)
