@@ -694,3 +694,41 @@ def test_generalised_anchor_options(priors300):
     dec = bbox.decode_bbox(l1[0], priors300, scale=300.0, variances=var)
     close(dec, O.decode_bbox_var(l1[0], priors300, 300.0, var), rtol=RTOL, atol=1e-6)
     close(dec[m1[0]], bbox.decode_bbox(l0[0], priors300, scale=300.0)[m0[0]], rtol=1e-4, atol=1e-4)   # round trip
+
+
+def test_chained_step_full_batch_equals_standalone_calls(priors300):
+    """BASELINE size (SSD300, B=256): the chained HotPath.step -- four streams, one pass over the logits shared by
+    the loss and the post-processing -- against the three standalone entry points on the same device buffers:
+    targets and detections identical, loss within tolerance (the two CE passes round differently), and the result
+    is reproducible run to run (no race between the streams)."""
+    from ssdgeom.pipeline import HotPath
+    b = 256
+    boxes, cls, off = synth.make_gt(71, b, 100, "coco")
+    hp = HotPath(synth.TABLES["ssd300"], batch=b, max_gt=int(np.diff(off).max()), total_gt=boxes.shape[0])
+    pc = np.empty((b, hp.A, hp.classes), np.float32)
+    pb = np.empty((b, hp.A, 4), np.float32)
+    for i in range(0, b, 32):
+        pc[i:i + 32], pb[i:i + 32] = synth.make_predictions(700 + i, 32, hp.A, hp.classes)
+    hp.upload(boxes, cls, off, pc, pb)
+    runs = []
+    for _ in range(3):
+        hp.step()
+        hp.s_main.sync()
+        runs.append((hp.loss["result"].to_host(), hp.det["kept"].to_host(), hp.det["count"].to_host(),
+                     hp.tgt["cls"].to_host(), hp.tgt["mask"].to_host(), hp.tgt["loc"].to_host()))
+    for r in runs[1:]:
+        assert all(np.array_equal(x, y) for x, y in zip(r[1:], runs[0][1:]))
+        close(r[0][:11], runs[0][0][:11], rtol=1e-12)
+    tgt = ops.match_encode(hp.gt_boxes, hp.gt_cls, hp.gt_off, hp.priors, b, hp.max_gt, 0.5)
+    assert np.array_equal(tgt["cls"].to_host(), runs[0][3]) and np.array_equal(tgt["mask"].to_host(), runs[0][4])
+    assert np.array_equal(tgt["loc"].to_host(), runs[0][5])
+    det = ops.detect(hp.pred_cls, hp.pred_box, hp.priors)
+    assert np.array_equal(det["kept"].to_host(), runs[0][1]) and np.array_equal(det["count"].to_host(), runs[0][2])
+    alone = ops.loss_result_to_host(ops.multibox_loss(tgt["cls"], tgt["loc"], tgt["mask"], hp.pred_box, hp.pred_cls)["result"])
+    r = runs[0][0]
+    assert int(r[4]) == alone["num_pos"] and abs(int(r[5]) - alone["num_neg"]) <= 2
+    close(r[0], alone["total"], rtol=1e-6)
+    # sampled oracle check of the chained outputs: first 4 images
+    for i in range(4):
+        w_cls, w_loc, w_mask = O.assign_encode(cls[off[i]:off[i + 1]], boxes[off[i]:off[i + 1]], priors300, sweeps=False)
+        assert np.array_equal(runs[0][3][i], w_cls) and np.array_equal(runs[0][4][i].astype(bool), w_mask)
