@@ -636,18 +636,19 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
       const float sy = tq * (bi.w - bi.y) - 1e-6f * (fabsf(bi.y) + fabsf(bi.w));
       const int ax = slab(bi.x + sx, dx0, dsx), bx = max(slab(bi.z - sx, dx0, dsx), ax);
       const int ay = slab(bi.y + sy, dy0, dsy), by = max(slab(bi.w - sy, dy0, dsy), ay);
-      // shrunk extents mostly touch one to three slabs: three fixed loads per axis, a loop for the rest
+      // shrunk extents mostly touch one to four slabs: four fixed loads per axis, a loop for the rest
       const int ax1 = min(ax + 1, bx), ax2 = min(ax + 2, bx), ay1 = min(ay + 1, by), ay2 = min(ay + 2, by);
-      const bool wide = bx - ax > 2 || by - ay > 2;
+      const int ax3 = min(ax + 3, bx), ay3 = min(ay + 3, by);
+      const bool wide = bx - ax > 3 || by - ay > 3;
       for (int w = 0; w <= gi; ++w) {
         const u32* px = slabx + w * kSlabs;
         const u32* py = slaby + w * kSlabs;
-        u32 mx = px[ax] | px[ax1] | px[ax2], my = py[ay] | py[ay1] | py[ay2];
+        u32 mx = px[ax] | px[ax1] | px[ax2] | px[ax3], my = py[ay] | py[ay1] | py[ay2] | py[ay3];
         if (wide) {
 #pragma unroll 1
-          for (int sl = ax + 3; sl <= bx; ++sl) mx |= px[sl];
+          for (int sl = ax + 4; sl <= bx; ++sl) mx |= px[sl];
 #pragma unroll 1
-          for (int sl = ay + 3; sl <= by; ++sl) my |= py[sl];
+          for (int sl = ay + 4; sl <= by; ++sl) my |= py[sl];
         }
         u32 cand = sane ? (mx & my) : 0u;
         if (w == gi) cand &= (1u << (i & 31)) - 1u;
