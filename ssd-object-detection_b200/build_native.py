@@ -46,10 +46,16 @@ def _stamp() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
+    """variant: a named side build (libssdgeom_<variant>.so, own object directory) for A/B measurements,
+    selected at run time with SSDGEOM_LIB; flags come from SSDG_EXTRA_NVCC_FLAGS as usual."""
+    global LIB, OBJ_DIR
+    if variant:
+        LIB = os.path.join(OUT_DIR, "libssdgeom_%s.so" % variant)
+        OBJ_DIR = os.path.join(HERE, "build", variant)
     os.makedirs(OUT_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)
-    stamp_file = os.path.join(OUT_DIR, "libssdgeom.stamp")
+    stamp_file = LIB[:-3] + ".stamp"
     stamp = _stamp()
     if not force and os.path.isfile(LIB) and os.path.isfile(stamp_file) and open(stamp_file).read() == stamp:
         return LIB
@@ -74,4 +80,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=_variant))

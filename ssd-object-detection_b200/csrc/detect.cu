@@ -17,6 +17,7 @@
 //                  registers (cheap float test with a margin, the exact IEEE formula for the survivors),
 //                  and a parallel fixed-point resolution of "kept(i) <=> no kept j < i suppresses i".
 #include <math_constants.h>
+#include <type_traits>
 #include "common.cuh"
 
 namespace ssdg {
@@ -122,51 +123,70 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
   u32 bits0 = 0u, bits1 = 0u, bits2 = 0u;
   if (valid) {
     if (!kProbs) {
-      float m0 = -CUDART_INF_F, m1 = m0, m2 = m0, m3 = m0;
-      int c = 0;
-      for (; c + 4 <= C; c += 4) {
-        m0 = fmaxf(m0, row[c]); m1 = fmaxf(m1, row[c + 1]); m2 = fmaxf(m2, row[c + 2]); m3 = fmaxf(m3, row[c + 3]);
-      }
-      for (; c < C; ++c) m0 = fmaxf(m0, row[c]);
-      const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      // The exponent reference of the row: the true maximum (two passes over the row), or -- when the rows
+      // are not overwritten -- first the background logit, which IS the maximum of nearly every trained row:
+      // e_c = 2^((x_c - ref) log2e), the common factor cancels in e/sum and in  log sum - (x - ref).  A row
+      // whose sum leaves [~1, 2^16] that way (a foreground logit > 11 above the background, NaN, inf) is
+      // redone with its maximum, so no input can overflow or lose precision.
+      auto row_max = [&]() {
+        float m0 = -CUDART_INF_F, m1 = m0, m2 = m0, m3 = m0;
+        int c = 0;
+        for (; c + 4 <= C; c += 4) {
+          m0 = fmaxf(m0, row[c]); m1 = fmaxf(m1, row[c + 1]); m2 = fmaxf(m2, row[c + 2]); m3 = fmaxf(m3, row[c + 3]);
+        }
+        for (; c < C; ++c) m0 = fmaxf(m0, row[c]);
+        return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      };
       const float xbg = row[C - 1];
-      kexp = -mx * SSDG_LOG2E;
-      float s0 = 0.f, s1 = 0.f;
-      auto chunk32 = [&](int c0) {   // a full word of 32 classes, fully unrolled: the bit positions are immediates
-        u32 bits = 0u;
-        float* r = row + c0;
+      const bool two_pass = kWrite || nfg > 96;   // rows (or the classes beyond the bit words) are overwritten
+      float ref = two_pass ? row_max() : xbg;
+      float s0, s1;
+      for (int attempt = two_pass ? 1 : 0;; ++attempt) {
+        kexp = -ref * SSDG_LOG2E;
+        s0 = 0.f; s1 = 0.f;
+        auto chunkN = [&](int c0, auto width) {   // `width` classes, fully unrolled: the bit positions are immediates
+          constexpr int kW = decltype(width)::value;
+          u32 bits = 0u;
+          float* r = row + c0;
 #pragma unroll
-        for (int cc = 0; cc < 32; cc += 2) {
-          const float e0 = exp2_ftz(fmaf(r[cc], SSDG_LOG2E, kexp)), e1 = exp2_ftz(fmaf(r[cc + 1], SSDG_LOG2E, kexp));
-          if (kWrite) { r[cc] = e0; r[cc + 1] = e1; }
-          s0 += e0; s1 += e1;
-          if (e0 > pre) bits |= 1u << cc;
-          if (e1 > pre) bits |= 2u << cc;
-        }
-        return bits;
-      };
-      auto chunk = [&](int c0, int cn) {
-        u32 bits = 0u;
-        for (int cc = 0; cc < cn; ++cc) {
-          const float e0 = exp2_ftz(fmaf(row[c0 + cc], SSDG_LOG2E, kexp));
-          if (kWrite) row[c0 + cc] = e0;
+          for (int cc = 0; cc < kW; cc += 2) {
+            const float e0 = exp2_ftz(fmaf(r[cc], SSDG_LOG2E, kexp)), e1 = exp2_ftz(fmaf(r[cc + 1], SSDG_LOG2E, kexp));
+            if (kWrite) { r[cc] = e0; r[cc + 1] = e1; }
+            s0 += e0; s1 += e1;
+            if (e0 > pre) bits |= 1u << cc;
+            if (e1 > pre) bits |= 2u << cc;
+          }
+          return bits;
+        };
+        auto chunk = [&](int c0, int cn) {
+          u32 bits = 0u;
+          int cc = 0;
+          if (cn >= 16) { bits = chunkN(c0, std::integral_constant<int, 16>()); cc = 16; }
+          for (; cc < cn; ++cc) {
+            const float e0 = exp2_ftz(fmaf(row[c0 + cc], SSDG_LOG2E, kexp));
+            if (kWrite) row[c0 + cc] = e0;
+            s0 += e0;
+            if (e0 > pre) bits |= 1u << cc;
+          }
+          return bits;
+        };
+        const std::integral_constant<int, 32> w32;
+        bits0 = nfg >= 32 ? chunkN(0, w32) : chunk(0, nfg);
+        if (nfg > 32) bits1 = nfg >= 64 ? chunkN(32, w32) : chunk(32, nfg - 32);
+        if (nfg > 64) bits2 = nfg >= 96 ? chunkN(64, w32) : chunk(64, nfg - 64);
+        for (int c = min(nfg, 96); c < C; ++c) {   // background and the classes beyond 96
+          const float e0 = exp2_ftz(fmaf(row[c], SSDG_LOG2E, kexp));
+          if (two_pass) row[c] = e0;
           s0 += e0;
-          if (e0 > pre) bits |= 1u << cc;
         }
-        return bits;
-      };
-      bits0 = nfg >= 32 ? chunk32(0) : chunk(0, nfg);
-      if (nfg > 32) bits1 = nfg >= 64 ? chunk32(32) : chunk(32, nfg - 32);
-      if (nfg > 64) bits2 = nfg >= 96 ? chunk32(64) : chunk(64, nfg - 64);
-      for (c = min(nfg, 96); c < C; ++c) {   // background and the classes beyond 96: always stored
-        const float e0 = exp2_ftz(fmaf(row[c], SSDG_LOG2E, kexp));
-        row[c] = e0; s0 += e0;
+        if (attempt > 0 || (s0 + s1) <= 65536.f) break;
+        ref = row_max();
       }
       inv_s = __frcp_rn(s0 + s1);
       if (P.row_ml) {   // the loss of the same predictions reuses this pass instead of streaming the logits again
         const float lg = logf(s0 + s1);
-        P.row_ml[n] = make_float2(mx, lg);
-        P.row_negbg[n] = lg - (xbg - mx);
+        P.row_ml[n] = make_float2(ref, lg);
+        P.row_negbg[n] = lg - (xbg - ref);
       }
     } else {
       const int lim = min(nfg, 96);
@@ -275,27 +295,23 @@ __global__ void __launch_bounds__(kFThreads, 2) filter_kernel(DetectParams P, in
   u64* mybar = bars + warp;
   const u64 pol = evict_first_policy();
 
-  auto tile_rows = [&](long long t) { const int j = (int)(t % tpi); return min(32, A - j * 32); };
-  auto tile_src = [&](long long t) {
-    const long long b = t / tpi;
-    const int j = (int)(t - b * tpi);
-    return P.pred_cls + ((size_t)b * A + (size_t)j * 32) * C;
-  };
-  auto issue = [&](long long t) {  // lane 0 only
-    const u32 bytes = (u32)tile_rows(t) * (u32)C * 4u;
+  // (image, tile of the image) of the warp's current tile, advanced without divisions
+  int b = (int)(gw / tpi), j = (int)(gw - (long long)b * tpi);
+  const int step_b = (int)(stride / tpi), step_j = (int)(stride - (long long)step_b * tpi);
+  auto issue = [&](int ib, int ij) {  // lane 0 only
+    const u32 bytes = (u32)min(32, A - ij * 32) * (u32)C * 4u;
     mbar_arrive_expect_tx(mybar, bytes);
-    tma_load_hint(tile, tile_src(t), bytes, mybar, pol);
+    tma_load_hint(tile, P.pred_cls + ((size_t)ib * A + (size_t)ij * 32) * C, bytes, mybar, pol);
   };
   // One tile in flight per warp; the other 15 warps of the CTA hide its latency.
-  if (P.tma_ok && lane == 0 && gw < ntiles) issue(gw);
+  if (P.tma_ok && lane == 0 && gw < ntiles) issue(b, j);
   int k = 0;
   for (long long t = gw; t < ntiles; t += stride, ++k) {
-    const int rows = tile_rows(t);
-    const int b = (int)(t / tpi), j = (int)(t - (long long)b * tpi);
+    const int rows = min(32, A - j * 32);
     if (P.tma_ok) {
       mbar_wait(mybar, (u32)(k & 1));
     } else {  // unaligned shapes: plain cooperative copy
-      const float* g = tile_src(t);
+      const float* g = P.pred_cls + ((size_t)b * A + (size_t)j * 32) * C;
       for (int i = lane; i < rows * C; i += 32) tile[i] = g[i];
       __syncwarp();
     }
@@ -308,8 +324,9 @@ __global__ void __launch_bounds__(kFThreads, 2) filter_kernel(DetectParams P, in
       for (int i = lane; i < rows * C; i += 32) __stcs(&dst[i], tile[i]);
       __syncwarp();
     }
-    const long long tn = t + stride;
-    if (P.tma_ok && lane == 0 && tn < ntiles) issue(tn);
+    b += step_b; j += step_j;
+    if (j >= tpi) { j -= tpi; ++b; }
+    if (P.tma_ok && lane == 0 && t + stride < ntiles) issue(b, j);
   }
 }
 
@@ -433,12 +450,10 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
   __shared__ int sel_k, sel_fill;
 
   const size_t list = blockIdx.x;
-  const int b = (int)(list / P.n_fg);
+  const int b = (int)(blockIdx.x / (u32)P.n_fg);
   int n = (int)P.cls_cnt[list];
   const u64* cl = P.sorted + (size_t)b * P.img_stride + P.cls_off[list];
 
-  for (int i = tid; i < sortn; i += kNmsThreads) keys[i] = 0ull;
-  __syncthreads();
   if (n <= sortn) {
     for (int i = tid; i < n; i += kNmsThreads) keys[i] = cl[i];
   } else {
@@ -737,18 +752,30 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
   }
   __syncthreads();
 
-  // kept priors in visit order
+  // kept priors in visit order; hist[w] = kept boxes before word w
+  if (warp == 0) {
+    const int c = lane < W ? __popc(keptw[lane]) : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(SSDG_FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane < W) hist[lane] = (u32)(incl - c);   // W <= 32 (shared memory limits sortn to 1024)
+    if (lane == 31) hist[W] = (u32)incl;
+  }
+  __syncthreads();
   int* ok = P.out_kept + list * (size_t)P.top_k;
   float* os = P.out_score ? P.out_score + list * (size_t)P.top_k : nullptr;
-  int total = 0;
-  for (int w = 0; w < W; ++w) total += __popc(keptw[w]);
-  for (int i = tid; i < P.top_k; i += kNmsThreads) {
-    if (i >= total) { ok[i] = -1; if (os) os[i] = 0.f; }
+  const int total = (int)hist[W];
+  for (int i = total + tid; i < P.top_k; i += kNmsThreads) {
+    ok[i] = -1;
+    if (os) os[i] = 0.f;
   }
   for (int i = tid; i < m; i += kNmsThreads) {
-    if (keptw[i >> 5] & (1u << (i & 31))) {
-      int rank = __popc(keptw[i >> 5] & ((1u << (i & 31)) - 1u));
-      for (int w = 0; w < (i >> 5); ++w) rank += __popc(keptw[w]);
+    const u32 kw = keptw[i >> 5], bit = 1u << (i & 31);
+    if (kw & bit) {
+      const int rank = (int)hist[i >> 5] + __popc(kw & (bit - 1u));
       ok[rank] = (int)(~(u32)keys[i]);
       if (os) os[rank] = unkey32((u32)(keys[i] >> 32));
     }

@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libssdgeom.so")
+# SSDGEOM_LIB selects another build of the same library (A/B measurements of kernel variants); never a fallback
+LIB_PATH = os.environ.get("SSDGEOM_LIB") or os.path.join(_HERE, "_lib", "libssdgeom.so")
 
 OK = 0
 ERR_ARG, ERR_TOO_MANY_GT, ERR_THRESH, ERR_SHAPE, ERR_NO_POSITIVE = -1, -2, -3, -4, -5
