@@ -22,7 +22,18 @@
 
 namespace ssdg {
 
-constexpr int kFThreads = 512;
+#ifndef SSDG_FILTER_THREADS
+#define SSDG_FILTER_THREADS 512
+#endif
+#ifndef SSDG_FILTER_MINB
+#define SSDG_FILTER_MINB 2
+#endif
+#ifdef SSDG_FILTER_MAXNREG
+#define SSDG_FILTER_BOUNDS __maxnreg__(SSDG_FILTER_MAXNREG)
+#else
+#define SSDG_FILTER_BOUNDS __launch_bounds__(SSDG_FILTER_THREADS, SSDG_FILTER_MINB)
+#endif
+constexpr int kFThreads = SSDG_FILTER_THREADS;
 constexpr int kFWarps = kFThreads / 32;
 constexpr int kNmsThreads = 128;
 constexpr int kNmsWarps = kNmsThreads / 32;
@@ -274,7 +285,7 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
 }
 
 template <typename TP, bool kProbs, bool kWrite>
-__global__ void __launch_bounds__(kFThreads, 2) filter_kernel(DetectParams P, int warps_per_cta) {   // <= 64 registers: leaves room for a matcher CTA
+__global__ void SSDG_FILTER_BOUNDS filter_kernel(DetectParams P, int warps_per_cta) {   // <= 64 registers: leaves room for a matcher CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int C = P.C, A = P.A, tpi = P.tpi;
   const size_t tile_floats = (size_t)32 * C;

@@ -270,13 +270,13 @@ static size_t match_smem_bytes(int tm, int ntiles_s, int bit_words) {
 constexpr int kSearchThreads = 128;
 constexpr int kSearchWarps = kSearchThreads / 32;
 
-template <typename TG, typename TP>
+template <typename TG, typename TP, bool kCached>   // kCached: per-warp shared-memory cache of the row's tile bounds
 __global__ void __launch_bounds__(kSearchThreads, 8) search_kernel(MatchParams P) {
   typedef typename Promote<TG, TP>::type R;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int A = P.A, ntiles = P.ntiles;
-  const bool cached = ntiles <= kTileSmemMax;   // per-warp cache of the row's tile bounds
+  constexpr bool cached = kCached;
   // the tile statistics stay in global memory (L1/L2-resident, 14 KB for SSD300): staging them per CTA costs
   // shared memory that decides how many of these CTAs fit beside a streaming kernel of the other branch
   float* ubw = reinterpret_cast<float*>(smem_raw) + (size_t)warp * (cached ? ntiles : 0);
@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(kSearchThreads, 8) search_kernel(MatchParams P
     u64 best_key = 0ull;
     int best_a = 0x7fffffff;
     float rowlo = 0.f;
+    u32 rowhi = 0u;
     // exact evaluation of one tile for this row (all lanes)
     auto evaluate = [&](int tile) {
       const int slot = (tile << 5) + lane;
@@ -341,12 +342,13 @@ __global__ void __launch_bounds__(kSearchThreads, 8) search_kernel(MatchParams P
           if (pos < kCandCap) { Cand c; c.key = key; c.a = a; c.t = t; cand[pos] = c; }
         }
       }
-      u64 wk = key;
-      int wa = valid ? a : 0x7fffffff;
-      warp_argmax_u64(wk, wa);
-      if (wk > best_key || (wk == best_key && wa < best_a)) {
-        best_key = wk; best_a = wa;
-        rowlo = fmaxf(f_down(unkey64(wk)), 0.f);
+      // every lane keeps its own best (key, then lowest prior): one arg-max across the warp per ROW.  The running
+      // row maximum only prunes: a lower bound of it (the key's high word, one REDUX) is all pass 2 needs.
+      if (valid && (key > best_key || (key == best_key && a < best_a))) { best_key = key; best_a = a; }
+      const u32 mhi = __reduce_max_sync(SSDG_FULL, (u32)(key >> 32));
+      if (mhi > rowhi) {
+        rowhi = mhi;
+        rowlo = fmaxf(f_down(unkey64((u64)mhi << 32)), 0.f);
       }
     };
     // pass 1: bound every tile; the highest bound seeds the running maximum
@@ -390,6 +392,7 @@ __global__ void __launch_bounds__(kSearchThreads, 8) search_kernel(MatchParams P
         evaluate(tb + l);
       }
     }
+    warp_argmax_u64(best_key, best_a);
     if (lane == 0) {
       P.ws_rowkey[(size_t)img * P.tm + t] = best_key;
       P.ws_rowcol[(size_t)img * P.tm + t] = best_a;
@@ -821,16 +824,16 @@ static int launch_match(const MatchParams& P, int grid, size_t smem, cudaStream_
   SSDG_CUDA_TRY(cudaFuncSetAttribute(match_kernel<TG, TP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   prof_begin(SSDG_PROF_MATCH, st);
   {
-    const size_t ssm = P.ntiles <= kTileSmemMax ? (size_t)P.ntiles * kSearchWarps * 4 : 0;
-    if (ssm > 48 * 1024)
-      SSDG_CUDA_TRY(cudaFuncSetAttribute(search_kernel<TG, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
-    SSDG_CUDA_TRY(cudaFuncSetAttribute(search_kernel<TG, TP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    const bool cached = P.ntiles <= kTileSmemMax;
+    const size_t ssm = cached ? (size_t)P.ntiles * kSearchWarps * 4 : 0;
+    auto skern = cached ? search_kernel<TG, TP, true> : search_kernel<TG, TP, false>;
+    SSDG_CUDA_TRY(cudaFuncSetAttribute(skern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     static const char* env = getenv("SSDG_SEARCH_CTAS_PER_SM");   // experiment knob
     long long sgrid = (long long)sm_count() * (env ? atoi(env) : 8);
     const long long want = ((long long)P.B * (P.max_gt > 0 ? P.max_gt : 1) + kSearchWarps - 1) / kSearchWarps;
     if (want < sgrid) sgrid = want;
     prof_begin(SSDG_PROF_SEARCH, st);
-    search_kernel<TG, TP><<<(unsigned)sgrid, kSearchThreads, ssm, st>>>(P);
+    skern<<<(unsigned)sgrid, kSearchThreads, ssm, st>>>(P);
     prof_end(SSDG_PROF_SEARCH, st);
     SSDG_LAUNCH_CHECK();
   }
