@@ -440,23 +440,24 @@ struct NmsParams {
   float* out_score;
 };
 
-__global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
+__global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int sortn = P.sortn, W = sortn >> 5, WP = W | 1;
+  // sortn keys take part in the sort; only the first mcap = top_k rounded up to 32 boxes exist afterwards
+  const int sortn = P.sortn, mcap = (P.top_k + 31) & ~31, W = mcap >> 5, RL = (4 * W) | 1;
   u64* keys = reinterpret_cast<u64*>(smem_raw);                 // [sortn]
-  float4* crn = reinterpret_cast<float4*>(keys + sortn);        // [sortn] x1,y1,x2,y2
-  float2* q2 = reinterpret_cast<float2*>(crn + sortn);          // [sortn] qa*1.0001, qa*0.9999
-  float* area = reinterpret_cast<float*>(q2 + sortn);           // [sortn]
-  u32* sup = reinterpret_cast<u32*>(area + sortn);              // [sortn][WP] lower triangle
-  u32* keptw = sup + (size_t)sortn * WP;                        // [W]
+  float4* crn = reinterpret_cast<float4*>(keys + sortn);        // [mcap] x1,y1,x2,y2 (sort scratch: sortn keys)
+  float* qlo = reinterpret_cast<float*>(crn + mcap);            // [mcap] q*area*0.9999
+  float* area = qlo + mcap;                                     // [mcap]
+  u32* slidx = reinterpret_cast<u32*>(area + mcap);             // [mcap] slab interval ax | bx<<8 | ay<<16 | by<<24
+  u32* sup = slidx + mcap;                                      // lower triangle, [group g][word w <= g][row of the group]
+  u32* keptw = sup + (size_t)16 * W * (W + 1);                  // [W]
   u32* remw = keptw + W;                                        // [W]
-  u32* hist = remw + W;                                         // [256]
-  u32* slabx = hist + 256;                                      // [W][kSlabs] boxes whose shrunk x extent touches the slab
-  u32* slaby = slabx + kSlabs * W;                              // same for y
-  float* dom = reinterpret_cast<float*>(slaby + kSlabs * W);    // [4 + 4*kNmsWarps] slab domain
-  u32* bstart = reinterpret_cast<u32*>(dom + 4 + 4 * kNmsWarps);  // [256] rank sort: first slot of each bucket
-  u32* mm = bstart + 256;                                       // [4] min/max of the score and prior words
+  float* dom = reinterpret_cast<float*>(remw + W);              // [4 + 4*kNmsWarps] slab domain
+  u32* mm = reinterpret_cast<u32*>(dom + 4 + 4 * kNmsWarps);    // [4] min/max of the score and prior words
+  u32* hist = mm + 4;                                           // [256] sort / select histogram
+  u32* bstart = hist + 256;                                     // [256] rank sort: first slot of each bucket
+  u32* tab = hist;                                              // [kSlabs][RL] interval tables of the join (after the sort)
   __shared__ u64 sel_prefix;
   __shared__ int sel_k, sel_fill;
 
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
     }
     crn[i] = cr;
     area[i] = ar;
-    q2[i] = make_float2(qa * 1.0001f, qa * 0.9999f);
+    qlo[i] = qa * 0.9999f;
   }
   for (int i = tid; i < W; i += kNmsThreads) { keptw[i] = 0u; remw[i] = 0u; }
   __syncthreads();
@@ -604,7 +605,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
     {
       u32 k1 = ~0u, k2 = ~0u, k3 = 0u, k4 = 0u;
       for (int i = tid; i < m; i += kNmsThreads) {
-        if (isfinite(q2[i].y)) {
+        if (isfinite(qlo[i])) {
           const float4 c = crn[i];
           const float pr = (c.z - c.x) * (c.w - c.y);
           inexact |= !(area[i] >= 0.999f * pr && area[i] <= 1.001f * pr);
@@ -617,7 +618,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
         dom[4 + 4 * warp + 0] = unkey32(k1); dom[4 + 4 * warp + 1] = unkey32(k2);
         dom[4 + 4 * warp + 2] = unkey32(k3); dom[4 + 4 * warp + 3] = unkey32(k4);
       }
-      for (int i = tid; i < 2 * kSlabs * W; i += kNmsThreads) slabx[i] = 0u;   // both axes
+      for (int i = tid; i < kSlabs * RL; i += kNmsThreads) tab[i] = 0u;   // the sort is done with hist / bstart
       inexact = __syncthreads_or(inexact);
       if (tid == 0) {
         float x1 = CUDART_INF_F, y1 = CUDART_INF_F, x2 = -CUDART_INF_F, y2 = -CUDART_INF_F;
@@ -639,44 +640,54 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
     // 0.98: inter > q (a_i + a_j) and the 0.1% above leave ex > 0.997 q (w'_i + w'_j); the guard g covers the
     // float rounding of the shrunk ends (a few ulps of the coordinates)
     const float tq = inexact ? 0.f : fminf(0.98f * q, 0.49f);
-    // slab bitsets as [word][slab]: lanes with different slabs hit different banks
+    // Every box has a slab interval [a, b] per axis; two intervals meet  <=>  a_j <= b_i  and  b_j >= a_i.
+    // Tables per axis, one bitset over the boxes per slab s:  LE[s] = {j : a_j <= s},  GE[s] = {j : b_j >= s}
+    // -- the boxes whose x interval meets box i's are  LE[b_i] & GE[a_i]:  two loads per axis whatever the
+    // width.  Built by registering each box at its two end slabs, then a running OR along the slabs.
+    // Layout tab[slab][RL], column = kind * W + word (kind: LEx, GEx, LEy, GEy); RL odd: lanes with different
+    // slabs (queries) or different columns (the running OR) hit different banks.
     for (int i = tid; i < m; i += kNmsThreads) {
-      if (!isfinite(q2[i].y)) continue;
+      if (!isfinite(qlo[i])) { slidx[i] = 0u; continue; }
       const float4 c = crn[i];
       const u32 bit = 1u << (i & 31);
-      const int wi = (i >> 5) * kSlabs;
+      const int wi = i >> 5;
       const float sx = tq * (c.z - c.x) - 1e-6f * (fabsf(c.x) + fabsf(c.z));
       const float sy = tq * (c.w - c.y) - 1e-6f * (fabsf(c.y) + fabsf(c.w));
       const int ax = slab(c.x + sx, dx0, dsx), bx = max(slab(c.z - sx, dx0, dsx), ax);
       const int ay = slab(c.y + sy, dy0, dsy), by = max(slab(c.w - sy, dy0, dsy), ay);
-      for (int sl = ax; sl <= bx; ++sl) atomicOr(&slabx[wi + sl], bit);
-      for (int sl = ay; sl <= by; ++sl) atomicOr(&slaby[wi + sl], bit);
+      slidx[i] = (u32)ax | ((u32)bx << 8) | ((u32)ay << 16) | ((u32)by << 24);
+      atomicOr(&tab[ax * RL + wi], bit);
+      atomicOr(&tab[bx * RL + W + wi], bit);
+      atomicOr(&tab[ay * RL + 2 * W + wi], bit);
+      atomicOr(&tab[by * RL + 3 * W + wi], bit);
     }
     __syncthreads();
-    for (int i = tid; i < m; i += kNmsThreads) {
+    for (int col = tid; col < 4 * W; col += kNmsThreads) {
+      const bool up = ((col / W) & 1) == 0;   // LE: ascending running OR, GE: descending
+      u32 acc = 0u;
+#pragma unroll 8
+      for (int k = 0; k < kSlabs; ++k) {
+        const int sl = up ? k : kSlabs - 1 - k;
+        acc |= tab[sl * RL + col];
+        tab[sl * RL + col] = acc;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < mpad; i += kNmsThreads) {   // whole warps: rows 32g .. 32g+31
       const int gi = i >> 5;
-      const float4 bi = crn[i];
-      const float qi_lo = q2[i].y;
+      const bool live = i < m;
+      const float4 bi = live ? crn[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float qi_lo = live ? qlo[i] : CUDART_INF_F;
       const bool sane = isfinite(qi_lo);
-      const float sx = tq * (bi.z - bi.x) - 1e-6f * (fabsf(bi.x) + fabsf(bi.z));
-      const float sy = tq * (bi.w - bi.y) - 1e-6f * (fabsf(bi.y) + fabsf(bi.w));
-      const int ax = slab(bi.x + sx, dx0, dsx), bx = max(slab(bi.z - sx, dx0, dsx), ax);
-      const int ay = slab(bi.y + sy, dy0, dsy), by = max(slab(bi.w - sy, dy0, dsy), ay);
-      // shrunk extents mostly touch one to four slabs: four fixed loads per axis, a loop for the rest
-      const int ax1 = min(ax + 1, bx), ax2 = min(ax + 2, bx), ay1 = min(ay + 1, by), ay2 = min(ay + 2, by);
-      const int ax3 = min(ax + 3, bx), ay3 = min(ay + 3, by);
-      const bool wide = bx - ax > 3 || by - ay > 3;
-      for (int w = 0; w <= gi; ++w) {
-        const u32* px = slabx + w * kSlabs;
-        const u32* py = slaby + w * kSlabs;
-        u32 mx = px[ax] | px[ax1] | px[ax2] | px[ax3], my = py[ay] | py[ay1] | py[ay2] | py[ay3];
-        if (wide) {
-#pragma unroll 1
-          for (int sl = ax + 4; sl <= bx; ++sl) mx |= px[sl];
-#pragma unroll 1
-          for (int sl = ay + 4; sl <= by; ++sl) my |= py[sl];
-        }
-        u32 cand = sane ? (mx & my) : 0u;
+      const u32 si = live ? slidx[i] : 0u;
+      const u32* lex = tab + ((si >> 8) & 255u) * RL;            // LEx[b_i]
+      const u32* gex = tab + (si & 255u) * RL + W;               // GEx[a_i]
+      const u32* ley = tab + (si >> 24) * RL + 2 * W;            // LEy[b_i]
+      const u32* gey = tab + ((si >> 16) & 255u) * RL + 3 * W;   // GEy[a_i]
+      const float ai = live ? area[i] : 0.f;
+      u32 any = 0u;
+      auto word = [&](int w) {
+        u32 cand = sane ? (lex[w] & gex[w] & ley[w] & gey[w]) : 0u;
         if (w == gi) cand &= (1u << (i & 31)) - 1u;
         u32 bits = 0u;
         while (cand) {
@@ -686,16 +697,27 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
           const float4 bj = crn[j];
           const float fx = fminf(bi.z, bj.z) - fmaxf(bi.x, bj.x);
           const float fy = fminf(bi.w, bj.w) - fmaxf(bi.y, bj.y);
-          if (!(fx > 0.f && fx * fy >= qi_lo + q2[j].y)) continue;   // cheap float test, 1e-4 margin
+          if (!(fx > 0.f && fx * fy >= qi_lo + qlo[j])) continue;   // cheap float test, 1e-4 margin
           // the formula itself: IEEE float32, no contraction (utils/bbox.py:13-25)
           const float ex = fmaxf(0.f, __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
           const float ey = fmaxf(0.f, __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
           const float inter = __fmul_rn(ex, ey);
-          const float den = __fadd_rn(__fsub_rn(__fadd_rn(area[j], area[i]), inter), 1e-10f);
+          const float den = __fadd_rn(__fsub_rn(__fadd_rn(area[j], ai), inter), 1e-10f);
           if (__fdiv_rn(inter, den) > thr) bits |= 1u << jj;
         }
-        sup[(size_t)i * WP + w] = bits;
+        sup[16 * gi * (gi + 1) + (w << 5) + lane] = bits;
+        any |= bits;
+      };
+      if (W <= 8) {   // the usual top_k <= 256: word offsets become immediates
+#pragma unroll
+        for (int w = 0; w < 8; ++w)
+          if (w <= gi) word(w);
+      } else {
+        for (int w = 0; w <= gi; ++w) word(w);
       }
+      // rows nobody suppresses are kept at once; the fixed point below only resolves the others
+      const u32 free_rows = __ballot_sync(SSDG_FULL, live && any == 0u);
+      if (lane == 0) keptw[gi] = free_rows;
     }
   } else {
   // No division-free test for this threshold: all pairs, the formula itself.
@@ -708,18 +730,17 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
     const int w = task - g * (g + 1) / 2;
     const int i = (g << 5) + lane;
     const float4 bi = crn[i];
-    const float2 qi = q2[i];
     // every pair that can exceed the threshold passes the cheap float test (1e-4 relative margin,
     // float rounding is ~1e-7); the rare survivors are decided by the formula itself
     u32 maybe = 0u;
-    const float qi_lo = qi.y;
+    const float qi_lo = qlo[i];
 #pragma unroll
     for (int jj = 0; jj < 32; ++jj) {
       const int j = (w << 5) + jj;
       const float4 bj = crn[j];
       const float ex = fminf(bi.z, bj.z) - fmaxf(bi.x, bj.x);
       const float ey = fminf(bi.w, bj.w) - fmaxf(bi.y, bj.y);
-      const u32 hit = (u32)(ex > 0.f) & (u32)(ex * ey >= qi_lo + q2[j].y);   // no branch
+      const u32 hit = (u32)(ex > 0.f) & (u32)(ex * ey >= qi_lo + qlo[j]);   // no branch
       maybe |= hit << jj;
     }
     if (!fast_ok) maybe = 0xffffffffu;
@@ -738,7 +759,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
       const float den = __fadd_rn(__fsub_rn(__fadd_rn(area[j], area[i]), inter), 1e-10f);
       if (__fdiv_rn(inter, den) > thr) bits |= 1u << jj;
     }
-    sup[(size_t)i * WP + w] = bits;
+    sup[16 * g * (g + 1) + (w << 5) + lane] = bits;
   }
   }
   __syncthreads();
@@ -750,8 +771,9 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams P) {
       const u32 bit = 1u << (i & 31);
       if ((keptw[i >> 5] | remw[i >> 5]) & bit) continue;
       bool hit_kept = false, all_removed = true;
+      const int sbase = 16 * (i >> 5) * ((i >> 5) + 1) + (i & 31);
       for (int w = 0; w <= (i >> 5); ++w) {
-        const u32 sb = sup[(size_t)i * WP + w];
+        const u32 sb = sup[sbase + (w << 5)];
         if (sb & keptw[w]) hit_kept = true;
         if (sb & ~remw[w]) all_removed = false;
       }
@@ -804,10 +826,11 @@ static int next_pow2(int v) {
   while (p < v) p <<= 1;
   return p;
 }
-static size_t nms_smem_bytes(int sortn) {
-  const int W = sortn / 32, WP = W | 1;
-  return (size_t)sortn * (8 + 16 + 8 + 4) + (size_t)sortn * WP * 4 + 2 * W * 4 + 256 * 4 +
-         (size_t)2 * kSlabs * W * 4 + (4 + 4 * kNmsWarps) * 4 + 260 * 4 + 128;
+static size_t nms_smem_bytes(int sortn, int top_k) {
+  const int mcap = (top_k + 31) & ~31, W = mcap / 32, RL = (4 * W) | 1;
+  const size_t tab = (size_t)kSlabs * RL > 512 ? (size_t)kSlabs * RL : 512;   // hist + bstart, then the join tables
+  return (size_t)sortn * 8 + (size_t)mcap * (16 + 4 + 4 + 4) + (size_t)16 * W * (W + 1) * 4 + 2 * W * 4 +
+         (4 + 4 * kNmsWarps) * 4 + 16 + tab * 4 + 128;
 }
 
 struct DetectWs {
@@ -881,7 +904,7 @@ static int run_nms(const DetectWs& ws, const float* boxes, long long batch, int 
   Q.boxes = boxes; Q.A = A; Q.n_fg = C - 1; Q.top_k = top_k;
   Q.sortn = next_pow2(top_k); Q.iou_thresh = iou_thresh;
   Q.out_kept = out_kept; Q.out_count = out_count; Q.out_score = out_score;
-  const size_t smem = nms_smem_bytes(Q.sortn);
+  const size_t smem = nms_smem_bytes(Q.sortn, top_k);
   if ((int)smem > max_smem_optin()) return SSDG_ERR_LIMIT;
   if (smem > 48 * 1024)
     SSDG_CUDA_TRY(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
