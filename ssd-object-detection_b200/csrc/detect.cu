@@ -38,6 +38,7 @@ constexpr int kFWarps = kFThreads / 32;
 constexpr int kNmsThreads = 128;
 constexpr int kNmsWarps = kNmsThreads / 32;
 constexpr int kSlabs = 32;   // slabs per axis of the NMS candidate join
+constexpr int kSizeCls = 16; // width / height classes of the join
 constexpr int kBucketThreads = 512;
 constexpr int kABitsD = 21;     // prior index bits in a staged candidate (A < 2^21, C <= 2048)
 
@@ -453,11 +454,13 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
   u32* sup = slidx + mcap;                                      // lower triangle, [group g][word w <= g][row of the group]
   u32* keptw = sup + (size_t)16 * W * (W + 1);                  // [W]
   u32* remw = keptw + W;                                        // [W]
-  float* dom = reinterpret_cast<float*>(remw + W);              // [4 + 4*kNmsWarps] slab domain
-  u32* mm = reinterpret_cast<u32*>(dom + 4 + 4 * kNmsWarps);    // [4] min/max of the score and prior words
+  float* dom = reinterpret_cast<float*>(remw + W);              // [8 + 4*kNmsWarps] slab domain, log2 of its extents
+  u32* mm = reinterpret_cast<u32*>(dom + 8 + 4 * kNmsWarps);    // [4] min/max of the score and prior words
   u32* hist = mm + 4;                                           // [256] sort / select histogram
   u32* bstart = hist + 256;                                     // [256] rank sort: first slot of each bucket
   u32* tab = hist;                                              // [kSlabs][RL] interval tables of the join (after the sort)
+  const int RS = (2 * W) | 1;
+  u32* stab = tab + max(512, kSlabs * RL);                      // [kSizeCls][RS] width / height class neighbourhoods
   __shared__ u64 sel_prefix;
   __shared__ int sel_k, sel_fill;
 
@@ -615,20 +618,23 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
       k1 = __reduce_min_sync(SSDG_FULL, k1); k2 = __reduce_min_sync(SSDG_FULL, k2);
       k3 = __reduce_max_sync(SSDG_FULL, k3); k4 = __reduce_max_sync(SSDG_FULL, k4);
       if (lane == 0) {
-        dom[4 + 4 * warp + 0] = unkey32(k1); dom[4 + 4 * warp + 1] = unkey32(k2);
-        dom[4 + 4 * warp + 2] = unkey32(k3); dom[4 + 4 * warp + 3] = unkey32(k4);
+        dom[8 + 4 * warp + 0] = unkey32(k1); dom[8 + 4 * warp + 1] = unkey32(k2);
+        dom[8 + 4 * warp + 2] = unkey32(k3); dom[8 + 4 * warp + 3] = unkey32(k4);
       }
       for (int i = tid; i < kSlabs * RL; i += kNmsThreads) tab[i] = 0u;   // the sort is done with hist / bstart
+      for (int i = tid; i < kSizeCls * RS; i += kNmsThreads) stab[i] = 0u;
       inexact = __syncthreads_or(inexact);
       if (tid == 0) {
         float x1 = CUDART_INF_F, y1 = CUDART_INF_F, x2 = -CUDART_INF_F, y2 = -CUDART_INF_F;
         for (int w = 0; w < kNmsWarps; ++w) {
-          x1 = fminf(x1, dom[4 + 4 * w]); y1 = fminf(y1, dom[5 + 4 * w]);
-          x2 = fmaxf(x2, dom[6 + 4 * w]); y2 = fmaxf(y2, dom[7 + 4 * w]);
+          x1 = fminf(x1, dom[8 + 4 * w]); y1 = fminf(y1, dom[9 + 4 * w]);
+          x2 = fmaxf(x2, dom[10 + 4 * w]); y2 = fmaxf(y2, dom[11 + 4 * w]);
         }
         dom[0] = x1; dom[1] = y1;
         dom[2] = (x2 > x1) ? (float)kSlabs / (x2 - x1) : 0.f;
         dom[3] = (y2 > y1) ? (float)kSlabs / (y2 - y1) : 0.f;
+        dom[4] = (x2 > x1) ? __log2f(x2 - x1) : 0.f;
+        dom[5] = (y2 > y1) ? __log2f(y2 - y1) : 0.f;
       }
       __syncthreads();
     }
@@ -646,6 +652,17 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
     // width.  Built by registering each box at its two end slabs, then a running OR along the slabs.
     // Layout tab[slab][RL], column = kind * W + word (kind: LEx, GEx, LEy, GEy); RL odd: lanes with different
     // slabs (queries) or different columns (the running OR) hit different banks.
+    // Size classes.  iou > thr needs  inter > t' E_i  (E = extent product, within 0.1% of the formula's area;
+    // t' = 0.99 thr / (1 + 0.001 thr)) and inter <= w_j h_i:  the widths -- and the heights -- of a pair differ by
+    // less than a factor 1/t', so with classes of that ratio a pair's classes differ by at most one.  A box
+    // registers in its class; the neighbourhood {c-1, c, c+1} is ORed below; the query ANDs both dimensions.
+    const float tp = 0.99f * thr / (1.f + 0.001f * thr);
+    const float inv_l = (!inexact && tp < 0.98f) ? -1.f / __log2f(tp) : 0.f;
+    const float lwx = dom[4], lwy = dom[5];
+    auto size_cls = [&](float ext, float lref) {   // monotone in ext, clamped (clamping only merges classes)
+      const float f = (lref - __log2f(ext)) * inv_l;
+      return f >= (float)(kSizeCls - 1) ? kSizeCls - 1 : (f > 0.f ? (int)f : 0);
+    };
     for (int i = tid; i < m; i += kNmsThreads) {
       if (!isfinite(qlo[i])) { slidx[i] = 0u; continue; }
       const float4 c = crn[i];
@@ -655,21 +672,35 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
       const float sy = tq * (c.w - c.y) - 1e-6f * (fabsf(c.y) + fabsf(c.w));
       const int ax = slab(c.x + sx, dx0, dsx), bx = max(slab(c.z - sx, dx0, dsx), ax);
       const int ay = slab(c.y + sy, dy0, dsy), by = max(slab(c.w - sy, dy0, dsy), ay);
-      slidx[i] = (u32)ax | ((u32)bx << 8) | ((u32)ay << 16) | ((u32)by << 24);
+      const int cw = inv_l > 0.f ? size_cls(c.z - c.x, lwx) : 0, ch = inv_l > 0.f ? size_cls(c.w - c.y, lwy) : 0;
+      slidx[i] = (u32)ax | ((u32)bx << 5) | ((u32)ay << 10) | ((u32)by << 15) | ((u32)cw << 20) | ((u32)ch << 24);
       atomicOr(&tab[ax * RL + wi], bit);
       atomicOr(&tab[bx * RL + W + wi], bit);
       atomicOr(&tab[ay * RL + 2 * W + wi], bit);
       atomicOr(&tab[by * RL + 3 * W + wi], bit);
+      atomicOr(&stab[cw * RS + wi], bit);
+      atomicOr(&stab[ch * RS + W + wi], bit);
     }
     __syncthreads();
-    for (int col = tid; col < 4 * W; col += kNmsThreads) {
-      const bool up = ((col / W) & 1) == 0;   // LE: ascending running OR, GE: descending
-      u32 acc = 0u;
+    for (int col = tid; col < 6 * W; col += kNmsThreads) {
+      if (col < 4 * W) {
+        const bool up = ((col / W) & 1) == 0;   // LE: ascending running OR, GE: descending
+        u32 acc = 0u;
 #pragma unroll 8
-      for (int k = 0; k < kSlabs; ++k) {
-        const int sl = up ? k : kSlabs - 1 - k;
-        acc |= tab[sl * RL + col];
-        tab[sl * RL + col] = acc;
+        for (int k = 0; k < kSlabs; ++k) {
+          const int sl = up ? k : kSlabs - 1 - k;
+          acc |= tab[sl * RL + col];
+          tab[sl * RL + col] = acc;
+        }
+      } else {
+        u32* sc = stab + (col - 4 * W);
+        u32 prev = 0u, cur = sc[0];
+#pragma unroll 4
+        for (int k = 0; k < kSizeCls; ++k) {
+          const u32 nxt = k + 1 < kSizeCls ? sc[(k + 1) * RS] : 0u;
+          sc[k * RS] = prev | cur | nxt;
+          prev = cur; cur = nxt;
+        }
       }
     }
     __syncthreads();
@@ -680,14 +711,16 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
       const float qi_lo = live ? qlo[i] : CUDART_INF_F;
       const bool sane = isfinite(qi_lo);
       const u32 si = live ? slidx[i] : 0u;
-      const u32* lex = tab + ((si >> 8) & 255u) * RL;            // LEx[b_i]
-      const u32* gex = tab + (si & 255u) * RL + W;               // GEx[a_i]
-      const u32* ley = tab + (si >> 24) * RL + 2 * W;            // LEy[b_i]
-      const u32* gey = tab + ((si >> 16) & 255u) * RL + 3 * W;   // GEy[a_i]
+      const u32* lex = tab + ((si >> 5) & 31u) * RL;             // LEx[b_i]
+      const u32* gex = tab + (si & 31u) * RL + W;                // GEx[a_i]
+      const u32* ley = tab + ((si >> 15) & 31u) * RL + 2 * W;    // LEy[b_i]
+      const u32* gey = tab + ((si >> 10) & 31u) * RL + 3 * W;    // GEy[a_i]
+      const u32* szw = stab + ((si >> 20) & 15u) * RS;           // width classes next to the row's
+      const u32* szh = stab + (si >> 24) * RS + W;               // height classes
       const float ai = live ? area[i] : 0.f;
       u32 any = 0u;
       auto word = [&](int w) {
-        u32 cand = sane ? (lex[w] & gex[w] & ley[w] & gey[w]) : 0u;
+        u32 cand = sane ? (lex[w] & gex[w] & ley[w] & gey[w] & szw[w] & szh[w]) : 0u;
         if (w == gi) cand &= (1u << (i & 31)) - 1u;
         u32 bits = 0u;
         while (cand) {
@@ -830,7 +863,7 @@ static size_t nms_smem_bytes(int sortn, int top_k) {
   const int mcap = (top_k + 31) & ~31, W = mcap / 32, RL = (4 * W) | 1;
   const size_t tab = (size_t)kSlabs * RL > 512 ? (size_t)kSlabs * RL : 512;   // hist + bstart, then the join tables
   return (size_t)sortn * 8 + (size_t)mcap * (16 + 4 + 4 + 4) + (size_t)16 * W * (W + 1) * 4 + 2 * W * 4 +
-         (4 + 4 * kNmsWarps) * 4 + 16 + tab * 4 + 128;
+         (8 + 4 * kNmsWarps) * 4 + 16 + tab * 4 + (size_t)kSizeCls * ((2 * W) | 1) * 4 + 128;
 }
 
 struct DetectWs {
