@@ -446,31 +446,41 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // sortn keys take part in the sort; only the first mcap = top_k rounded up to 32 boxes exist afterwards
   const int sortn = P.sortn, mcap = (P.top_k + 31) & ~31, W = mcap >> 5, RL = (4 * W) | 1;
+  const int RS = (2 * W) | 1;
+  const int tabn = (max(512, kSlabs * RL) + kSizeCls * RS + 3) & ~3;   // words, whole uint4s
   u64* keys = reinterpret_cast<u64*>(smem_raw);                 // [sortn]
   float4* crn = reinterpret_cast<float4*>(keys + sortn);        // [mcap] x1,y1,x2,y2 (sort scratch: sortn keys)
-  float* qlo = reinterpret_cast<float*>(crn + mcap);            // [mcap] q*area*0.9999
-  float* area = qlo + mcap;                                     // [mcap]
-  u32* slidx = reinterpret_cast<u32*>(area + mcap);             // [mcap] slab interval ax | bx<<8 | ay<<16 | by<<24
-  u32* sup = slidx + mcap;                                      // lower triangle, [group g][word w <= g][row of the group]
-  u32* keptw = sup + (size_t)16 * W * (W + 1);                  // [W]
-  u32* remw = keptw + W;                                        // [W]
-  float* dom = reinterpret_cast<float*>(remw + W);              // [8 + 4*kNmsWarps] slab domain, log2 of its extents
-  u32* mm = reinterpret_cast<u32*>(dom + 8 + 4 * kNmsWarps);    // [4] min/max of the score and prior words
-  u32* hist = mm + 4;                                           // [256] sort / select histogram
+  u32* hist = reinterpret_cast<u32*>(crn + mcap);               // [256] sort / select histogram
   u32* bstart = hist + 256;                                     // [256] rank sort: first slot of each bucket
   u32* tab = hist;                                              // [kSlabs][RL] interval tables of the join (after the sort)
-  const int RS = (2 * W) | 1;
   u32* stab = tab + max(512, kSlabs * RL);                      // [kSizeCls][RS] width / height class neighbourhoods
+  float* qlo = reinterpret_cast<float*>(tab + tabn);            // [mcap] q*area*0.9999
+  float* area = qlo + mcap;                                     // [mcap]
+  u32* slidx = reinterpret_cast<u32*>(area + mcap);             // [mcap] slab intervals and size classes of the box
+  u32* sup = slidx + mcap;                                      // lower triangle, [group g][word w <= g][row of the group]
+  u32* unres = sup + (size_t)16 * W * (W + 1);                  // [mcap] rows the join could not keep at once
+  float* dom = reinterpret_cast<float*>(unres + mcap);          // [4*kNmsWarps] per-warp extents of the boxes
+  u32* mm = reinterpret_cast<u32*>(dom + 4 * kNmsWarps);        // [4*kNmsWarps] per-warp min/max of the score and prior words
+  u32* keptw = mm + 4 * kNmsWarps;                              // [W]
+  u32* remw = keptw + W;                                        // [W]
+  __shared__ int n_unres;
   __shared__ u64 sel_prefix;
   __shared__ int sel_k, sel_fill;
 
   const size_t list = blockIdx.x;
   const int b = (int)(blockIdx.x / (u32)P.n_fg);
   int n = (int)P.cls_cnt[list];
+  const bool selected = n > P.sortn;   // more candidates than the sort takes: radix select first
   const u64* cl = P.sorted + (size_t)b * P.img_stride + P.cls_off[list];
 
+  u32 hmin = ~0u, hmax = 0u, lmin = ~0u, lmax = 0u;   // range of the score and prior words of the keys
   if (n <= sortn) {
-    for (int i = tid; i < n; i += kNmsThreads) keys[i] = cl[i];
+    for (int i = tid; i < n; i += kNmsThreads) {
+      const u64 v = cl[i];
+      keys[i] = v;
+      hmin = min(hmin, (u32)(v >> 32)); hmax = max(hmax, (u32)(v >> 32));
+      lmin = min(lmin, (u32)v); lmax = max(lmax, (u32)v);
+    }
   } else {
     // Radix select of the top_k-th largest composite key (keys are unique), 8 bits per pass.
     if (tid == 0) { sel_prefix = 0ull; sel_k = P.top_k; sel_fill = 0; }
@@ -513,22 +523,30 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
   // the scores are pathologically clustered (then the count loop gets long, the result stays exact).
   {
     u64* tmp = reinterpret_cast<u64*>(crn);   // [n] keys grouped by bucket; crn is filled after the sort
-    if (tid < 4) mm[tid] = (tid & 1) ? 0u : ~0u;
     for (int i = tid; i < 256; i += kNmsThreads) hist[i] = 0u;
-    __syncthreads();
-    u32 hmin = ~0u, hmax = 0u, lmin = ~0u, lmax = 0u;
-    for (int i = tid; i < n; i += kNmsThreads) {
-      const u64 v = keys[i];
-      hmin = min(hmin, (u32)(v >> 32)); hmax = max(hmax, (u32)(v >> 32));
-      lmin = min(lmin, (u32)v); lmax = max(lmax, (u32)v);
+    if (selected) {   // the keys came out of the select: scan them
+      for (int i = tid; i < n; i += kNmsThreads) {
+        const u64 v = keys[i];
+        hmin = min(hmin, (u32)(v >> 32)); hmax = max(hmax, (u32)(v >> 32));
+        lmin = min(lmin, (u32)v); lmax = max(lmax, (u32)v);
+      }
     }
     hmin = __reduce_min_sync(SSDG_FULL, hmin); hmax = __reduce_max_sync(SSDG_FULL, hmax);
     lmin = __reduce_min_sync(SSDG_FULL, lmin); lmax = __reduce_max_sync(SSDG_FULL, lmax);
-    if (lane == 0) { atomicMin(&mm[0], hmin); atomicMax(&mm[1], hmax); atomicMin(&mm[2], lmin); atomicMax(&mm[3], lmax); }
+    if (lane == 0) { mm[4 * warp] = hmin; mm[4 * warp + 1] = hmax; mm[4 * warp + 2] = lmin; mm[4 * warp + 3] = lmax; }
     __syncthreads();
-    const bool byscore = mm[1] > mm[0];
-    const u32 kbase = byscore ? mm[0] : mm[2];
-    const float kscale = 256.f / ((float)((byscore ? mm[1] : mm[3]) - kbase) + 1.f);
+    {
+      const uint4 p0 = reinterpret_cast<const uint4*>(mm)[0];
+      hmin = p0.x; hmax = p0.y; lmin = p0.z; lmax = p0.w;
+#pragma unroll
+      for (int w = 1; w < kNmsWarps; ++w) {
+        const uint4 pw = reinterpret_cast<const uint4*>(mm)[w];
+        hmin = min(hmin, pw.x); hmax = max(hmax, pw.y); lmin = min(lmin, pw.z); lmax = max(lmax, pw.w);
+      }
+    }
+    const bool byscore = hmax > hmin;
+    const u32 kbase = byscore ? hmin : lmin;
+    const float kscale = 256.f / ((float)((byscore ? hmax : lmax) - kbase) + 1.f);
     auto bucket = [&](u64 v) {   // conversions, the product and the truncation are all monotone
       const u32 x = (byscore ? (u32)(v >> 32) : (u32)v) - kbase;
       return min(255, (int)((float)x * kscale));
@@ -575,6 +593,10 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
   const float thr = P.iou_thresh;
   const bool fast_ok = thr > 0.f && thr < 1e6f;
   const float q = fast_ok ? thr / (1.f + thr) : 0.f;
+  // The same pass collects what the join needs: the extents of all sane boxes (slab domain) and whether every
+  // box's corner extents reproduce its area to 0.1% (always, unless a box is a few ulps wide).
+  int inexact = 0;
+  u32 k1 = ~0u, k2 = ~0u, k3 = 0u, k4 = 0u;
   for (int i = tid; i < mpad; i += kNmsThreads) {
     float4 cr = make_float4(0.f, 0.f, 0.f, 0.f);
     float ar = 0.f, qa = CUDART_INF_F;
@@ -586,59 +608,48 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
       ar = __fmul_rn(bx.z, bx.w);
       const bool sane = bx.z > 0.f && bx.w > 0.f && isfinite(cr.x) && isfinite(cr.y) && isfinite(cr.z) &&
                         isfinite(cr.w) && isfinite(ar);
-      if (sane) qa = q * (ar + 0.5e-10f);
+      if (sane) {
+        qa = q * (ar + 0.5e-10f);
+        const float pr = (cr.z - cr.x) * (cr.w - cr.y);
+        inexact |= !(ar >= 0.999f * pr && ar <= 1.001f * pr);
+        k1 = min(k1, key32(cr.x)); k2 = min(k2, key32(cr.y)); k3 = max(k3, key32(cr.z)); k4 = max(k4, key32(cr.w));
+      }
     }
     crn[i] = cr;
     area[i] = ar;
     qlo[i] = qa * 0.9999f;
   }
+  k1 = __reduce_min_sync(SSDG_FULL, k1); k2 = __reduce_min_sync(SSDG_FULL, k2);
+  k3 = __reduce_max_sync(SSDG_FULL, k3); k4 = __reduce_max_sync(SSDG_FULL, k4);
+  if (lane == 0) reinterpret_cast<float4*>(dom)[warp] = make_float4(unkey32(k1), unkey32(k2), unkey32(k3), unkey32(k4));
   for (int i = tid; i < W; i += kNmsThreads) { keptw[i] = 0u; remw[i] = 0u; }
-  __syncthreads();
+  if (tid == 0) n_unres = 0;
+  // the sort is done with hist / bstart: the join tables take their place
+  for (int i = tid; i < (tabn >> 2); i += kNmsThreads) reinterpret_cast<uint4*>(tab)[i] = make_uint4(0u, 0u, 0u, 0u);
+  inexact = __syncthreads_or(inexact);
 
-  // Suppression bits, lower triangle: sup[i][w] bit l  <=>  iou(box_{32w+l}, box_i) > thresh, 32w+l < i.
+  // Suppression bits, lower triangle: sup(i, w) bit l  <=>  iou(box_{32w+l}, box_i) > thresh, 32w+l < i.
   if (fast_ok) {
     // Slab join.  iou(i, j) > thr means inter > q (area_i + area_j) with q = thr / (1 + thr); the y overlap is
     // at most min(h_i, h_j), so the x overlap exceeds q (w_i + w_j): the x extents of i and j, each SHRUNK by
-    // q times its width at both ends, still meet (and the same in y).  Every box registers its shrunk extents
-    // in 32 slabs per axis (one bitset per slab); row i ORs the bitsets of the slabs its own shrunk extents
-    // touch, and only the boxes found in both axes -- a few percent of all pairs -- get the overlap test.
-    // The bound is stated in the formula's areas w*h; it carries over to the corner extents when every box's
-    // extents reproduce its area to 0.1% (always, unless a box is a few ulps wide) -- else nothing is shrunk.
-    int inexact = 0;
+    // q times its width at both ends, still meet (and the same in y).  Every box gets the interval of slabs (32
+    // per axis) its shrunk extents touch; only the pairs whose intervals meet in both axes -- a few percent of
+    // all pairs -- get the overlap test.  The bound is stated in the formula's areas w*h; it carries over to
+    // the corner extents unless `inexact` -- then nothing is shrunk.
+    float dx0, dy0, dsx, dsy, lwx, lwy;
     {
-      u32 k1 = ~0u, k2 = ~0u, k3 = 0u, k4 = 0u;
-      for (int i = tid; i < m; i += kNmsThreads) {
-        if (isfinite(qlo[i])) {
-          const float4 c = crn[i];
-          const float pr = (c.z - c.x) * (c.w - c.y);
-          inexact |= !(area[i] >= 0.999f * pr && area[i] <= 1.001f * pr);
-          k1 = min(k1, key32(c.x)); k2 = min(k2, key32(c.y)); k3 = max(k3, key32(c.z)); k4 = max(k4, key32(c.w));
-        }
+      float4 e = reinterpret_cast<const float4*>(dom)[0];
+#pragma unroll
+      for (int w = 1; w < kNmsWarps; ++w) {
+        const float4 f = reinterpret_cast<const float4*>(dom)[w];
+        e.x = fminf(e.x, f.x); e.y = fminf(e.y, f.y); e.z = fmaxf(e.z, f.z); e.w = fmaxf(e.w, f.w);
       }
-      k1 = __reduce_min_sync(SSDG_FULL, k1); k2 = __reduce_min_sync(SSDG_FULL, k2);
-      k3 = __reduce_max_sync(SSDG_FULL, k3); k4 = __reduce_max_sync(SSDG_FULL, k4);
-      if (lane == 0) {
-        dom[8 + 4 * warp + 0] = unkey32(k1); dom[8 + 4 * warp + 1] = unkey32(k2);
-        dom[8 + 4 * warp + 2] = unkey32(k3); dom[8 + 4 * warp + 3] = unkey32(k4);
-      }
-      for (int i = tid; i < kSlabs * RL; i += kNmsThreads) tab[i] = 0u;   // the sort is done with hist / bstart
-      for (int i = tid; i < kSizeCls * RS; i += kNmsThreads) stab[i] = 0u;
-      inexact = __syncthreads_or(inexact);
-      if (tid == 0) {
-        float x1 = CUDART_INF_F, y1 = CUDART_INF_F, x2 = -CUDART_INF_F, y2 = -CUDART_INF_F;
-        for (int w = 0; w < kNmsWarps; ++w) {
-          x1 = fminf(x1, dom[8 + 4 * w]); y1 = fminf(y1, dom[9 + 4 * w]);
-          x2 = fmaxf(x2, dom[10 + 4 * w]); y2 = fmaxf(y2, dom[11 + 4 * w]);
-        }
-        dom[0] = x1; dom[1] = y1;
-        dom[2] = (x2 > x1) ? (float)kSlabs / (x2 - x1) : 0.f;
-        dom[3] = (y2 > y1) ? (float)kSlabs / (y2 - y1) : 0.f;
-        dom[4] = (x2 > x1) ? __log2f(x2 - x1) : 0.f;
-        dom[5] = (y2 > y1) ? __log2f(y2 - y1) : 0.f;
-      }
-      __syncthreads();
+      dx0 = e.x; dy0 = e.y;
+      dsx = (e.z > e.x) ? (float)kSlabs / (e.z - e.x) : 0.f;
+      dsy = (e.w > e.y) ? (float)kSlabs / (e.w - e.y) : 0.f;
+      lwx = (e.z > e.x) ? __log2f(e.z - e.x) : 0.f;
+      lwy = (e.w > e.y) ? __log2f(e.w - e.y) : 0.f;
     }
-    const float dx0 = dom[0], dy0 = dom[1], dsx = dom[2], dsy = dom[3];
     auto slab = [&](float v, float o, float sc) {   // monotone in v
       const float f = (v - o) * sc;
       return f >= (float)(kSlabs - 1) ? kSlabs - 1 : (f > 0.f ? (int)f : 0);
@@ -658,7 +669,6 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
     // registers in its class; the neighbourhood {c-1, c, c+1} is ORed below; the query ANDs both dimensions.
     const float tp = 0.99f * thr / (1.f + 0.001f * thr);
     const float inv_l = (!inexact && tp < 0.98f) ? -1.f / __log2f(tp) : 0.f;
-    const float lwx = dom[4], lwy = dom[5];
     auto size_cls = [&](float ext, float lref) {   // monotone in ext, clamped (clamping only merges classes)
       const float f = (lref - __log2f(ext)) * inv_l;
       return f >= (float)(kSizeCls - 1) ? kSizeCls - 1 : (f > 0.f ? (int)f : 0);
@@ -741,16 +751,19 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
         sup[16 * gi * (gi + 1) + (w << 5) + lane] = bits;
         any |= bits;
       };
-      if (W <= 8) {   // the usual top_k <= 256: word offsets become immediates
-#pragma unroll
-        for (int w = 0; w < 8; ++w)
-          if (w <= gi) word(w);
-      } else {
-        for (int w = 0; w <= gi; ++w) word(w);
-      }
-      // rows nobody suppresses are kept at once; the fixed point below only resolves the others
+      // (a rolled loop: unrolling the words into immediates offsets measured 7% slower -- instruction cache)
+#pragma unroll 1
+      for (int w = 0; w <= gi; ++w) word(w);
+      // rows nobody suppresses are kept at once; the others are listed for the resolution below
       const u32 free_rows = __ballot_sync(SSDG_FULL, live && any == 0u);
+      const u32 open_rows = __ballot_sync(SSDG_FULL, live && any != 0u);
       if (lane == 0) keptw[gi] = free_rows;
+      if (open_rows) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&n_unres, __popc(open_rows));
+        base = __shfl_sync(SSDG_FULL, base, 0);
+        if (live && any != 0u) unres[base + __popc(open_rows & ((1u << lane) - 1u))] = (u32)i;
+      }
     }
   } else {
   // No division-free test for this threshold: all pairs, the formula itself.
@@ -794,32 +807,36 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
     }
     sup[16 * g * (g + 1) + (w << 5) + lane] = bits;
   }
+  for (int i = tid; i < m; i += kNmsThreads) unres[i] = (u32)i;
+  if (tid == 0) n_unres = m;
   }
   __syncthreads();
 
   // fixed point of  kept(i) <=> no kept j < i with sup(i, j);  removed(i) <=> some kept j < i with sup(i, j)
-  for (;;) {
-    int unknown = 0;
-    for (int i = tid; i < m; i += kNmsThreads) {
-      const u32 bit = 1u << (i & 31);
-      if ((keptw[i >> 5] | remw[i >> 5]) & bit) continue;
-      bool hit_kept = false, all_removed = true;
-      const int sbase = 16 * (i >> 5) * ((i >> 5) + 1) + (i & 31);
-      for (int w = 0; w <= (i >> 5); ++w) {
-        const u32 sb = sup[sbase + (w << 5)];
-        if (sb & keptw[w]) hit_kept = true;
-        if (sb & ~remw[w]) all_removed = false;
-      }
-      if (hit_kept) atomicOr(&remw[i >> 5], bit);
-      else if (all_removed) atomicOr(&keptw[i >> 5], bit);
-      else unknown = 1;
-    }
-    if (!__syncthreads_or(unknown)) break;
-  }
-  __syncthreads();
-
-  // kept priors in visit order; hist[w] = kept boxes before word w
+  // over the listed rows, by one warp (a handful of rows per list: no CTA-wide barrier per round); then
+  // hist[w] = kept boxes before word w for the output
   if (warp == 0) {
+    const int nu = n_unres;
+    for (;;) {
+      bool unknown = false;
+      for (int k = lane; k < nu; k += 32) {
+        const int i = (int)unres[k], gi = i >> 5;
+        const u32 bit = 1u << (i & 31);
+        if ((keptw[gi] | remw[gi]) & bit) continue;
+        bool hit_kept = false, all_removed = true;
+        const int sbase = 16 * gi * (gi + 1) + (i & 31);
+        for (int w = 0; w <= gi; ++w) {
+          const u32 sb = sup[sbase + (w << 5)];
+          if (sb & keptw[w]) hit_kept = true;
+          if (sb & ~remw[w]) all_removed = false;
+        }
+        if (hit_kept) atomicOr(&remw[gi], bit);
+        else if (all_removed) atomicOr(&keptw[gi], bit);
+        else unknown = true;
+      }
+      __syncwarp();
+      if (!__any_sync(SSDG_FULL, unknown)) break;
+    }
     const int c = lane < W ? __popc(keptw[lane]) : 0;
     int incl = c;
 #pragma unroll
@@ -863,7 +880,7 @@ static size_t nms_smem_bytes(int sortn, int top_k) {
   const int mcap = (top_k + 31) & ~31, W = mcap / 32, RL = (4 * W) | 1;
   const size_t tab = (size_t)kSlabs * RL > 512 ? (size_t)kSlabs * RL : 512;   // hist + bstart, then the join tables
   return (size_t)sortn * 8 + (size_t)mcap * (16 + 4 + 4 + 4) + (size_t)16 * W * (W + 1) * 4 + 2 * W * 4 +
-         (8 + 4 * kNmsWarps) * 4 + 16 + tab * 4 + (size_t)kSizeCls * ((2 * W) | 1) * 4 + 128;
+         (size_t)mcap * 4 + 8 * kNmsWarps * 4 + tab * 4 + (size_t)kSizeCls * ((2 * W) | 1) * 4 + 16 + 128;
 }
 
 struct DetectWs {
