@@ -441,6 +441,9 @@ struct NmsParams {
   float* out_score;
 };
 
+// The NMS kernel is instruction-cache sensitive (12 CTAs per SM in different phases): its block-stride loops
+// stay rolled (3280 -> 2240 SASS instructions, 7% faster).
+#define NMS_LOOP _Pragma("unroll 1")
 __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -475,6 +478,7 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
 
   u32 hmin = ~0u, hmax = 0u, lmin = ~0u, lmax = 0u;   // range of the score and prior words of the keys
   if (n <= sortn) {
+    NMS_LOOP
     for (int i = tid; i < n; i += kNmsThreads) {
       const u64 v = cl[i];
       keys[i] = v;
@@ -486,10 +490,12 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
     if (tid == 0) { sel_prefix = 0ull; sel_k = P.top_k; sel_fill = 0; }
     __syncthreads();
     for (int shift = 56; shift >= 0; shift -= 8) {
+      NMS_LOOP
       for (int i = tid; i < 256; i += kNmsThreads) hist[i] = 0u;
       __syncthreads();
       const u64 pre = sel_prefix;
       const u64 hmask = shift == 56 ? 0ull : (~0ull << (shift + 8));
+      NMS_LOOP
       for (int i = tid; i < n; i += kNmsThreads) {
         const u64 v = cl[i];
         if ((v & hmask) == pre) atomicAdd(&hist[(u32)(v >> shift) & 255u], 1u);
@@ -507,6 +513,7 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
       __syncthreads();
     }
     const u64 kth = sel_prefix;
+    NMS_LOOP
     for (int i = tid; i < n; i += kNmsThreads) {
       const u64 v = cl[i];
       if (v >= kth) {
@@ -523,8 +530,10 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
   // the scores are pathologically clustered (then the count loop gets long, the result stays exact).
   {
     u64* tmp = reinterpret_cast<u64*>(crn);   // [n] keys grouped by bucket; crn is filled after the sort
+    NMS_LOOP
     for (int i = tid; i < 256; i += kNmsThreads) hist[i] = 0u;
     if (selected) {   // the keys came out of the select: scan them
+      NMS_LOOP
       for (int i = tid; i < n; i += kNmsThreads) {
         const u64 v = keys[i];
         hmin = min(hmin, (u32)(v >> 32)); hmax = max(hmax, (u32)(v >> 32));
@@ -551,6 +560,7 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
       const u32 x = (byscore ? (u32)(v >> 32) : (u32)v) - kbase;
       return min(255, (int)((float)x * kscale));
     };
+    NMS_LOOP
     for (int i = tid; i < n; i += kNmsThreads) atomicAdd(&hist[bucket(keys[i])], 1u);
     __syncthreads();
     if (warp == 0) {   // start[b] = number of keys in buckets above b; lane l owns buckets 255-8l .. 248-8l
@@ -568,11 +578,13 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
       for (int r = 0; r < 8; ++r) { bstart[255 - 8 * lane - r] = run; hist[255 - 8 * lane - r] = run; run += c[r]; }
     }
     __syncthreads();
+    NMS_LOOP
     for (int i = tid; i < n; i += kNmsThreads) {
       const u64 v = keys[i];
       tmp[atomicAdd(&hist[bucket(v)], 1u)] = v;   // hist[b] ends as the end of bucket b
     }
     __syncthreads();
+    NMS_LOOP
     for (int i = tid; i < n; i += kNmsThreads) {
       const u64 v = tmp[i];
       const int bk = bucket(v);
@@ -597,6 +609,7 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
   // box's corner extents reproduce its area to 0.1% (always, unless a box is a few ulps wide).
   int inexact = 0;
   u32 k1 = ~0u, k2 = ~0u, k3 = 0u, k4 = 0u;
+  NMS_LOOP
   for (int i = tid; i < mpad; i += kNmsThreads) {
     float4 cr = make_float4(0.f, 0.f, 0.f, 0.f);
     float ar = 0.f, qa = CUDART_INF_F;
@@ -622,9 +635,11 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
   k1 = __reduce_min_sync(SSDG_FULL, k1); k2 = __reduce_min_sync(SSDG_FULL, k2);
   k3 = __reduce_max_sync(SSDG_FULL, k3); k4 = __reduce_max_sync(SSDG_FULL, k4);
   if (lane == 0) reinterpret_cast<float4*>(dom)[warp] = make_float4(unkey32(k1), unkey32(k2), unkey32(k3), unkey32(k4));
+  NMS_LOOP
   for (int i = tid; i < W; i += kNmsThreads) { keptw[i] = 0u; remw[i] = 0u; }
   if (tid == 0) n_unres = 0;
   // the sort is done with hist / bstart: the join tables take their place
+  NMS_LOOP
   for (int i = tid; i < (tabn >> 2); i += kNmsThreads) reinterpret_cast<uint4*>(tab)[i] = make_uint4(0u, 0u, 0u, 0u);
   inexact = __syncthreads_or(inexact);
 
@@ -673,6 +688,7 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
       const float f = (lref - __log2f(ext)) * inv_l;
       return f >= (float)(kSizeCls - 1) ? kSizeCls - 1 : (f > 0.f ? (int)f : 0);
     };
+    NMS_LOOP
     for (int i = tid; i < m; i += kNmsThreads) {
       if (!isfinite(qlo[i])) { slidx[i] = 0u; continue; }
       const float4 c = crn[i];
@@ -692,6 +708,7 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
       atomicOr(&stab[ch * RS + W + wi], bit);
     }
     __syncthreads();
+    NMS_LOOP
     for (int col = tid; col < 6 * W; col += kNmsThreads) {
       if (col < 4 * W) {
         const bool up = ((col / W) & 1) == 0;   // LE: ascending running OR, GE: descending
@@ -714,6 +731,7 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
       }
     }
     __syncthreads();
+    NMS_LOOP
     for (int i = tid; i < mpad; i += kNmsThreads) {   // whole warps: rows 32g .. 32g+31
       const int gi = i >> 5;
       const bool live = i < m;
@@ -807,6 +825,7 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
     }
     sup[16 * g * (g + 1) + (w << 5) + lane] = bits;
   }
+  NMS_LOOP
   for (int i = tid; i < m; i += kNmsThreads) unres[i] = (u32)i;
   if (tid == 0) n_unres = m;
   }
@@ -855,6 +874,7 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
     ok[i] = -1;
     if (os) os[i] = 0.f;
   }
+  NMS_LOOP
   for (int i = tid; i < m; i += kNmsThreads) {
     const u32 kw = keptw[i >> 5], bit = 1u << (i & 31);
     if (kw & bit) {
