@@ -44,6 +44,12 @@ class HotPath:
         self.s_n, self.s_l = D.Stream("low"), D.Stream("high")
         self.ev_begin, self.ev_a, self.ev_d, self.ev_mid, self.ev_m = (D.Event() for _ in range(5))
         self.split = True
+        # the post-processing chain can run in `detect_parts` slices of the batch: the NMS of a slice then overlaps
+        # the filter pass of the next one (kernels bound by different resources) instead of waiting for the whole
+        # batch.  SSDGEOM_DETECT_PARTS overrides for measurements.
+        import os
+        self.detect_parts = max(1, min(int(os.environ.get("SSDGEOM_DETECT_PARTS", "1")), self.batch))
+        self.ev_parts = [D.Event() for _ in range(self.detect_parts)]
         # one pass over the logits serves both branches: the filter leaves per-prior softmax statistics and the
         # loss gathers from them instead of streaming the 724 MB again (only in the chained step)
         self.fused = True
@@ -60,7 +66,8 @@ class HotPath:
                 raise ValueError("global mining needs allreduce and global_priors")
             self.staged = ops.StagedLoss(self.tgt["cls"], self.tgt["loc"], self.tgt["mask"], self.pred_box, self.pred_cls,
                                          int(global_priors), self.neg_ratio, out=self.loss)
-        self.kernel_launches_per_step = 9   # search, match | lossprep (or ce), select x2, final | filter, bucket, nms
+        # search, match | lossprep (or ce), select x2, final | filter, bucket, nms per slice of the post-processing
+        self.kernel_launches_per_step = 6 + 3 * self.detect_parts
         self.h2d_bytes = (self.gt_boxes.nbytes + self.gt_cls.nbytes + self.gt_off.nbytes + self.pred_cls.nbytes +
                           self.pred_box.nbytes)
         self.d2h_bytes = self.loss["result"].nbytes + self.det["kept"].nbytes + self.det["count"].nbytes
@@ -87,10 +94,23 @@ class HotPath:
         ops.multibox_loss(self.tgt["cls"], self.tgt["loc"], self.tgt["mask"], self.pred_box, self.pred_cls,
                           self.neg_ratio, out=self.loss, stream=stream)
 
-    def detect_stage(self, stream, stage=None, stats=False):
+    def detect_stage(self, stream, stage=None, stats=False, part=None):
         out = dict(self.det, **self.det_stats) if stats else self.det
-        ops.detect(self.pred_cls, self.pred_box, self.priors, self.score_thresh, self.top_k, self.iou_thresh,
-                   out=out, stream=stream, stage=stage, want_row_stats=stats)
+        if part is None:
+            ops.detect(self.pred_cls, self.pred_box, self.priors, self.score_thresh, self.top_k, self.iou_thresh,
+                       out=out, stream=stream, stage=stage, want_row_stats=stats)
+            return
+        # images [lo, hi) of the batch, with a workspace of their own
+        lo = self.batch * part // self.detect_parts
+        hi = self.batch * (part + 1) // self.detect_parts
+
+        def rows(x):
+            per = x.nbytes // self.batch
+            return D.DeviceArray((hi - lo,) + x.shape[1:], x.dtype, ptr=x.ptr + lo * per, owner=x)
+
+        ops.detect(rows(self.pred_cls), rows(self.pred_box), self.priors, self.score_thresh, self.top_k,
+                   self.iou_thresh, out={k: rows(v) for k, v in out.items()}, stream=stream, stage=stage,
+                   want_row_stats=stats, ws_key="detect%d" % part)
 
     def step(self):
         """One pass of the chain over the resident batch; work is ordered on ``s_main``.
@@ -104,12 +124,17 @@ class HotPath:
         D.stream_wait_event(self.s_d, self.ev_begin)
         fused = self.fused
         if self.split:
-            self.detect_stage(self.s_d, stage=0, stats=fused)
+            parts = self.detect_parts
+            for part in range(parts):
+                self.detect_stage(self.s_d, stage=0, stats=fused, part=part if parts > 1 else None)
+                self.ev_parts[part].record(self.s_d)
+                if part == 0:
+                    self.assign(self.s_a)
+                    self.ev_m.record(self.s_a)
             self.ev_mid.record(self.s_d)
-            self.assign(self.s_a)
-            self.ev_m.record(self.s_a)
-            D.stream_wait_event(self.s_n, self.ev_mid)
-            self.detect_stage(self.s_n, stage=1, stats=fused)
+            for part in range(parts):
+                D.stream_wait_event(self.s_n, self.ev_parts[part])
+                self.detect_stage(self.s_n, stage=1, stats=fused, part=part if parts > 1 else None)
             D.stream_wait_event(self.s_l, self.ev_m)
             if fused:
                 D.stream_wait_event(self.s_l, self.ev_mid)
