@@ -219,21 +219,9 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
     const float2 ax = aux[r];
     return (kWrite ? *p : exp2_ftz(fmaf(*p, SSDG_LOG2E, ax.x))) * ax.y;
   };
-  auto exact = [&](u32 rb, int c) {   // keeps the rows whose score passes; without kWrite the score replaces the logit
-    u32 keep = 0u;
-    while (rb) {
-      const int r = __ffs(rb) - 1;
-      rb &= rb - 1;
-      float* p = tile + r * C + c;
-      const float sc = score_at(p, r);
-      if (sc > thr) {
-        keep |= 1u << r;
-        if (!kProbs && !kWrite) *p = sc;
-      }
-    }
-    return keep;
-  };
-  t0 = exact(t0, lane); t1 = exact(t1, 32 + lane); t2 = exact(t2, 64 + lane);
+  // One loop per class word tests and appends: the segment position of a lane comes from its number of
+  // PRE-FILTER hits, and the rare hit whose exact score fails (the pre-filter keeps a 0.1% margin) leaves a
+  // hole -- an entry of the class one past the last, which the bucketing pass drops.
   int extra = 0;   // classes beyond 96 (row phase layout): counted here, emitted below
   if (valid)
     for (int c = 96; c < nfg; ++c) extra += ((kProbs ? row[c] : row[c] * inv_s) > thr) ? 1 : 0;
@@ -251,10 +239,10 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
     while (rb) {
       const int r = __ffs(rb) - 1;
       rb &= rb - 1;
-      float* p = tile + r * C + c;
-      const float score = (kProbs || !kWrite) ? *p : *p * aux[r].y;
+      const float score = score_at(tile + r * C + c, r);
       const u32 sk = kProbs ? key32(score) : (__float_as_uint(score) | 0x80000000u);   // softmax scores are >= +0
-      *dst++ = ((u64)sk << 32) | (u64)(((u32)c << kABitsD) | (u32)(j * 32 + r));
+      const u32 cls = score > thr ? (u32)c : (u32)nfg;
+      *dst++ = ((u64)sk << 32) | (u64)((cls << kABitsD) | (u32)(j * 32 + r));
     }
   };
   emit(t0, lane); emit(t1, 32 + lane); emit(t2, 64 + lane);
@@ -347,10 +335,11 @@ __global__ void __launch_bounds__(kBucketThreads, 2) bucket_kernel(DetectParams 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nfg = P.C - 1, tpi = P.tpi, b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  u32* hist = reinterpret_cast<u32*>(smem_raw);   // [nfg]
-  u32* off = hist + nfg;                          // [nfg]
-  u32* tpre = off + nfg;                          // [tpi + 1] exclusive prefix of the tile counts
-  for (int c = tid; c < nfg; c += kBucketThreads) hist[c] = 0u;
+  const int nb = nfg;                             // entries of class nfg are the holes of the filter pass: dropped
+  u32* hist = reinterpret_cast<u32*>(smem_raw);   // [nb]
+  u32* off = hist + nb;                           // [nb]
+  u32* tpre = off + nb;                          // [tpi + 1] exclusive prefix of the tile counts
+  for (int c = tid; c < nb; c += kBucketThreads) hist[c] = 0u;
   const u32* tcnt = P.tile_cnt + (size_t)b * tpi;
   const size_t tstride = (size_t)32 * nfg;
   const u64* seg = P.seg + (size_t)b * tpi * tstride;
@@ -371,47 +360,52 @@ __global__ void __launch_bounds__(kBucketThreads, 2) bucket_kernel(DetectParams 
     if (lane == 0) tpre[tpi] = running;
   }
   __syncthreads();
-  // Each warp takes four tiles at a time: the first 64 entries of each (all of them, for trained-like
-  // scores) are loaded up front, so eight independent loads per lane are in flight.
+  // Each warp takes four tiles at a time: the first 96 entries of each (all of them, for trained-like scores:
+  // ~60 candidates + ~15 holes per tile) are loaded up front, so twelve independent loads per lane are in flight.
   constexpr int kBW = kBucketThreads / 32;
+  constexpr int kUp = 3;
   auto for_tiles = [&](auto&& visit) {
     for (int j0 = warp * 4; j0 < tpi; j0 += kBW * 4) {
-      u64 v[4][2];
+      u64 v[4][kUp];
       int cnt[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int j = j0 + q;
         cnt[q] = j < tpi ? (int)(tpre[j + 1] - tpre[j]) : 0;
         const u64* sp = seg + (size_t)j * tstride;
-        v[q][0] = lane < cnt[q] ? sp[lane] : 0ull;
-        v[q][1] = lane + 32 < cnt[q] ? sp[lane + 32] : 0ull;
+#pragma unroll
+        for (int u = 0; u < kUp; ++u) v[q][u] = lane + 32 * u < cnt[q] ? sp[lane + 32 * u] : 0ull;
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        if (lane < cnt[q]) visit(v[q][0]);
-        if (lane + 32 < cnt[q]) visit(v[q][1]);
-        if (cnt[q] > 64) {
+#pragma unroll
+        for (int u = 0; u < kUp; ++u)
+          if (lane + 32 * u < cnt[q]) visit(v[q][u]);
+        if (cnt[q] > 32 * kUp) {
           const u64* sp = seg + (size_t)(j0 + q) * tstride;
-          for (int e = lane + 64; e < cnt[q]; e += 32) visit(sp[e]);
+          for (int e = lane + 32 * kUp; e < cnt[q]; e += 32) visit(sp[e]);
         }
       }
     }
   };
-  for_tiles([&](u64 v) { atomicAdd(&hist[(u32)v >> kABitsD], 1u); });
+  for_tiles([&](u64 v) {
+    const u32 c = (u32)v >> kABitsD;
+    if (c < (u32)nfg) atomicAdd(&hist[c], 1u);
+  });
   __syncthreads();
   if (warp == 0) {
     u32 running = 0u;
-    for (int c0 = 0; c0 < nfg; c0 += 32) {
+    for (int c0 = 0; c0 < nb; c0 += 32) {
       const int c = c0 + lane;
-      const u32 cnt = c < nfg ? hist[c] : 0u;
+      const u32 cnt = c < nb ? hist[c] : 0u;
       u32 incl = cnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const u32 v = __shfl_up_sync(SSDG_FULL, incl, o);
         if (lane >= o) incl += v;
       }
+      if (c < nb) off[c] = running + incl - cnt;
       if (c < nfg) {
-        off[c] = running + incl - cnt;
         P.cls_cnt[(size_t)b * nfg + c] = cnt;
         P.cls_off[(size_t)b * nfg + c] = running + incl - cnt;
       }
@@ -422,6 +416,7 @@ __global__ void __launch_bounds__(kBucketThreads, 2) bucket_kernel(DetectParams 
   u64* out = P.sorted + (size_t)b * tpi * tstride;
   for_tiles([&](u64 v) {
     const u32 low = (u32)v;
+    if ((low >> kABitsD) >= (u32)nfg) return;
     const u32 pos = atomicAdd(&off[low >> kABitsD], 1u);
     out[pos] = (v & 0xffffffff00000000ull) | (u64)(~(low & ((1u << kABitsD) - 1u)));
   });
@@ -953,7 +948,7 @@ static int run_filter(DetectParams& P, int prior_dtype, cudaStream_t st) {
   SSDG_LAUNCH_CHECK();
   SSDG_CUDA_TRY(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   {
-    const size_t bsm = ((size_t)2 * (P.C - 1) + P.tpi + 1) * 4;
+    const size_t bsm = ((size_t)2 * P.C + P.tpi + 1) * 4;
     if ((int)bsm > max_smem_optin()) return SSDG_ERR_LIMIT;
     if (bsm > 48 * 1024)
       SSDG_CUDA_TRY(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
