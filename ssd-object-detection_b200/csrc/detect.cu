@@ -196,7 +196,10 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
       }
       inv_s = __frcp_rn(s0 + s1);
       if (P.row_ml) {   // the loss of the same predictions reuses this pass instead of streaming the logits again
-        const float lg = logf(s0 + s1);
+        // every e_c carries the common factor 2^d, d = ref*log2e + kexp (the rounding of kexp; exact in one FMA):
+        // it cancels in e/sum, the logarithm takes it out explicitly
+        const float d = fmaf(ref, SSDG_LOG2E, kexp);
+        const float lg = fmaf(-d, 0.693147180559945f, logf(s0 + s1));
         P.row_ml[n] = make_float2(ref, lg);
         P.row_negbg[n] = lg - (xbg - ref);
       }

@@ -620,6 +620,53 @@ def test_detect_full_batch_properties(priors300):
     assert np.array_equal(np.concatenate([k1, h2["kept"].to_host()]), kept)
 
 
+def _check_detect_streaming(pred_cls, pred_box, priors, **kw):
+    """The streaming variant of the filter (no probabilities output: the rows are not overwritten, the exponent
+    reference is the background logit with an exact fallback) against the float64 oracle: kept scores within
+    tolerance, the lists equal wherever no score sits within rounding of the threshold / of a neighbour."""
+    out = ops.detect(pred_cls, pred_box, priors, want_scores=True, want_row_stats=True, **kw)
+    kept, count, score = out["kept"].to_host(), out["count"].to_host(), out["kept_score"].to_host()
+    row_ml, negbg = out["row_ml"].to_host().astype(np.float64), out["row_negbg"].to_host().astype(np.float64)
+    equal = lists = 0
+    for i in range(pred_cls.shape[0]):
+        w_kept, w_count, w_probs, _ = O.detect(pred_cls[i], pred_box[i], priors, **kw)
+        for c in range(kept.shape[1]):
+            k = kept[i, c, :count[i, c]]
+            close(score[i, c, :count[i, c]], w_probs[k, c], rtol=RTOL, atol=1e-9)
+            assert np.all(score[i, c, :count[i, c]] > kw["score_thresh"]) and np.all(np.diff(score[i, c, :count[i, c]]) <= 0)
+        lists += kept.shape[1]
+        equal += int(np.sum(np.all(kept[i] == w_kept, axis=1)))
+        # the loss's by-product: log-sum-exp = reference + log sum, background CE
+        x = pred_cls[i].astype(np.float64)
+        lse = np.log(np.sum(np.exp(x - x.max(axis=1, keepdims=True)), axis=1)) + x.max(axis=1)
+        close(row_ml[i, :, 0] + row_ml[i, :, 1], lse, rtol=RTOL, atol=2e-6)
+        close(negbg[i], lse - x[:, -1], rtol=RTOL, atol=2e-6)
+    return equal, lists
+
+
+def test_detect_streaming_background_reference_and_fallback(priors300):
+    kw = dict(score_thresh=0.01, top_k=200, iou_thresh=0.45)
+    # trained-like rows: the background logit is the reference of nearly every row (one pass)
+    pred_cls, pred_box = synth.make_predictions(51, 2, 8732, bg_bias=7.0)
+    eq, lists = _check_detect_streaming(pred_cls, pred_box, priors300, **kw)
+    assert eq >= lists - 2
+    # wide logits: foreground far above the background (sum > 2^16, overflow of the float exponent) -> the rows
+    # are redone with their maximum; background far above everything -> sums of exactly 1
+    rng = np.random.default_rng(52)
+    wide = (rng.standard_normal((2, 8732, 81)) * 12.0).astype(np.float32)
+    wide[0, ::7, 3] += 90.0
+    wide[1, ::5, -1] += 120.0
+    wide[1, 1::5, -1] -= 150.0
+    # (saturated scores tie within rounding by the hundred here: the kept scores and the row statistics are
+    # checked against the oracle, list equality is not meaningful)
+    _check_detect_streaming(wide, pred_box, priors300, **kw)
+    # both filter variants agree on what they keep
+    plain = ops.detect(pred_cls, pred_box, priors300, **kw)
+    full = ops.detect(pred_cls, pred_box, priors300, want_probs=True, **kw)
+    same = np.all(plain["kept"].to_host() == full["kept"].to_host(), axis=2)
+    assert same.sum() >= same.size - 2
+
+
 def test_loss_from_filter_row_statistics(priors300):
     """The chained step's single pass over the logits: the softmax filter leaves per-prior (max, log-sum) and the
     background CE, and ssdg_multibox_loss_fused must give the loss of the standalone path -- per-prior CE within
