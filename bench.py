@@ -301,6 +301,7 @@ def run_ours(args):
     ev0.record(hp.s_main)
     for _ in range(args.steps):
         full_step()
+    hp.finish_exchange()          # the last step's loss exchange belongs to the timed region
     ev1.record(hp.s_main)
     hp.s_main.sync()
     barrier()
