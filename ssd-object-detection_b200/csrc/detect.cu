@@ -4,18 +4,22 @@
 //
 //   filter_kernel  one streaming pass over the logits [B,A,C].  Tiles are 32 priors of ONE image; each
 //                  of the 16 warps of a CTA owns one shared-memory tile filled by 1-D bulk TMA
-//                  (cp.async.bulk + mbarrier); lane r owns row r (stride C words: conflict-free for odd
-//                  C).  exp(x - max) is written back into the row while summing, with a one-bit-per-class
-//                  pre-filter; the exact scores exp(x-max)*(1/sum) > score_thresh of the few surviving
-//                  classes are then appended, lane after lane (one warp scan), to the tile's private
-//                  segment of the candidate buffer.  No atomics, one count word per tile.
+//                  (cp.async.bulk + mbarrier).  Row phase, lane r owns row r (stride C words: conflict-free
+//                  for odd C): e_c = 2^((x_c - ref) log2e) with the background logit as reference (one pass;
+//                  rows that would overflow or lose precision are redone with their maximum), the sum, one
+//                  pre-filter bit per class.  Class phase, after a warp transpose of the bit matrices lane l
+//                  owns classes l, 32+l, 64+l: exact score e_c * (1/sum) > score_thresh and append to the
+//                  tile's private segment of the candidate buffer in one loop (failures leave holes).  No
+//                  atomics, one count word per tile.  Optionally leaves per-prior (ref, log sum) and the
+//                  background CE for the loss, the probabilities, and the reference's score head.
 //   bucket_kernel  one CTA per image: counting sort of the image's candidates by class (shared-memory
-//                  histogram, scan, scatter) into contiguous per-class lists.
-//   nms_kernel     one CTA per (image, class): exact top-k by (score desc, prior asc) -- radix select when
-//                  the list is longer than the sort width, then a bitonic sort (register shuffles for the
-//                  short strides) -- the lower-triangle suppression bit matrix built by 32x32 tasks in
-//                  registers (cheap float test with a margin, the exact IEEE formula for the survivors),
-//                  and a parallel fixed-point resolution of "kept(i) <=> no kept j < i suppresses i".
+//                  histogram, scan, scatter) into contiguous per-class lists; drops the holes.
+//   nms_kernel     one CTA per (image, class): exact top-k by (score desc, prior asc) -- radix select when the
+//                  list is longer than the sort width, then a bucketed rank sort; the lower-triangle
+//                  suppression bits from an interval join (cumulative slab bitsets per axis + width / height
+//                  class neighbourhoods, cheap float test with a margin, the exact IEEE formula for the
+//                  survivors); rows without suppressors are kept by ballot, the rest resolved by one warp
+//                  iterating "kept(i) <=> no kept j < i suppresses i" to its fixed point.
 #include <math_constants.h>
 #include <type_traits>
 #include "common.cuh"
