@@ -135,7 +135,7 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
   if (!kProbs && valid && P.boxes) tbox = __ldg(reinterpret_cast<const float4*>(P.pred_box) + n);  // early: hide latency
   float inv_s = 1.f, kexp = 0.f;
   // first 96 classes as bit words in registers; more classes fall back to re-testing every class
-  const float pre = kProbs ? thr : thr * 0.999f;
+  float pre = kProbs ? thr : thr * 0.999f;
   u32 bits0 = 0u, bits1 = 0u, bits2 = 0u;
   if (valid) {
     if (!kProbs) {
@@ -187,10 +187,21 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
           return bits;
         };
         const std::integral_constant<int, 32> w32;
+        // p_c > thr needs e_c > thr * sum, and the sum is at least what has been added so far: the pre-filter of
+        // the later words tightens with the partial sum, which leaves fewer holes for the class phase
+        const float pre0 = pre;
+        if (nfg <= 96) {   // the background first: it opens the partial sum (e = 1 when it is the reference)
+          const float eb = exp2_ftz(fmaf(xbg, SSDG_LOG2E, kexp));
+          if (two_pass) row[C - 1] = eb;
+          s0 = eb;
+        }
         bits0 = nfg >= 32 ? chunkN(0, w32) : chunk(0, nfg);
+        pre = fmaxf(pre0, pre0 * (s0 + s1));
         if (nfg > 32) bits1 = nfg >= 64 ? chunkN(32, w32) : chunk(32, nfg - 32);
+        pre = fmaxf(pre0, pre0 * (s0 + s1));
         if (nfg > 64) bits2 = nfg >= 96 ? chunkN(64, w32) : chunk(64, nfg - 64);
-        for (int c = min(nfg, 96); c < C; ++c) {   // background and the classes beyond 96
+        pre = pre0;
+        for (int c = nfg > 96 ? 96 : C; c < C; ++c) {   // the classes beyond 96 and their background
           const float e0 = exp2_ftz(fmaf(row[c], SSDG_LOG2E, kexp));
           if (two_pass) row[c] = e0;
           s0 += e0;
