@@ -378,10 +378,10 @@ __global__ void __launch_bounds__(kBucketThreads, 2) bucket_kernel(DetectParams 
     if (lane == 0) tpre[tpi] = running;
   }
   __syncthreads();
-  // Each warp takes four tiles at a time: the first 96 entries of each (all of them, for trained-like scores:
-  // ~60 candidates + ~15 holes per tile) are loaded up front, so twelve independent loads per lane are in flight.
+  // Each warp takes four tiles at a time: the first 128 entries of each (nearly all of them, for trained-like scores:
+  // ~57 candidates + ~34 holes per tile) are loaded up front, so sixteen independent loads per lane are in flight.
   constexpr int kBW = kBucketThreads / 32;
-  constexpr int kUp = 3;
+  constexpr int kUp = 4;
   auto for_tiles = [&](auto&& visit) {
     for (int j0 = warp * 4; j0 < tpi; j0 += kBW * 4) {
       u64 v[4][kUp];
