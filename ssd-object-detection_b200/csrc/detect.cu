@@ -186,7 +186,6 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
           }
           return bits;
         };
-        const std::integral_constant<int, 32> w32;
         // p_c > thr needs e_c > thr * sum, and the sum is at least what has been added so far: the pre-filter of
         // the later words tightens with the partial sum, which leaves fewer holes for the class phase
         const float pre0 = pre;
@@ -195,11 +194,27 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
           if (two_pass) row[C - 1] = eb;
           s0 = eb;
         }
-        bits0 = nfg >= 32 ? chunkN(0, w32) : chunk(0, nfg);
-        pre = fmaxf(pre0, pre0 * (s0 + s1));
-        if (nfg > 32) bits1 = nfg >= 64 ? chunkN(32, w32) : chunk(32, nfg - 32);
-        pre = fmaxf(pre0, pre0 * (s0 + s1));
-        if (nfg > 64) bits2 = nfg >= 96 ? chunkN(64, w32) : chunk(64, nfg - 64);
+#ifndef SSDG_FILTER_PRE_STEP
+#define SSDG_FILTER_PRE_STEP 16
+#endif
+        constexpr int kPs = SSDG_FILTER_PRE_STEP;   // classes between two updates of the bound
+        auto word32 = [&](int c0) {
+          u32 bits = 0u;
+#pragma unroll
+          for (int o = 0; o < 32; o += kPs) {
+            bits |= chunkN(c0 + o, std::integral_constant<int, kPs>()) << o;
+            pre = fmaxf(pre0, pre0 * (s0 + s1));
+          }
+          return bits;
+        };
+        auto tail = [&](int c0, int cn) {
+          const u32 bits = chunk(c0, cn);
+          pre = fmaxf(pre0, pre0 * (s0 + s1));
+          return bits;
+        };
+        bits0 = nfg >= 32 ? word32(0) : tail(0, nfg);
+        if (nfg > 32) bits1 = nfg >= 64 ? word32(32) : tail(32, nfg - 32);
+        if (nfg > 64) bits2 = nfg >= 96 ? word32(64) : tail(64, nfg - 64);
         pre = pre0;
         for (int c = nfg > 96 ? 96 : C; c < C; ++c) {   // the classes beyond 96 and their background
           const float e0 = exp2_ftz(fmaf(row[c], SSDG_LOG2E, kexp));
