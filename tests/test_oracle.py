@@ -238,3 +238,88 @@ def test_input_glue_golden(golden_dir):
         assert got.dtype == np.float32 and np.array_equal(got, g["rel"][off[i]:off[i + 1]])
     x = np.linspace(-1, 2, 101, dtype=np.float32)
     assert np.array_equal(O.normalize_image(x), (x - np.float32(0.5)) * np.float32(2))
+
+
+# ---- the pruning rules of the CUDA kernels, restated in float32 NumPy: necessary conditions only -------------
+def _nms_join_candidates(boxes, thr):
+    """The candidate pairs nms_kernel's interval join keeps (detect.cu: shrunk-extent slab intervals per axis plus
+    width / height class neighbourhoods), restated with the kernel's float32 arithmetic."""
+    f = np.float32
+    b = boxes.astype(f)
+    hw, hh = b[:, 2] * f(0.5), b[:, 3] * f(0.5)
+    x1, y1, x2, y2 = b[:, 0] - hw, b[:, 1] - hh, b[:, 0] + hw, b[:, 1] + hh
+    area = b[:, 2] * b[:, 3]
+    q = f(thr) / (f(1) + f(thr))
+    pr = (x2 - x1) * (y2 - y1)
+    inexact = bool(np.any(~((area >= f(0.999) * pr) & (area <= f(1.001) * pr))))
+    tq = f(0) if inexact else min(f(0.98) * q, f(0.49))
+    nslab = 32
+
+    def slab(v, o, sc):
+        return np.clip(np.nan_to_num((v - o) * sc, nan=0.0), 0, nslab - 1).astype(np.int64)
+
+    dx0, dy0 = x1.min(), y1.min()
+    dsx = f(nslab) / (x2.max() - dx0) if x2.max() > dx0 else f(0)
+    dsy = f(nslab) / (y2.max() - dy0) if y2.max() > dy0 else f(0)
+    sx = tq * (x2 - x1) - f(1e-6) * (np.abs(x1) + np.abs(x2))
+    sy = tq * (y2 - y1) - f(1e-6) * (np.abs(y1) + np.abs(y2))
+    ax, bx = slab(x1 + sx, dx0, dsx), None
+    bx = np.maximum(slab(x2 - sx, dx0, dsx), ax)
+    ay = slab(y1 + sy, dy0, dsy)
+    by = np.maximum(slab(y2 - sy, dy0, dsy), ay)
+    tp = f(0.99) * f(thr) / (f(1) + f(0.001) * f(thr))
+    if (not inexact) and tp < f(0.98):
+        inv_l = f(-1) / np.log2(tp)
+        lwx = np.log2(x2.max() - dx0) if x2.max() > dx0 else f(0)
+        lwy = np.log2(y2.max() - dy0) if y2.max() > dy0 else f(0)
+        cw = np.clip((lwx - np.log2(x2 - x1)) * inv_l, 0, 15).astype(np.int64)
+        ch = np.clip((lwy - np.log2(y2 - y1)) * inv_l, 0, 15).astype(np.int64)
+    else:
+        cw = ch = np.zeros(len(b), np.int64)
+    i, j = np.tril_indices(len(b), -1)
+    keep = ((ax[j] <= bx[i]) & (bx[j] >= ax[i]) & (ay[j] <= by[i]) & (by[j] >= ay[i]) &
+            (np.abs(cw[i] - cw[j]) <= 1) & (np.abs(ch[i] - ch[j]) <= 1))
+    return i, j, keep
+
+
+@pytest.mark.parametrize("thr", [0.05, 0.3, 0.45, 0.6, 0.9])
+def test_nms_join_never_drops_a_suppressing_pair(thr):
+    """Every pair the formula (utils/bbox.py:13-25, float32) puts above the threshold survives the join."""
+    rng = np.random.default_rng(int(thr * 100))
+    for scale in (0.05, 0.3, 1.0):
+        n = 200
+        c = rng.uniform(0, 1, (n, 2))
+        wh = np.exp(rng.uniform(np.log(0.01), np.log(0.9), (n, 2))) * scale
+        boxes = np.concatenate([c, wh], 1).astype(np.float32)
+        dup = boxes[1::9][:len(boxes[::9])].copy()                              # near duplicates: real suppression
+        dup[:, 2:] *= np.float32(1.01)
+        boxes[::9] = dup
+        i, j, keep = _nms_join_candidates(boxes, thr)
+        iou = O.iou(boxes[i], boxes[j])
+        hot = iou > np.float32(thr)
+        assert hot.sum() > 0
+        assert not np.any(hot & ~keep)
+        assert keep.sum() < 0.5 * len(i)                                        # and it does prune
+
+
+def test_filter_partial_sum_prefilter_is_necessary():
+    """filter_kernel's pre-filter: with the background as exponent reference and the bound refreshed every 16 classes
+    from the partial sum, e_c > 0.999 thr * max(1, partial) never rejects a class whose softmax score exceeds thr."""
+    f = np.float32
+    for bias, seed in ((7.0, 0), (0.0, 1), (3.0, 2)):
+        x, _ = synth.make_predictions(seed, 1, 4096, 81, bg_bias=bias)
+        x = x[0]
+        p = O.softmax(x)
+        e = np.exp2((x - x[:, -1:]) * f(1.4426950408889634)).astype(f)
+        part = e[:, -1].copy()                                                  # the background opens the sum
+        passed = np.zeros((x.shape[0], 80), bool)
+        pre0 = f(0.01) * f(0.999)
+        pre = np.full(x.shape[0], pre0, f)
+        for c0 in range(0, 80, 16):
+            blk = e[:, c0:c0 + 16]
+            passed[:, c0:c0 + 16] = blk > pre[:, None]
+            part = part + blk.sum(1, dtype=f)
+            pre = np.maximum(pre0, pre0 * part)
+        must = p[:, :80] > 0.01 * (1 + 1e-5)
+        assert not np.any(must & ~passed)
+        assert passed.sum() < 2.2 * max(must.sum(), 1) or bias == 0.0
