@@ -743,6 +743,20 @@ def test_generalised_anchor_options(priors300):
     close(dec[m1[0]], bbox.decode_bbox(l0[0], priors300, scale=300.0)[m0[0]], rtol=1e-4, atol=1e-4)   # round trip
 
 
+def test_ssd512_loss_and_detect(priors512):
+    """BASELINE config 4's table (SSD512, 24 564 priors, 768 tiles -- more than the SSD300 index): the loss and the
+    post-processing against the oracle on a small batch (the assignment is covered by test_assign_random_bit_exact)."""
+    batch = 2
+    boxes, cls, off = synth.make_gt(81, batch, 100, "coco")
+    y_true = _targets(boxes, cls, off, priors512, batch)
+    pred_cls, pred_box = synth.make_predictions(81, batch, priors512.shape[0], bg_bias=7.0)
+    _check_loss(y_true, (pred_box, pred_cls))
+    eq, lists = _check_detect(pred_cls[:1], pred_box[:1], priors512, score_thresh=0.01, top_k=200, iou_thresh=0.45)
+    assert eq >= lists - 2
+    eq, lists = _check_detect_streaming(pred_cls[:1], pred_box[:1], priors512, score_thresh=0.01, top_k=200, iou_thresh=0.45)
+    assert eq >= lists - 2
+
+
 def test_chained_step_full_batch_equals_standalone_calls(priors300):
     """BASELINE size (SSD300, B=256): the chained HotPath.step -- four streams, one pass over the logits shared by
     the loss and the post-processing -- against the three standalone entry points on the same device buffers:
