@@ -14,7 +14,8 @@
  *  - The library never allocates device memory inside a compute entry point: the caller passes
  *    a workspace of at least ssdg_*_workspace_bytes() bytes (256-byte aligned).
  *  - Return value: 0 = OK; negative = argument error mirroring the reference's asserts
- *    (SSDG_ERR_*); positive = a cudaError_t.  Nothing throws across the boundary.
+ *    (SSDG_ERR_*); positive = a cudaError_t (or SSDG_ERR_NCCL_BASE + ncclResult_t from
+ *    ssdg_comm_*).  Nothing throws across the boundary.
  *  - Data-dependent errors that only the device can see (num_pos == 0, hard-negative k out of
  *    range) are reported through a status word in the result block, see each function.
  *  - There is no CPU fallback: without a CUDA device every compute entry point returns a
@@ -50,10 +51,18 @@ extern "C" {
 #define SSDG_ERR_ALIGN (-8)        /* a pointer that must be 16-byte aligned is not             */
 #define SSDG_ERR_LIMIT (-9)        /* size beyond an implementation limit (see function)        */
 #define SSDG_ERR_POS_NEG_OVERLAP (-10) /* a positive prior was mined as negative  models/ssd_model.py:375 */
+#define SSDG_ERR_NO_NCCL (-11)     /* ssdg_comm_*: libnccl.so.2 could not be loaded              */
+#define SSDG_ERR_LABEL_RANGE (-12) /* a positive prior's class id is outside [0, C) (TensorFlow's
+                                      sparse_softmax_cross_entropy_with_logits raises; :357)     */
+#define SSDG_ERR_STALE_INDEX (-13) /* the prior index does not belong to these priors (content check) */
+#define SSDG_ERR_NCCL_BASE 10000   /* ssdg_comm_*: SSDG_ERR_NCCL_BASE + ncclResult_t             */
 
 /* element types for the box arrays whose dtype decides the matcher's rounding */
 #define SSDG_F32 0
 #define SSDG_F64 1
+/* (ssdg_comm_allreduce_sum only) */
+#define SSDG_I32 2
+#define SSDG_I64 3
 
 SSDG_API const char* ssdg_status_string(int status);
 SSDG_API int ssdg_version(void);
@@ -61,6 +70,7 @@ SSDG_API int ssdg_version(void);
 /* ---- device / memory helpers (so host code needs no other CUDA binding) --------------------- */
 SSDG_API int ssdg_device_count(int* count);
 SSDG_API int ssdg_set_device(int device);
+SSDG_API int ssdg_get_device(int* device);
 SSDG_API int ssdg_device_alloc(void** dptr, size_t bytes);
 SSDG_API int ssdg_device_free(void* dptr);
 SSDG_API int ssdg_host_alloc(void** hptr, size_t bytes);           /* pinned */
@@ -79,10 +89,12 @@ SSDG_API int ssdg_stream_wait_event(void* stream, void* event);
 SSDG_API int ssdg_event_elapsed_ms(void* start, void* stop, float* ms); /* synchronises on `stop` */
 
 /* ---- per-kernel timing (for bench.py's roofline line) --------------------------------------------
- * When enabled, the three dominant kernels (SSDG_PROF_MATCH: match_kernel, SSDG_PROF_CE: ce_kernel,
- * SSDG_PROF_FILTER: filter_kernel, SSDG_PROF_NMS: nms_kernel) are bracketed by CUDA events on the
- * stream they are launched on.  ssdg_profile_last_ms synchronises on the kernel's stop event and
- * returns the duration of its most recent launch. */
+ * When enabled, the dominant kernels (SSDG_PROF_MATCH: search + match_kernel, SSDG_PROF_CE: ce_kernel or
+ * lossprep_kernel, SSDG_PROF_FILTER: filter_kernel, SSDG_PROF_NMS: nms_kernel, ...) are bracketed by CUDA
+ * events on the stream they are launched on.  ssdg_profile_last_ms synchronises on the kernel's stop event
+ * and returns the duration of its most recent launch on the CURRENT device.  A measurement aid: the switch is
+ * process-wide and the events are per device, so enable it only from a driver that launches from one thread
+ * per device (bench.py); it is off by default and compute entry points are otherwise free of global state. */
 #define SSDG_PROF_MATCH 0
 #define SSDG_PROF_CE 1
 #define SSDG_PROF_FILTER 2
@@ -90,11 +102,8 @@ SSDG_API int ssdg_event_elapsed_ms(void* start, void* stop, float* ms); /* synch
 #define SSDG_PROF_BUCKET 4      /* bucket_kernel */
 #define SSDG_PROF_SEARCH 5      /* search_kernel (SSDG_PROF_MATCH covers search + per-image kernel) */
 #define SSDG_PROF_LOSS_TAIL 6   /* select_kernel x2 + final_kernel */
+#define SSDG_PROF_GRAD 7        /* grad_kernel */
 SSDG_API int ssdg_profile_enable(int enable);
-/* Scheduling hook: when set (non-NULL), ssdg_detect / ssdg_nms record this cudaEvent_t on their stream right
- * after the HBM-bound filter + bucket kernels and before the ALU-bound nms_kernel, so a caller can start
- * latency-bound work (the matcher) on another stream exactly when it overlaps best.  NULL clears it. */
-SSDG_API int ssdg_detect_set_mid_event(void* event);
 SSDG_API int ssdg_profile_last_ms(int which, float* ms);
 /* Begin / end of the bracketed kernel relative to a caller-recorded event (ms): a timeline of one step. */
 SSDG_API int ssdg_profile_span_ms(int32_t which, void* ref_event, float* begin_ms, float* end_ms);
@@ -142,10 +151,15 @@ SSDG_API size_t ssdg_match_workspace_bytes(int32_t batch, int32_t n_priors, int3
  * spatially compact 32-prior tiles, plus per-tile statistics, so the matcher's tile-level IoU bound is
  * tight.  It changes no result.  ssdg_prior_index_build copies the priors to the host, sorts there and
  * SYNCHRONISES; call it once per prior set.  `index` is device memory of ssdg_prior_index_bytes bytes
- * (256-byte aligned) that must stay alive and unmodified while it is passed to ssdg_match_encode. */
+ * (256-byte aligned) that must stay alive and unmodified while it is passed to ssdg_match_encode, on the device
+ * it was built on.  The index remembers a content checksum of its priors: every ssdg_match_encode that is given
+ * an index re-derives it on the device and raises status bit 3 (ssdg_match_status) when the priors were changed
+ * afterwards (e.g. ssdg_priors_clip in place) or the index belongs to another array.  ssdg_prior_index_destroy
+ * forgets the index (call it before freeing or reusing the memory). */
 SSDG_API size_t ssdg_prior_index_bytes(int32_t n_priors);
 SSDG_API int ssdg_prior_index_build(const void* priors, int32_t prior_dtype, int32_t n_priors, void* index,
                            size_t index_bytes, void* stream);
+SSDG_API int ssdg_prior_index_destroy(void* index);
 SSDG_API int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const float* gt_cls,
                       const int32_t* gt_offsets, const void* priors, int32_t prior_dtype,
                       const void* prior_index /* NULL or from ssdg_prior_index_build for these priors */,
@@ -153,8 +167,10 @@ SSDG_API int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const flo
                       int32_t* out_cls, float* out_box, float* out_loc, uint8_t* out_mask,
                       int32_t* out_match, void* workspace, size_t workspace_bytes, void* stream);
 /* Synchronous: copies the status word of the last ssdg_match_encode on `workspace` to *status
- * (bit 0: some T > max_gt, bit 1: some T > A, bit 2: internal log overflow handled by rescan --
- * informational). */
+ * (bit 0: some T > max_gt, bit 1: some T > A -- those images were written as all-unmatched, where the reference
+ * matches every box / asserts utils/bbox.py:50; bit 2: internal log overflow handled by rescan -- informational;
+ * bit 3: the prior index does not belong to these priors -- results invalid).  The word is the second uint32 of
+ * the workspace: an asynchronous caller copies workspace[4..8) itself (ssdgeom/pipeline.py does, with the results). */
 SSDG_API int ssdg_match_status(const void* workspace, int32_t* status, void* stream);
 
 /* Stand-alone encode / decode over [batch, A, 4] boxes against shared priors.
@@ -182,10 +198,12 @@ SSDG_API int ssdg_iou_pairs(const void* boxes_1, int32_t dtype_1, const void* bo
  * out_result: double[SSDG_LOSS_RESULT_LEN] on the device:
  *   [0] total  [1] "cls loss pos"  [2] "cls loss neg"  [3] "loc loss"
  *   [4] num_pos [5] num_neg [6] mining threshold (k-th largest background CE)
- *   [7] status: 0 OK, SSDG_ERR_NO_POSITIVE, SSDG_ERR_TOPK_RANGE, SSDG_ERR_POS_NEG_OVERLAP
- *       (then [0..3] are NaN)
+ *   [7] status: 0 OK, SSDG_ERR_NO_POSITIVE, SSDG_ERR_TOPK_RANGE, SSDG_ERR_POS_NEG_OVERLAP,
+ *       SSDG_ERR_LABEL_RANGE (then [0..3] are NaN)
  *   [8] sum of positive CE [9] sum of mined-negative CE [10] sum of positive L1 (the separable
  *   sums a data-parallel caller all-reduces together with [4],[5]) [11] this shard's own positives
+ *   [12] data-dependent errors seen by this shard (positives mined as negatives + class ids out of
+ *        range): additive, so that every shard of a data-parallel run agrees on success
  * out_neg_mask (optional) uint8 [B,A]: the mined negative mask.
  * out_neg_ce   (optional) float [B,A]: per-prior background CE * (1-pos) (the mining input).
  * grad_box / grad_cls (optional, both or neither): d total / d pred_box, d total / d pred_cls --
@@ -206,7 +224,11 @@ SSDG_API int ssdg_multibox_loss(const int32_t* gt_cls, const float* gt_box, cons
  *   stage 0  CE pass                 then sum  exchange 3 (int64 x1: positives) and exchange 0 (int32 x2048)
  *   stage 1  radix level 1           then sum  exchange 1 (int32 x2048)
  *   stage 2  radix level 2           then sum  exchange 2 (int32 x2048)
- *   stage 3  mask, sums, result      then sum  out_result[8..11] and [5]:  loss = ([8] + [10]) / sum[11] + [9] / sum[5]
+ *   stage 3  mask, sums, result      then sum  out_result[8..12] and [5]:  loss = ([8] + [10]) / sum[11] + [9] / sum[5],
+ *                                              valid iff [7] == 0 and sum[12] == 0
+ *   stage 4  gradient (optional; needs grad_box / grad_cls) -- AFTER the stage-3 exchange: it reads the summed
+ *            num_neg [5] (and the global num_pos [4]), so the gradient of every shard is the slice of the
+ *            single-device gradient of the whole batch
  * Every stage takes the arguments of ssdg_multibox_loss (same buffers each time) plus global_priors =
  * sum over shards of batch * n_priors, and optionally (both or neither, else NULL) the per-prior softmax statistics
  * of ssdg_detect_stage so that stage 0 skips its own pass over the logits (see ssdg_multibox_loss_fused).  After stage 3 out_result[4] is the global positive count, [11] the
@@ -231,6 +253,28 @@ SSDG_API int ssdg_multibox_loss_fused(const float* row_ml, const float* row_negb
                        int32_t neg_ratio, double* out_result, uint8_t* out_neg_mask, float* out_neg_ce,
                        float* grad_box, float* grad_cls, void* workspace, size_t workspace_bytes,
                        void* stream);
+
+/* ---- data-parallel exchange ---------------------------------------------------
+ * The path shards by image (batch_data_iter is a per-image loop, models/ssd_model.py:211-215; NMS is per image
+ * and class), so the only cross-device step is the loss's: with per-shard mining -- what the reference does per
+ * slice under split_batch, models/ssd_model.py:235-256 -- the seven additive words out_result[4..10] are summed
+ * once per step; with exact batch-global mining (:368-372) the exchange buffers of ssdg_multibox_loss_stage.
+ * These entry points wrap NCCL (bound at run time from libnccl.so.2; SSDG_ERR_NO_NCCL if absent) so that a
+ * TensorFlow or plain C host needs no other collective library:
+ *   rank 0:  ssdg_comm_unique_id(id)  -> ship the SSDG_COMM_ID_BYTES bytes to every rank (any out-of-band channel)
+ *   all:     ssdg_comm_init_rank(&comm, id, world, rank)      (collective; uses the current device)
+ *   step:    ssdg_comm_allreduce_sum(comm, buf, count, dtype, stream)   in place, stream-ordered, asynchronous
+ *   end:     ssdg_comm_destroy(comm)
+ * ssdg_comm_allreduce_sum_multi sums n buffers as one NCCL group (one launch). */
+#define SSDG_COMM_ID_BYTES 128
+SSDG_API int ssdg_comm_available(int* nccl_version /* may be NULL */);
+SSDG_API int ssdg_comm_unique_id(void* id_out /* host, SSDG_COMM_ID_BYTES */);
+SSDG_API int ssdg_comm_init_rank(void** comm_out, const void* id /* host */, int32_t world, int32_t rank);
+SSDG_API int ssdg_comm_world(void* comm, int32_t* world, int32_t* rank);
+SSDG_API int ssdg_comm_allreduce_sum(void* comm, void* buf, int64_t count, int32_t dtype, void* stream);
+SSDG_API int ssdg_comm_allreduce_sum_multi(void* comm, int32_t n, void* const* bufs, const int64_t* counts,
+                                  const int32_t* dtypes, void* stream);
+SSDG_API int ssdg_comm_destroy(void* comm);
 
 /* ---- input glue ----------------------------------------------------------
  * ssdg_gt_prepare replaces, for a whole batch of annotation rows at once,

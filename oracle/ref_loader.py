@@ -1,13 +1,16 @@
 """TEST INFRASTRUCTURE ONLY -- import the *unmodified* reference source from
 ``/root/reference`` under the NumPy ``tensorflow`` shim (oracle/tf_shim.py).
 
-Only usable in the build container: ``/root/reference`` does not exist on the GPU
-box, so nothing reachable from ``pytest -m gpu``, ``smoke()`` or ``bench.py`` calls
-this.  It is used by
+``/root/reference`` exists only in the build container.  On the GPU box the same modules are imported from
+``oracle/_ref`` -- source-less ``.pyc`` files byte-compiled from ``/root/reference`` by ``oracle/build_ref.py``
+(git-ignored build artefacts that travel with the snapshot, like the built ``.so``).  It is used by
 
-* ``oracle/make_golden.py`` to generate ``tests/golden/*.npz`` and
+* ``oracle/make_golden.py`` to generate ``tests/golden/*.npz``,
 * ``tests/test_oracle_vs_reference.py`` (skipped when the reference is absent)
-  to pin ``oracle/ssd_oracle.py`` against the real thing.
+  to pin ``oracle/ssd_oracle.py`` against the real thing, and
+* ``bench.py``'s CPU legs (``--impl reference`` and ``cpu_baseline``), which time the reference's own
+  ``match_bbox`` / ``apply_anchor_box`` / ``_ssd_loss`` when either location is present
+  (``cpu_baseline.kind == "reference"``), else the NumPy port (``"port"``).
 
 Reference entry points exposed (file:line in /root/reference):
   utils/bbox.py:6    iou
@@ -26,10 +29,20 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("SSDGEOM_REFERENCE_ROOT", "/root/reference")
+COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def root() -> str | None:
+    """Where the reference's modules can be imported from: its source tree, else the byte-compiled copy."""
+    if os.path.isfile(os.path.join(REFERENCE_ROOT, "utils", "bbox.py")):
+        return REFERENCE_ROOT
+    if os.path.isfile(os.path.join(COMPILED_ROOT, "utils", "bbox.pyc")):
+        return COMPILED_ROOT
+    return None
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "utils", "bbox.py"))
+    return root() is not None
 
 
 _cache = {}
@@ -39,8 +52,9 @@ def load():
     """Return a namespace with the reference's hot-path callables."""
     if "ns" in _cache:
         return _cache["ns"]
-    if not available():
-        raise RuntimeError("reference source not present at %s" % REFERENCE_ROOT)
+    where = root()
+    if where is None:
+        raise RuntimeError("reference not present at %s nor byte-compiled under %s" % (REFERENCE_ROOT, COMPILED_ROOT))
     from . import tf_shim
 
     tf_shim.install()
@@ -49,12 +63,12 @@ def load():
     for name in list(sys.modules):
         if name.split(".")[0] in ("utils", "models", "data_loaders"):
             raise RuntimeError("a module named %r is already imported; cannot load the reference" % name)
-    sys.path.insert(0, REFERENCE_ROOT)
+    sys.path.insert(0, where)
     try:
         bbox = importlib.import_module("utils.bbox")
         ssd_model = importlib.import_module("models.ssd_model")
     finally:
-        sys.path.remove(REFERENCE_ROOT)
+        sys.path.remove(where)
     model_cls = ssd_model.SSDObjectDetectionModel
 
     def build_prior_box(size_list, input_size=300):
@@ -77,6 +91,7 @@ def load():
         ssd_loss=model_cls._ssd_loss,
         bbox_module=bbox,
         model_module=ssd_model,
+        root=where,
     )
     _cache["ns"] = ns
     return ns

@@ -84,6 +84,27 @@ def iou(box_a, box_b, dtype=np.float32):
     return inter / (a[..., 2] * a[..., 3] + b[..., 2] * b[..., 3] - inter + dtype(1e-10))
 
 
+def iou_all_pairs(boxes, dtype=np.float32):
+    """``iou`` (utils/bbox.py:6-25) of every pair of rows of ``boxes`` [..., m, 4] -> [..., m, m]: the same
+    element-wise operations in the same order and dtype -- the per-box terms (corners, areas) are evaluated
+    once per box instead of once per pair, which changes no bit (asserted in tests/test_oracle.py)."""
+    b = np.asarray(boxes, dtype=dtype)
+    two = dtype(2)
+    x1, y1 = b[..., 0] - b[..., 2] / two, b[..., 1] - b[..., 3] / two
+    x2, y2 = b[..., 0] + b[..., 2] / two, b[..., 1] + b[..., 3] / two
+    area = b[..., 2] * b[..., 3]
+    ex = np.minimum(x2[..., :, None], x2[..., None, :]) - np.maximum(x1[..., :, None], x1[..., None, :])
+    np.maximum(dtype(0), ex, out=ex)
+    ey = np.minimum(y2[..., :, None], y2[..., None, :]) - np.maximum(y1[..., :, None], y1[..., None, :])
+    np.maximum(dtype(0), ey, out=ey)
+    ex *= ey                                                              # inter
+    den = area[..., :, None] + area[..., None, :]
+    den -= ex
+    den += dtype(1e-10)
+    ex /= den
+    return ex
+
+
 def iou_matrix(gt_box, prior_box):
     """utils/bbox.py:28-41 (``iou_n``) applied to every (ground truth, prior) pair, i.e. what
     ``match_bbox`` builds at :53-58 with repeat/tile -- here by broadcasting, which performs the
@@ -375,11 +396,52 @@ def nms_per_class(probs, boxes, score_thresh=0.01, top_k=200, iou_thresh=0.45):
     return kept, counts
 
 
-def detect(pred_cls, pred_box, prior_box, score_thresh=0.01, top_k=200, iou_thresh=0.45):
+def nms_per_class_batched(probs, boxes, score_thresh=0.01, top_k=200, iou_thresh=0.45):
+    """Same result as ``nms_per_class`` (asserted in tests/test_oracle.py), vectorised over the classes
+    so that the CPU baseline of bench.py is not dominated by interpreter overhead: the visit lists of all
+    classes are padded to one [C-1, m] array, the ``iou`` formula (utils/bbox.py:13-25, float32, the very
+    same element-wise operations) is evaluated once for all [C-1, m, m] pairs, and the greedy visit runs
+    as m steps over all classes at once."""
+    probs = np.asarray(probs, dtype=np.float32)
+    boxes = np.asarray(boxes, dtype=np.float32)
+    n_fg = probs.shape[1] - 1
+    kept = np.full((n_fg, top_k), -1, dtype=np.int32)
+    counts = np.zeros((n_fg,), dtype=np.int32)
+    lists = []
+    for c in range(n_fg):
+        s = probs[:, c]
+        cand = np.nonzero(s > np.float32(score_thresh))[0]
+        if cand.size:
+            cand = cand[np.lexsort((cand, -s[cand].astype(np.float64)))][:top_k]
+        lists.append(cand)
+    m = max((l.size for l in lists), default=0)
+    if m == 0:
+        return kept, counts
+    idx = np.zeros((n_fg, m), dtype=np.int64)
+    live = np.zeros((n_fg, m), dtype=bool)
+    for c, l in enumerate(lists):
+        idx[c, :l.size] = l
+        live[c, :l.size] = True
+    b = boxes[idx]                                                     # [C-1, m, 4]
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        sup = iou_all_pairs(b) > np.float32(iou_thresh)                # [C-1, m(visited), m(later)]
+    alive = live.copy()
+    for i in range(m):
+        k = alive[:, i]                     # classes whose i-th candidate is kept
+        if i + 1 < m:
+            alive[:, i + 1:] &= ~(sup[:, i, i + 1:] & k[:, None])
+    for c in range(n_fg):
+        k = idx[c, alive[c]].astype(np.int32)
+        kept[c, :k.size] = k
+        counts[c] = k.size
+    return kept, counts
+
+
+def detect(pred_cls, pred_box, prior_box, score_thresh=0.01, top_k=200, iou_thresh=0.45, batched=True):
     """Decode (scale 1.0) + softmax + per-class NMS for one image."""
     probs = softmax(pred_cls)
     boxes = decode_bbox(pred_box, prior_box, scale=1.0, exp_dtype=np.float64)
-    kept, counts = nms_per_class(probs, boxes, score_thresh, top_k, iou_thresh)
+    kept, counts = (nms_per_class_batched if batched else nms_per_class)(probs, boxes, score_thresh, top_k, iou_thresh)
     return kept, counts, probs, boxes
 
 

@@ -8,7 +8,7 @@ b,c,o = synth.make_gt(100, 256, 100, "max")
 for it in range(3):
     out = ops.match_encode(b,c,o,pri,256,100,0.5)
     D.sync()
-ws = ops.POOL.get("match", 256)
+ws = out["_match_ws"]
 head = ws.view((64,), np.uint32).to_host()
 t = head[8:8+10].view(np.uint64)
 print("phase clocks per image (setup, search, phase2, greedy, output):", [int(x)//256 for x in t])

@@ -1,25 +1,44 @@
-"""Bucket an `ncu --page source --csv` export into contiguous SASS regions of similar execution count.
-usage: python profiles/sass_regions.py file.csv units_per_launch [min_share]"""
-import csv, sys
+"""Executed warp-instructions and stall samples of one kernel per SOURCE-LINE REGION (ncu source page joined with
+nvdisasm line info, like sass_by_source.py).
+usage: python profiles/sass_regions.py ncu_source.csv nvdisasm.txt kernel_substr units file name:lo-hi [name:lo-hi ...]"""
+import csv, re, sys, collections
 rows = list(csv.reader(open(sys.argv[1])))
-units = float(sys.argv[2]); min_share = float(sys.argv[3]) if len(sys.argv) > 3 else 0.01
+dis = open(sys.argv[2]).read().splitlines()
+kern, units, fname = sys.argv[3], float(sys.argv[4]), sys.argv[5]
+regions = []
+for a in sys.argv[6:]:
+    n, r = a.split(':'); lo, hi = r.split('-'); regions.append((n, int(lo), int(hi)))
 hdr = next(r for r in rows if 'Source' in r and '# Samples' in r)
 i_src, i_s, i_ex = hdr.index('Source'), hdr.index('# Samples'), hdr.index('Instructions Executed')
 data = [r for r in rows[rows.index(hdr) + 1:] if len(r) > max(i_src, i_s, i_ex) and r[i_s].isdigit()]
-# ncu lists every line twice in this export mode; keep the first copy
-half = len(data) // 2
-if half and all(data[i][i_src] == data[i + half][i_src] for i in range(0, half, max(1, half // 50))):
-    data = data[:half]
-tot = sum(int(r[i_ex]) for r in data) or 1; ts = sum(int(r[i_s]) for r in data) or 1
-print('sass lines', len(data), 'warp-instr', tot, 'per unit', round(tot / units, 1), 'samples', ts)
-reg, cur = [], None
-for idx, r in enumerate(data):
-    e, s = int(r[i_ex]), int(r[i_s])
-    if cur and abs(e - cur['e']) <= 0.25 * max(e, cur['e'], 1):
-        cur['n'] += 1; cur['sum'] += e; cur['s'] += s; cur['end'] = idx
+start = next(i for i, l in enumerate(dis) if l.startswith('.text.') and kern in l)
+seq, line = [], None
+for l in dis[start + 1:]:
+    if l.startswith('.text.') or l.startswith('.section'):
+        if seq:
+            break
+    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+    if m:
+        line = (m.group(1).split('/')[-1], int(m.group(2)))
+        continue
+    m = re.match(r'\s+/\*([0-9a-f]{4,})\*/\s+(.*?);', l)
+    if m:
+        seq.append((line, m.group(2).strip()))
+n = len(seq)
+agg = collections.Counter(); smp = collections.Counter(); nsass = collections.Counter()
+last = 'other'
+for (ln, _), r in zip(seq, data[:n]):
+    name = None
+    if ln and ln[0] == fname:
+        for rn, lo, hi in regions:
+            if lo <= ln[1] <= hi:
+                name = rn
+                break
+        last = name or 'other'
     else:
-        cur = {'start': idx, 'end': idx, 'e': e, 'n': 1, 'sum': e, 's': s}; reg.append(cur)
-for g in reg:
-    if g['sum'] > min_share * tot or g['s'] > min_share * ts:
-        print(f"lines {g['start']:5d}-{g['end']:5d} n={g['n']:4d} exec/line/unit={g['e']/units:8.2f} instr/unit={g['sum']/units:9.1f} "
-              f"share={100*g['sum']/tot:5.1f}% stall={100*g['s']/ts:5.1f}%  {data[g['start']][i_src][:50]}")
+        name = last          # inlined helpers (common.cuh, device headers) go to the region that called them
+    agg[name or 'other'] += int(r[i_ex]); smp[name or 'other'] += int(r[i_s]); nsass[name or 'other'] += 1
+tot = sum(agg.values()); ts = sum(smp.values()) or 1
+print('sass instructions', n, ' executed warp-instr per unit %.0f' % (tot / units))
+for rn in [r[0] for r in regions] + ['other']:
+    print(f"{rn:22s} {nsass[rn]:5d} sass {agg[rn]/units:9.1f} instr/unit {100*agg[rn]/tot:5.1f}%  stall samples {100*smp[rn]/ts:5.1f}%")

@@ -31,6 +31,7 @@ UNITS = {
     "glue.cu": ["-fmad=false"],
     "loss.cu": [],
     "detect.cu": [],
+    "comm.cu": [],
 }
 
 
@@ -72,7 +73,7 @@ def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % unit)
-    link = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o", LIB] + objs
+    link = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o", LIB] + objs + ["-ldl"]
     subprocess.run(link, check=True)
     with open(stamp_file, "w") as f:
         f.write(stamp)

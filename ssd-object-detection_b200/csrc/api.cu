@@ -27,51 +27,53 @@ int max_smem_optin() {
   }
   return g_smem_optin[d];
 }
-static cudaEvent_t g_mid_event = nullptr;
-cudaEvent_t detect_mid_event() { return g_mid_event; }
+// Optional event bracketing of the dominant kernels (ssdg_profile_enable): one set of events per device, created
+// on first use on that device; a measurement aid for single-threaded drivers (bench.py), off by default.
+constexpr int kProfSlots = 8;
 static bool g_prof = false;
-static cudaEvent_t g_prof_ev[8][2];
-static bool g_prof_have[8];
+static cudaEvent_t g_prof_ev[64][kProfSlots][2];
+static bool g_prof_have[64][kProfSlots];
 void prof_begin(int which, cudaStream_t st) {
   if (!g_prof) return;
-  if (!g_prof_have[which]) {
-    cudaEventCreate(&g_prof_ev[which][0]);
-    cudaEventCreate(&g_prof_ev[which][1]);
-    g_prof_have[which] = true;
+  const int d = cur_dev();
+  if (!g_prof_have[d][which]) {
+    cudaEventCreate(&g_prof_ev[d][which][0]);
+    cudaEventCreate(&g_prof_ev[d][which][1]);
+    g_prof_have[d][which] = true;
   }
-  cudaEventRecord(g_prof_ev[which][0], st);
+  cudaEventRecord(g_prof_ev[d][which][0], st);
 }
 void prof_end(int which, cudaStream_t st) {
-  if (!g_prof || !g_prof_have[which]) return;
-  cudaEventRecord(g_prof_ev[which][1], st);
+  if (!g_prof) return;
+  const int d = cur_dev();
+  if (!g_prof_have[d][which]) return;
+  cudaEventRecord(g_prof_ev[d][which][1], st);
 }
 }  // namespace ssdg
 
 extern "C" {
 
-int ssdg_detect_set_mid_event(void* event) {
-  ssdg::g_mid_event = (cudaEvent_t)event;
-  return SSDG_OK;
-}
 int ssdg_profile_enable(int enable) {
   ssdg::g_prof = enable != 0;
   return SSDG_OK;
 }
 int ssdg_profile_span_ms(int32_t which, void* ref_event, float* begin_ms, float* end_ms) {
-  if (which < 0 || which >= 8 || !ref_event || !begin_ms || !end_ms) return SSDG_ERR_ARG;
-  if (!ssdg::g_prof_have[which]) return SSDG_ERR_ARG;
-  cudaError_t e = cudaEventSynchronize(ssdg::g_prof_ev[which][1]);
+  if (which < 0 || which >= ssdg::kProfSlots || !ref_event || !begin_ms || !end_ms) return SSDG_ERR_ARG;
+  const int d = ssdg::cur_dev();
+  if (!ssdg::g_prof_have[d][which]) return SSDG_ERR_ARG;
+  cudaError_t e = cudaEventSynchronize(ssdg::g_prof_ev[d][which][1]);
   if (e != cudaSuccess) return (int)e;
-  e = cudaEventElapsedTime(begin_ms, (cudaEvent_t)ref_event, ssdg::g_prof_ev[which][0]);
+  e = cudaEventElapsedTime(begin_ms, (cudaEvent_t)ref_event, ssdg::g_prof_ev[d][which][0]);
   if (e != cudaSuccess) return (int)e;
-  return (int)cudaEventElapsedTime(end_ms, (cudaEvent_t)ref_event, ssdg::g_prof_ev[which][1]);
+  return (int)cudaEventElapsedTime(end_ms, (cudaEvent_t)ref_event, ssdg::g_prof_ev[d][which][1]);
 }
 int ssdg_profile_last_ms(int which, float* ms) {
-  if (which < 0 || which >= 8 || !ms) return SSDG_ERR_ARG;
-  if (!ssdg::g_prof_have[which]) { *ms = 0.f; return SSDG_ERR_ARG; }
-  cudaError_t e = cudaEventSynchronize(ssdg::g_prof_ev[which][1]);
+  if (which < 0 || which >= ssdg::kProfSlots || !ms) return SSDG_ERR_ARG;
+  const int d = ssdg::cur_dev();
+  if (!ssdg::g_prof_have[d][which]) { *ms = 0.f; return SSDG_ERR_ARG; }
+  cudaError_t e = cudaEventSynchronize(ssdg::g_prof_ev[d][which][1]);
   if (e != cudaSuccess) return (int)e;
-  return (int)cudaEventElapsedTime(ms, ssdg::g_prof_ev[which][0], ssdg::g_prof_ev[which][1]);
+  return (int)cudaEventElapsedTime(ms, ssdg::g_prof_ev[d][which][0], ssdg::g_prof_ev[d][which][1]);
 }
 
 const char* ssdg_status_string(int status) {
@@ -87,8 +89,12 @@ const char* ssdg_status_string(int status) {
     case SSDG_ERR_ALIGN: return "pointer not 16-byte aligned";
     case SSDG_ERR_LIMIT: return "size beyond an implementation limit";
     case SSDG_ERR_POS_NEG_OVERLAP: return "a positive prior was mined as a hard negative";
+    case SSDG_ERR_NO_NCCL: return "libnccl.so.2 could not be loaded (ssdg_comm_* needs NCCL)";
+    case SSDG_ERR_LABEL_RANGE: return "class id of a positive prior outside [0, n_classes)";
+    case SSDG_ERR_STALE_INDEX: return "the prior index was not built from these priors";
     default: break;
   }
+  if (status >= SSDG_ERR_NCCL_BASE) return ssdg::nccl_error_string(status - SSDG_ERR_NCCL_BASE);
   if (status > 0) return cudaGetErrorString((cudaError_t)status);
   return "unknown status";
 }
@@ -102,6 +108,10 @@ int ssdg_device_count(int* count) {
   return SSDG_OK;
 }
 int ssdg_set_device(int device) { return (int)cudaSetDevice(device); }
+int ssdg_get_device(int* device) {
+  if (!device) return SSDG_ERR_ARG;
+  return (int)cudaGetDevice(device);
+}
 int ssdg_device_alloc(void** dptr, size_t bytes) {
   if (!dptr) return SSDG_ERR_ARG;
   return (int)cudaMalloc(dptr, bytes ? bytes : 1);

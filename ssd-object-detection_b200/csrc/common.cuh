@@ -31,7 +31,7 @@ int max_smem_optin();    // cached max dynamic shared memory per block (opt-in)
 // Optional event bracketing of the dominant kernels (ssdg_profile_enable).
 void prof_begin(int which, cudaStream_t st);
 void prof_end(int which, cudaStream_t st);
-cudaEvent_t detect_mid_event();   // scheduling hook (ssdg_detect_set_mid_event), may be null
+const char* nccl_error_string(int nccl_result);   // comm.cu
 
 // ---------------------------------------------------------------------------------------------
 // Exactly-rounded arithmetic (never contracted into FMA, whatever the compiler flags).

@@ -990,7 +990,6 @@ static int run_filter(DetectParams& P, int prior_dtype, cudaStream_t st) {
     prof_end(SSDG_PROF_BUCKET, st);
   }
   SSDG_LAUNCH_CHECK();
-  if (detect_mid_event()) SSDG_CUDA_TRY(cudaEventRecord(detect_mid_event(), st));
   return SSDG_OK;
 }
 

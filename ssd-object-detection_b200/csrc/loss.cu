@@ -30,7 +30,7 @@ struct LossWs {
   u32 fcount[1024][2];      // per-CTA: neg count, pos&neg overlap count
   u32 hist[3][kBins];       // the three radix levels
   u32 ticket[4];            // last-block-done counters
-  u32 nparts[4];            // grid sizes used
+  u32 nparts[4];            // [0] grid size of the CE pass, [1] positives whose class id is outside [0, C)
   unsigned long long xnpos; // number of positives as an integer: the exchange word of the cross-shard mining
   unsigned long long xpad;
 };
@@ -103,7 +103,10 @@ __device__ __forceinline__ void ce_one_prior(const LossParams& P, long long n, c
   float neg = 0.f;
   if (pos) {
     int lab = P.gt_cls[n];
-    lab = lab < 0 ? 0 : (lab >= C ? C - 1 : lab);
+    if (lab < 0 || lab >= C) {   // TensorFlow raises here (models/ssd_model.py:357): flagged through the status word
+      atomicAdd(&P.ws->nparts[1], 1u);
+      lab = lab < 0 ? 0 : C - 1;
+    }
     acc.pos_ce += lg - (row[lab] - m);
     const float4 pb = __ldg(reinterpret_cast<const float4*>(P.pred_box) + n);
     const float4 gb = __ldg(reinterpret_cast<const float4*>(P.gt_box) + n);
@@ -210,7 +213,10 @@ __global__ void __launch_bounds__(256) lossprep_kernel(LossParams P) {
   auto one = [&](long long n, bool pos, float negbg) -> float {
     if (!pos) return negbg;
     int lab = P.gt_cls[n];
-    lab = lab < 0 ? 0 : (lab >= C ? C - 1 : lab);
+    if (lab < 0 || lab >= C) {   // as in ce_one_prior
+      atomicAdd(&P.ws->nparts[1], 1u);
+      lab = lab < 0 ? 0 : C - 1;
+    }
     const float2 ml = P.row_ml[n];
     acc.pos_ce += ml.y - (__ldg(P.pred_cls + (size_t)n * C + lab) - ml.x);
     const float4 pb = __ldg(reinterpret_cast<const float4*>(P.pred_box) + n);
@@ -337,7 +343,7 @@ __device__ void derive_state(const LossParams& P, int levels_done, SelectState& 
 
 // level = 1: histogram bits 20..10 of keys whose bits 31..21 match; level = 2: bits 9..0.
 __global__ void __launch_bounds__(256) select_kernel(LossParams P, int level) {
-  __shared__ u32 sh[kBins];
+  __shared__ __align__(16) u32 sh[kBins];   // scan_level keeps 8-byte warp totals in its first words
   __shared__ int sh_bin;
   __shared__ long long sh_above;
   __shared__ double sh_np;
@@ -373,7 +379,7 @@ __global__ void __launch_bounds__(256) select_kernel(LossParams P, int level) {
 }
 
 __global__ void __launch_bounds__(256) final_kernel(LossParams P) {
-  __shared__ u32 sh[kBins];
+  __shared__ __align__(16) u32 sh[kBins];
   __shared__ int sh_bin;
   __shared__ long long sh_above;
   __shared__ double sh_np;
@@ -458,7 +464,9 @@ __global__ void __launch_bounds__(256) final_kernel(LossParams P) {
   n_neg = (unsigned long long)d_neg; n_ovl = (unsigned long long)d_ovl;
   double* r = P.result;
   int status = st.status;
+  const u32 n_badlab = ((volatile u32*)P.ws->nparts)[1];
   if (!status && n_ovl) status = SSDG_ERR_POS_NEG_OVERLAP;  // models/ssd_model.py:375 (positives mined as negatives)
+  if (!status && n_badlab) status = SSDG_ERR_LABEL_RANGE;
   const double nan = CUDART_NAN;
   const double l_pos = status ? nan : s_pos / st.num_pos;
   const double l_neg = status ? nan : s_neg / (double)n_neg;
@@ -470,7 +478,10 @@ __global__ void __launch_bounds__(256) final_kernel(LossParams P) {
   r[7] = (double)status;
   r[8] = s_pos; r[9] = s_neg; r[10] = s_l1;
   r[11] = sh_np;   // this shard's own positives (== r[4] unless the mining is cross-shard)
-  for (int i = 12; i < SSDG_LOSS_RESULT_LEN; ++i) r[i] = 0;
+  // data-dependent errors seen by THIS shard (overlap :375, label range): additive, so a cross-shard caller sums it
+  // with [8..11] and every shard agrees on success
+  r[12] = (double)n_ovl + (double)n_badlab;
+  for (int i = 13; i < SSDG_LOSS_RESULT_LEN; ++i) r[i] = 0;
 }
 
 // ---- gradient (models/ssd_model.py:248 through :355-386) ---------------------------------------------
@@ -480,7 +491,7 @@ __global__ void __launch_bounds__(256) final_kernel(LossParams P) {
 // mined negative are written as zeros without reading the logits.
 __global__ void __launch_bounds__(256) grad_kernel(LossParams P) {
   const double* r = P.result;
-  const bool bad = r[7] != 0.0;
+  const bool bad = r[7] != 0.0 || r[12] != 0.0;
   const float wpos = bad ? CUDART_NAN_F : (float)(1.0 / r[4]);
   const float wneg = bad ? CUDART_NAN_F : (float)(1.0 / r[5]);
   const u32 kth = key32((float)r[6]);
@@ -506,7 +517,7 @@ __global__ void __launch_bounds__(256) grad_kernel(LossParams P) {
       const float w = (pos ? wpos : 0.f) + (neg ? wneg : 0.f);
       const float inv = w / s;
       int lab = P.gt_cls[n];
-      lab = lab < 0 ? 0 : (lab >= C ? C - 1 : lab);
+      lab = lab < 0 ? 0 : (lab >= C ? C - 1 : lab);   // (out-of-range labels make the whole result `bad`)
       for (int c = lane; c < C; c += 32) {
         float v = __expf(x[c] - m) * inv;
         if (pos && c == lab) v -= wpos;
@@ -547,8 +558,9 @@ extern "C" size_t ssdg_loss_workspace_bytes(int64_t batch, int32_t n_priors, int
   return align_up(sizeof(LossWs), 256) + align_up((size_t)batch * n_priors * 4, 256);
 }
 
-// stages: 1 = CE pass (+ level-0 histogram, positives count), 2 / 4 = radix levels 1 / 2, 8 = mask, sums, result
-// (+ gradient).  Between the stages of a cross-shard run the caller sums the exchange words over the shards.
+// stages: 1 = CE pass (+ level-0 histogram, positives count), 2 / 4 = radix levels 1 / 2, 8 = mask, sums, result,
+// 16 = gradient (reads the result block: in a cross-shard run AFTER its exchange, so that 1/num_neg is the global
+// count).  Between the stages of a cross-shard run the caller sums the exchange words over the shards.
 static int loss_run(int stages, int global, long long n_all, const float* row_ml, const float* row_negbg,
                     const int32_t* gt_cls, const float* gt_box,
                     const uint8_t* gt_mask, const float* pred_box, const float* pred_cls, int64_t batch,
@@ -613,11 +625,13 @@ static int loss_run(int stages, int global, long long n_all, const float* row_ml
     final_kernel<<<sgrid, 256, 0, st>>>(P);
     prof_end(SSDG_PROF_LOSS_TAIL, st);
     SSDG_LAUNCH_CHECK();
-    if (grad_cls) {
-      int ggrid = sm_count() * 8;
-      grad_kernel<<<ggrid, 256, 0, st>>>(P);
-      SSDG_LAUNCH_CHECK();
-    }
+  }
+  if ((stages & 16) && grad_cls) {
+    prof_begin(SSDG_PROF_GRAD, st);
+    int ggrid = sm_count() * 8;
+    grad_kernel<<<ggrid, 256, 0, st>>>(P);
+    prof_end(SSDG_PROF_GRAD, st);
+    SSDG_LAUNCH_CHECK();
   }
   return SSDG_OK;
 }
@@ -627,7 +641,7 @@ extern "C" int ssdg_multibox_loss(const int32_t* gt_cls, const float* gt_box, co
                                   int32_t n_classes, int32_t neg_ratio, double* out_result, uint8_t* out_neg_mask,
                                   float* out_neg_ce, float* grad_box, float* grad_cls, void* workspace,
                                   size_t workspace_bytes, void* stream) {
-  return loss_run(15, 0, 0, nullptr, nullptr, gt_cls, gt_box, gt_mask, pred_box, pred_cls, batch, n_priors, n_classes, neg_ratio,
+  return loss_run(31, 0, 0, nullptr, nullptr, gt_cls, gt_box, gt_mask, pred_box, pred_cls, batch, n_priors, n_classes, neg_ratio,
                   out_result, out_neg_mask, out_neg_ce, grad_box, grad_cls, workspace, workspace_bytes, stream);
 }
 
@@ -638,7 +652,8 @@ extern "C" int ssdg_multibox_loss_stage(int32_t stage, int64_t global_priors, co
                                         int32_t neg_ratio, double* out_result, uint8_t* out_neg_mask,
                                         float* out_neg_ce, float* grad_box, float* grad_cls, void* workspace,
                                         size_t workspace_bytes, void* stream) {
-  if (stage < 0 || stage > 3 || global_priors <= 0) return SSDG_ERR_ARG;
+  if (stage < 0 || stage > 4 || global_priors <= 0) return SSDG_ERR_ARG;
+  if (stage == 4 && !grad_cls) return SSDG_ERR_ARG;
   return loss_run(1 << stage, 1, global_priors, row_ml, row_negbg, gt_cls, gt_box, gt_mask, pred_box, pred_cls, batch, n_priors,
                   n_classes, neg_ratio, out_result, out_neg_mask, out_neg_ce, grad_box, grad_cls, workspace,
                   workspace_bytes, stream);
@@ -651,7 +666,7 @@ extern "C" int ssdg_multibox_loss_fused(const float* row_ml, const float* row_ne
                                         float* out_neg_ce, float* grad_box, float* grad_cls, void* workspace,
                                         size_t workspace_bytes, void* stream) {
   if (!row_ml || !row_negbg) return SSDG_ERR_ARG;
-  return loss_run(15, 0, 0, row_ml, row_negbg, gt_cls, gt_box, gt_mask, pred_box, pred_cls, batch, n_priors, n_classes,
+  return loss_run(31, 0, 0, row_ml, row_negbg, gt_cls, gt_box, gt_mask, pred_box, pred_cls, batch, n_priors, n_classes,
                   neg_ratio, out_result, out_neg_mask, out_neg_ce, grad_box, grad_cls, workspace, workspace_bytes, stream);
 }
 

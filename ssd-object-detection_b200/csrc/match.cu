@@ -77,7 +77,7 @@ struct MatchParams {
   float* out_loc;
   uint8_t* out_mask;
   int* out_match;
-  u32* ws_head;             // [0] next image, [1] status bits, [2] next row of the search kernel
+  u32* ws_head;             // [0] next image, [1] status bits, [2] next row of the search kernel, [3] tiles evaluated
   u32* ws_ncand;            // [B] listed pairs of the image
   u64* ws_rowkey;           // [B*tm] row maximum (key64) found by the search kernel
   int* ws_rowcol;           // [B*tm] its first arg-max prior
@@ -92,7 +92,13 @@ struct MatchParams {
   int ntiles;
   int elim_words;
   int bits_in_smem;
+  u64 index_sum;            // content checksum of the priors the index was built from (0: no index)
+  long long prior_words;    // 8-byte words of the prior array
 };
+
+// Position-weighted sum of the 8-byte words of the prior array (mod 2^64): order-independent to accumulate, sensitive
+// to any changed, moved or swapped word.  Host (index build) and device (every launch with an index) agree exactly.
+__host__ __device__ __forceinline__ u64 checksum_term(u64 word, long long i) { return word * (2ull * (u64)i + 1ull); }
 
 template <typename TG, typename TP>
 struct Promote {
@@ -285,11 +291,15 @@ __global__ void __launch_bounds__(kSearchThreads, 8) search_kernel(MatchParams P
   const u64 thr_key = key64((double)(R)P.thresh);
   const float thr_lo = f_down((double)(R)P.thresh);
   const int total_rows = P.gt_off[P.B];
+  u32 n_eval = 0u;   // tiles this warp evaluated exactly (ws_head[3]: the matcher's work counter, bench.py)
   for (;;) {
     int gr = 0;
     if (lane == 0) gr = (int)atomicAdd(&P.ws_head[2], 1u);
     gr = __shfl_sync(SSDG_FULL, gr, 0);
-    if (gr >= total_rows) break;
+    if (gr >= total_rows) {
+      if (lane == 0 && n_eval) atomicAdd(&P.ws_head[3], n_eval);
+      break;
+    }
     // image of the row: last b with gt_off[b] <= gr
     int lo = 0, hi = P.B;
     while (hi - lo > 1) {
@@ -318,6 +328,7 @@ __global__ void __launch_bounds__(kSearchThreads, 8) search_kernel(MatchParams P
     u32 rowhi = 0u;
     // exact evaluation of one tile for this row (all lanes)
     auto evaluate = [&](int tile) {
+      ++n_eval;
       const int slot = (tile << 5) + lane;
       const int a = P.perm ? __ldg(P.perm + slot) : slot;
       const bool valid = a >= 0 && a < A;
@@ -438,6 +449,23 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
     return g;
   };
   auto bit_test = [&](const u32* bm, int a) { return (bm[a >> 5] >> (a & 31)) & 1u; };
+
+  // The index must belong to THESE priors (in-place edits such as ssdg_priors_clip, or a recycled address, would
+  // silently pair with stale tiles): one CTA re-derives the content checksum and raises status bit 3 on mismatch.
+  if (P.index_sum != 0ull && blockIdx.x == 0) {
+    const u64* w = reinterpret_cast<const u64*>(P.priors);
+    u64 acc = 0ull;
+    for (long long i = tid; i < P.prior_words; i += kMatchThreads) acc += checksum_term(__ldg(w + i), i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(SSDG_FULL, acc, o);
+    u64* cs = reinterpret_cast<u64*>(&S.ctl[C_RKEY_LO]);   // 8-byte aligned pair of control words (free before the loop)
+    if (tid == 0) *cs = 0ull;
+    __syncthreads();
+    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(cs), (unsigned long long)acc);
+    __syncthreads();
+    if (tid == 0 && *cs != P.index_sum) atomicOr(&P.ws_head[1], 8u);
+    __syncthreads();
+  }
 
 #ifdef SSDG_MATCH_TIMING
   long long tk0 = 0;
@@ -892,9 +920,10 @@ static size_t match_ws_layout(int batch, int n_priors, int max_gt, int ctas, Mat
 
 // ---- prior index ---------------------------------------------------------------------------------------
 constexpr int kIndexMaxShapes = 64;
-struct IndexInfo { int n_priors, ntiles, dtype; };
+struct IndexInfo { int n_priors, ntiles, dtype, device; u64 sum; };
 static std::mutex g_index_mu;
-static std::unordered_map<const void*, IndexInfo> g_index;   // device pointer -> geometry
+static std::unordered_map<const void*, IndexInfo> g_index;   // index device pointer -> geometry, owner device, checksum
+                                                             // (erased by ssdg_prior_index_destroy)
 
 static size_t index_slots(int n_priors) { return ((size_t)n_priors + 31) / 32 * 32 + (size_t)kIndexMaxShapes * 32; }
 static size_t index_perm_offset() { return 256; }
@@ -997,9 +1026,24 @@ extern "C" int ssdg_prior_index_build(const void* priors, int32_t prior_dtype, i
   }
   SSDG_LAUNCH_CHECK();
   SSDG_CUDA_TRY(cudaStreamSynchronize(st));
+  u64 sum = 0ull;
+  {
+    const u64* w = reinterpret_cast<const u64*>(raw.data());
+    const long long nw = (long long)(raw.size() / 8);
+    for (long long i = 0; i < nw; ++i) sum += checksum_term(w[i], i);
+    if (sum == 0ull) sum = 1ull;   // 0 means "no index" on the device side
+  }
+  int dev = 0;
+  SSDG_CUDA_TRY(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(g_index_mu);
-  g_index[index] = IndexInfo{n_priors, ntiles, prior_dtype};
+  g_index[index] = IndexInfo{n_priors, ntiles, prior_dtype, dev, sum};
   return SSDG_OK;
+}
+
+extern "C" int ssdg_prior_index_destroy(void* index) {
+  if (!index) return SSDG_OK;
+  std::lock_guard<std::mutex> lk(g_index_mu);
+  return g_index.erase(index) ? SSDG_OK : SSDG_ERR_ARG;
 }
 
 extern "C" size_t ssdg_match_workspace_bytes(int32_t batch, int32_t n_priors, int32_t max_gt) {
@@ -1034,6 +1078,8 @@ extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const f
   P.elim_words = (n_priors + 31) / 32;
   P.ws_head = ws.head; P.ws_ncand = ws.ncand; P.ws_rowkey = ws.rowkey; P.ws_rowcol = ws.rowcol; P.ws_cand = ws.cand; P.ws_colkey = ws.colkey; P.ws_colt = ws.colt; P.ws_bits = ws.bits;
   P.tiles = ws.tiles; P.perm = nullptr; P.unmatched = nullptr; P.pprior = nullptr; P.ntiles = (n_priors + 31) / 32;
+  P.index_sum = 0ull;
+  P.prior_words = (long long)n_priors * 4 * (prior_dtype == SSDG_F64 ? 8 : 4) / 8;
   if (prior_index) {
     IndexInfo info;
     {
@@ -1042,7 +1088,11 @@ extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const f
       if (it == g_index.end()) return SSDG_ERR_ARG;
       info = it->second;
     }
+    int dev = 0;
+    SSDG_CUDA_TRY(cudaGetDevice(&dev));
+    if (info.device != dev) return SSDG_ERR_ARG;
     if (info.n_priors != n_priors || info.dtype != prior_dtype) return SSDG_ERR_SHAPE;
+    P.index_sum = info.sum;
     const unsigned char* ib = (const unsigned char*)prior_index;
     P.perm = (const int*)(ib + index_perm_offset());
     P.tiles = (const TileStat*)(ib + index_tiles_offset(n_priors));

@@ -12,10 +12,13 @@ LIB_PATH = os.environ.get("SSDGEOM_LIB") or os.path.join(_HERE, "_lib", "libssdg
 OK = 0
 ERR_ARG, ERR_TOO_MANY_GT, ERR_THRESH, ERR_SHAPE, ERR_NO_POSITIVE = -1, -2, -3, -4, -5
 ERR_TOPK_RANGE, ERR_WORKSPACE, ERR_ALIGN, ERR_LIMIT, ERR_POS_NEG_OVERLAP = -6, -7, -8, -9, -10
-F32, F64 = 0, 1
+ERR_NO_NCCL, ERR_LABEL_RANGE, ERR_STALE_INDEX = -11, -12, -13
+ERR_NCCL_BASE = 10000
+F32, F64, I32, I64 = 0, 1, 2, 3
+COMM_ID_BYTES = 128
 LOSS_RESULT_LEN = 16
 PROF_MATCH, PROF_CE, PROF_FILTER, PROF_NMS = 0, 1, 2, 3
-PROF_BUCKET, PROF_SEARCH, PROF_LOSS_TAIL = 4, 5, 6
+PROF_BUCKET, PROF_SEARCH, PROF_LOSS_TAIL, PROF_GRAD = 4, 5, 6, 7
 
 _vp, _i32, _i64, _f32, _f64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_size_t
 _pi32, _pf64 = C.POINTER(C.c_int32), C.POINTER(C.c_double)
@@ -26,6 +29,7 @@ PROTOTYPES = {
     "ssdg_version": (C.c_int, []),
     "ssdg_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "ssdg_set_device": (C.c_int, [C.c_int]),
+    "ssdg_get_device": (C.c_int, [C.POINTER(C.c_int)]),
     "ssdg_device_alloc": (C.c_int, [C.POINTER(_vp), _sz]),
     "ssdg_device_free": (C.c_int, [_vp]),
     "ssdg_host_alloc": (C.c_int, [C.POINTER(_vp), _sz]),
@@ -43,7 +47,6 @@ PROTOTYPES = {
     "ssdg_stream_wait_event": (C.c_int, [_vp, _vp]),
     "ssdg_event_elapsed_ms": (C.c_int, [_vp, _vp, C.POINTER(_f32)]),
     "ssdg_profile_enable": (C.c_int, [C.c_int]),
-    "ssdg_detect_set_mid_event": (C.c_int, [_vp]),
     "ssdg_profile_last_ms": (C.c_int, [C.c_int, C.POINTER(_f32)]),
     "ssdg_profile_span_ms": (C.c_int, [_i32, _vp, C.POINTER(_f32), C.POINTER(_f32)]),
     "ssdg_prior_count": (_i64, [_pi32, _pi32, _pi32, _i32]),
@@ -51,6 +54,7 @@ PROTOTYPES = {
     "ssdg_match_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "ssdg_prior_index_bytes": (_sz, [_i32]),
     "ssdg_prior_index_build": (C.c_int, [_vp, _i32, _i32, _vp, _sz, _vp]),
+    "ssdg_prior_index_destroy": (C.c_int, [_vp]),
     "ssdg_match_encode": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _f64,
                                     _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ssdg_match_status": (C.c_int, [_vp, _pi32, _vp]),
@@ -75,6 +79,13 @@ PROTOTYPES = {
     "ssdg_multibox_loss_fused": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp,
                                            _vp, _vp, _vp, _sz, _vp]),
     "ssdg_nms": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ssdg_comm_available": (C.c_int, [C.POINTER(C.c_int)]),
+    "ssdg_comm_unique_id": (C.c_int, [_vp]),
+    "ssdg_comm_init_rank": (C.c_int, [C.POINTER(_vp), _vp, _i32, _i32]),
+    "ssdg_comm_world": (C.c_int, [_vp, _pi32, _pi32]),
+    "ssdg_comm_allreduce_sum": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
+    "ssdg_comm_allreduce_sum_multi": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(_i64), _pi32, _vp]),
+    "ssdg_comm_destroy": (C.c_int, [_vp]),
 }
 
 _lib = None
@@ -114,8 +125,12 @@ def check(status: int, what: str = ""):
     msg = "%s%s" % (what + ": " if what else "", status_string(status))
     if status in (ERR_TOO_MANY_GT, ERR_THRESH, ERR_SHAPE, ERR_POS_NEG_OVERLAP):
         raise AssertionError(msg)
+    if status == ERR_NO_NCCL:
+        raise SsdgeomError(msg)
     if status < 0:
         raise ValueError(msg)
+    if status >= ERR_NCCL_BASE:
+        raise SsdgeomError("NCCL error %d: %s" % (status - ERR_NCCL_BASE, msg))
     raise SsdgeomError("CUDA error %d: %s" % (status, msg))
 
 

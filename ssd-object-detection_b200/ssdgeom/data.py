@@ -7,6 +7,9 @@ per image (models/ssd_model.py:211-215) and ``.batch(B, drop_remainder=True)`` (
 arithmetic runs once per BATCH on the device; only ragged packing (lists -> CSR) stays on the host."""
 from __future__ import annotations
 
+import queue
+import threading
+
 import numpy as np
 
 from . import device as D
@@ -50,13 +53,20 @@ class TrainBatches:
     ``coco_pixels=True``, in which case they are COCO pixel [x,y,w,h] and ``image_wh`` is taken from a
     fourth element of the tuple (w, h) or from the image itself.  Iterating yields
     ``(images [B,H,W,3], (cls int32 [B,A], loc float32 [B,A,4], mask bool [B,A]))`` as host arrays
-    (``device=True``: DeviceArrays, mask uint8).  The trailing partial batch is dropped (:225)."""
+    (``device=True``: DeviceArrays, mask uint8).  The trailing partial batch is dropped (:225).
 
-    def __init__(self, source, priors, batch_size=1, thresh=0.5, coco_pixels=False, device=False, stream=None):
+    ``prefetch`` mirrors ``.prefetch(10)`` (:225): a producer thread packs, assigns and downloads up to that many
+    batches ahead of the consumer on a stream of its own (the library releases the GIL inside its calls), so the
+    assignment of batch k+1 overlaps whatever the training step does with batch k.  ``prefetch=0`` is synchronous."""
+
+    def __init__(self, source, priors, batch_size=1, thresh=0.5, coco_pixels=False, device=False, stream=None,
+                 prefetch=10):
         self.source, self.batch_size, self.thresh = source, int(batch_size), float(thresh)
         self.priors = D.as_device(priors)
         ops.prior_index(self.priors)
         self.coco_pixels, self.device, self.stream = bool(coco_pixels), bool(device), stream
+        self.prefetch = int(prefetch)
+        self.pool = ops.WorkspacePool()      # this iterator's own matcher scratch (its calls are in stream order)
 
     def _emit(self, images, cls_list, box_list, wh):
         cls, boxes, off = pack_gt(cls_list, box_list)
@@ -66,14 +76,55 @@ class TrainBatches:
         else:
             d_boxes = D.as_device(boxes.astype(np.float32, copy=False), np.float32)
         max_gt = int(np.diff(off).max()) if b else 0
-        tgt = ops.match_encode(d_boxes, cls, off, self.priors, b, max(max_gt, 1), self.thresh, stream=self.stream)
+        tgt = ops.match_encode(d_boxes, cls, off, self.priors, b, max(max_gt, 1), self.thresh, stream=self.stream,
+                               pool=self.pool)
         img = ops.image_normalize(np.stack(images).astype(np.float32, copy=False), stream=self.stream)
         if self.device:
+            ops.raise_for_match_status(ops.match_status(tgt, self.stream))      # synchronises: the batch is ready
             return img, (tgt["cls"], tgt["loc"], tgt["mask"])
         return img.to_host(self.stream), (tgt["cls"].to_host(self.stream), tgt["loc"].to_host(self.stream),
                                           tgt["mask"].to_host(self.stream).astype(bool))
 
     def __iter__(self):
+        if self.prefetch <= 0:
+            yield from self._batches()
+            return
+        if self.stream is None:
+            self.stream = D.Stream()         # not the legacy default stream: it would serialise with the consumer
+        q, stop, done = queue.Queue(maxsize=self.prefetch), threading.Event(), object()
+
+        def put(item):                       # never blocks forever: an abandoned consumer sets `stop`
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.1)
+                    return True
+                except queue.Full:
+                    continue
+            return False
+
+        def produce():
+            try:
+                for batch in self._batches():
+                    if not put(batch):
+                        return
+                put(done)
+            except BaseException as e:       # surfaces in the consumer, like an error inside the tf.data generator
+                put(e)
+
+        t = threading.Thread(target=produce, name="ssdgeom-train-batches", daemon=True)
+        t.start()
+        try:
+            while True:
+                item = q.get()
+                if item is done:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:
+            stop.set()
+
+    def _batches(self):
         images, cls_list, box_list, wh = [], [], [], []
         for item in self.source:
             image, cls, box = item[0], item[1], item[2]

@@ -46,6 +46,12 @@ def stream_handle(stream) -> int | None:
     return int(stream) or None
 
 
+def current_device() -> int:
+    d = C.c_int(0)
+    N.check(N.lib().ssdg_get_device(C.byref(d)), "get_device")
+    return d.value
+
+
 def sync(stream=None):
     N.check(N.lib().ssdg_stream_sync(stream_handle(stream)), "stream_sync")
 

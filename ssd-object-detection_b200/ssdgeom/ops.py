@@ -22,18 +22,24 @@ def _code(dtype) -> int:
 
 
 class WorkspacePool:
-    """Grow-only device scratch, one buffer per kernel family so families can overlap on
-    different streams."""
+    """Grow-only device scratch, one buffer per kernel family so families can overlap on different streams.
+    A pool belongs to ONE owner that enqueues its calls of a family in stream order: every ``HotPath`` and every
+    ``StagedLoss`` has its own (pass ``pool=``); the module-level default ``POOL`` serves the stand-alone,
+    one-call-at-a-time drop-ins and keeps a separate buffer per CUDA device."""
 
     def __init__(self):
         self._buf = {}
 
     def get(self, kind: str, nbytes: int) -> D.DeviceArray:
-        cur = self._buf.get(kind)
+        key = (D.current_device(), kind)
+        cur = self._buf.get(key)
         if cur is None or cur.nbytes < nbytes:
             cur = D.empty((int(nbytes) + 255) // 256 * 256, np.uint8)
-            self._buf[kind] = cur
+            self._buf[key] = cur
         return cur
+
+    def peek(self, kind: str):
+        return self._buf.get((D.current_device(), kind))
 
 
 POOL = WorkspacePool()
@@ -92,16 +98,29 @@ def prior_index(priors, stream=None) -> D.DeviceArray:
         return cached
     lib = N.lib()
     a = int(priors.shape[0])
-    idx = D.empty((int(lib.ssdg_prior_index_bytes(a)) + 255) // 256 * 256, np.uint8)
+    idx = PriorIndex((int(lib.ssdg_prior_index_bytes(a)) + 255) // 256 * 256, np.uint8)
     N.check(lib.ssdg_prior_index_build(priors.ptr, _code(priors.dtype), a, idx.ptr, idx.nbytes, D.stream_handle(stream)),
             "prior_index_build")
-    idx._keep = priors
-    priors._ssdg_index = idx
+    idx._built = True
+    priors._ssdg_index = idx          # (the index does not keep the priors alive: the priors own the index)
     return idx
 
 
+class PriorIndex(D.DeviceArray):
+    """Device memory of a matcher index; unregisters itself from the library before the memory is freed."""
+    _built = False
+
+    def __del__(self):
+        try:
+            if self._built and self.ptr:
+                N.lib().ssdg_prior_index_destroy(self.ptr)
+        except Exception:
+            pass
+        D.DeviceArray.__del__(self)
+
+
 def match_encode(gt_boxes, gt_cls, gt_offsets, priors, batch: int, max_gt: int, thresh: float = 0.5,
-                 want=("cls", "loc", "mask"), out=None, stream=None, index=None) -> dict:
+                 want=("cls", "loc", "mask"), out=None, stream=None, index=None, pool=None) -> dict:
     """Batched match_bbox + apply_anchor_box (utils/bbox.py:44-101, models/ssd_model.py:211-224).
     ``want`` selects outputs among cls, box, loc, mask, match; ``out`` may carry preallocated arrays."""
     gt_boxes, priors = D.as_device(gt_boxes), D.as_device(priors)
@@ -116,7 +135,7 @@ def match_encode(gt_boxes, gt_cls, gt_offsets, priors, batch: int, max_gt: int, 
             out[k] = D.empty(*spec[k])
     lib = N.lib()
     nbytes = lib.ssdg_match_workspace_bytes(batch, a, max_gt)
-    ws = POOL.get("match", nbytes)
+    ws = (pool or POOL).get("match", nbytes)
     if index is None:
         index = getattr(priors, "_ssdg_index", None)     # built by prior_index() for long-lived prior sets
     N.check(lib.ssdg_match_encode(gt_boxes.ptr, _code(gt_boxes.dtype), gt_cls.ptr, gt_offsets.ptr, priors.ptr,
@@ -124,14 +143,31 @@ def match_encode(gt_boxes, gt_cls, gt_offsets, priors, batch: int, max_gt: int, 
                                   _p(out.get("cls")), _p(out.get("box")), _p(out.get("loc")), _p(out.get("mask")),
                                   _p(out.get("match")), ws.ptr, ws.nbytes, D.stream_handle(stream)), "match_encode")
     out["_keep"] = (gt_boxes, gt_cls, gt_offsets, priors, ws)
+    out["_match_ws"] = ws
     return out
 
 
-def match_status(stream=None) -> int:
+MATCH_STATUS_TOO_MANY_GT, MATCH_STATUS_MORE_GT_THAN_PRIORS, MATCH_STATUS_RESCAN, MATCH_STATUS_STALE_INDEX = 1, 2, 4, 8
+
+
+def match_status(out, stream=None) -> int:
+    """Status bits of the ``match_encode`` call that returned ``out`` (synchronises): see ssdg_match_status."""
     st = C.c_int32(0)
-    ws = POOL.get("match", 256)
+    ws = out["_match_ws"] if isinstance(out, dict) else out
     N.check(N.lib().ssdg_match_status(ws.ptr, C.byref(st), D.stream_handle(stream)), "match_status")
     return st.value
+
+
+def raise_for_match_status(status: int):
+    """The reference matches every ground-truth box or asserts (utils/bbox.py:50): images the device had to skip
+    are an error, not a silent all-unmatched result."""
+    status = int(status)
+    if status & MATCH_STATUS_MORE_GT_THAN_PRIORS:
+        raise AssertionError("number of default boxes should greater than the number of targets")   # utils/bbox.py:50
+    if status & MATCH_STATUS_TOO_MANY_GT:
+        raise ValueError("an image has more ground-truth boxes than max_gt: its targets were not assigned")
+    if status & MATCH_STATUS_STALE_INDEX:
+        raise N.SsdgeomError("the prior index was not built from these priors (modified after prior_index()?)")
 
 
 def gt_prepare(xywh, img_wh, gt_offsets, out=None, stream=None) -> D.DeviceArray:
@@ -202,7 +238,8 @@ def iou_pairs(boxes_1, boxes_2, use_eps_clamp: bool, stream=None) -> D.DeviceArr
 
 # ---- A6 ----------------------------------------------------------------------------------------------
 def multibox_loss(gt_cls, gt_box, gt_mask, pred_box, pred_cls, neg_ratio: int = 3, want_neg_mask=False,
-                  want_neg_ce=False, want_grad=False, out=None, stream=None, ws_kind="loss", row_stats=None) -> dict:
+                  want_neg_ce=False, want_grad=False, out=None, stream=None, ws_kind="loss", row_stats=None,
+                  pool=None) -> dict:
     """models/ssd_model.py:341-396.  Returns {'result': float64[16] device block, ...}; see
     include/ssdgeom.h for the block layout.  row_stats = (row_ml, row_negbg) from ``detect(..., want_row_stats=True)``
     on the same pred_cls: the loss then skips its own pass over the logits (ssdg_multibox_loss_fused)."""
@@ -230,7 +267,7 @@ def multibox_loss(gt_cls, gt_box, gt_mask, pred_box, pred_cls, neg_ratio: int = 
         if "grad_cls" not in out:
             out["grad_cls"] = D.empty((b, a, c), np.float32)
     lib = N.lib()
-    ws = POOL.get(ws_kind, lib.ssdg_loss_workspace_bytes(b, a, c))
+    ws = (pool or POOL).get(ws_kind, lib.ssdg_loss_workspace_bytes(b, a, c))
     args = (gt_cls.ptr, gt_box.ptr, gt_mask.ptr, pred_box.ptr, pred_cls.ptr, b, a, c,
             int(neg_ratio), out["result"].ptr, _p(out.get("neg_mask")), _p(out.get("neg_ce")),
             _p(out.get("grad_box")), _p(out.get("grad_cls")), ws.ptr, ws.nbytes, D.stream_handle(stream))
@@ -250,7 +287,7 @@ class StagedLoss:
     (include/ssdgeom.h, ssdg_multibox_loss_stage).  Usage, on every shard:
 
         sl = StagedLoss(gt_cls, gt_box, gt_mask, pred_box, pred_cls, global_priors=sum of b*A over shards)
-        for stage in range(4):
+        for stage in range(sl.n_stages):        # 4, or 5 with want_grad (the gradient runs AFTER the last exchange)
             sl.run(stage)
             for buf in sl.exchange(stage):      # device buffers (int32 / int64 / float64)
                 <sum buf over the shards, in place>
@@ -261,7 +298,7 @@ class StagedLoss:
 
     def __init__(self, gt_cls, gt_box, gt_mask, pred_box, pred_cls, global_priors: int, neg_ratio: int = 3,
                  want_neg_mask=False, want_neg_ce=False, want_grad=False, stream=None, ws_kind="loss_staged", out=None,
-                 row_stats=None):
+                 row_stats=None, pool=None):
         self.gt_cls = D.as_device(gt_cls, np.int32)
         self.gt_box = D.as_device(gt_box, np.float32)
         self.gt_mask = D.as_device(gt_mask, np.uint8)
@@ -290,7 +327,9 @@ class StagedLoss:
             self.out["grad_box"] = D.empty((b, a, 4), np.float32)
             self.out["grad_cls"] = D.empty((b, a, c), np.float32)
         lib = N.lib()
-        self.ws = POOL.get(ws_kind, lib.ssdg_loss_workspace_bytes(b, a, c))
+        self.pool = pool or WorkspacePool()        # never shared: the stages keep state in the workspace
+        self.ws = self.pool.get(ws_kind, lib.ssdg_loss_workspace_bytes(b, a, c))
+        self.n_stages = 5 if want_grad else 4
 
     def run(self, stage: int):
         b, a, c = self.shape
@@ -319,9 +358,12 @@ class StagedLoss:
             return [self._xbuf(3, np.int64), self._xbuf(0, np.int32)]
         if stage in (1, 2):
             return [self._xbuf(stage, np.int32)]
+        if stage == 4:
+            return []
         r = self.out["result"]
-        # the separable sums [8..10], the shard's own positives [11] and its mined negatives [5]
-        return [D.DeviceArray((4,), np.float64, ptr=r.ptr + 8 * 8, owner=r),
+        # the separable sums [8..10], the shard's own positives [11], its data-dependent error count [12] and its
+        # mined negatives [5]
+        return [D.DeviceArray((5,), np.float64, ptr=r.ptr + 8 * 8, owner=r),
                 D.DeviceArray((1,), np.float64, ptr=r.ptr + 5 * 8, owner=r)]
 
     def finish(self) -> tuple:
@@ -333,6 +375,9 @@ class StagedLoss:
         if status == N.ERR_TOPK_RANGE:
             raise ValueError("3*num_pos exceeds the number of priors in the batch (tf.math.top_k, models/ssd_model.py:368)")
         N.check(status, "multibox_loss_stage")
+        if r[12] != 0:      # some shard mined a positive (models/ssd_model.py:375) or saw a class id out of range
+            raise AssertionError("a shard of the batch reported %d positives mined as negatives / class ids out of "
+                                 "range" % int(r[12]))
         s_pos, s_neg, s_l1, n_pos, n_neg = r[8], r[9], r[10], r[11], r[5]
         l_pos, l_neg, l_loc = s_pos / n_pos, s_neg / n_neg, s_l1 / n_pos
         return (l_loc + l_pos) + l_neg, {"cls loss pos": l_pos, "cls loss neg": l_neg, "loc loss": l_loc,
@@ -356,7 +401,7 @@ def loss_result_to_host(result: D.DeviceArray, stream=None) -> dict:
 # ---- A7 + A8 + A9 ---------------------------------------------------------------------------------------
 def detect(pred_cls, pred_box, priors, score_thresh=0.01, top_k=200, iou_thresh=0.45, want_scores=False,
            want_boxes=False, want_probs=False, head_thresh=None, out=None, stream=None, stage=None,
-           want_row_stats=False, ws_key="detect") -> dict:
+           want_row_stats=False, ws_key="detect", pool=None) -> dict:
     """stage: None = the whole post-processing; 0 = filter + decode + bucketing only; 1 = the NMS of a previous
     stage-0 call with the same arguments (include/ssdgeom.h, ssdg_detect_stage).  ws_key names the pooled
     workspace: calls that overlap on different streams need different keys."""
@@ -388,7 +433,7 @@ def detect(pred_cls, pred_box, priors, score_thresh=0.01, top_k=200, iou_thresh=
         need("head_cls", (b, a), np.int32)
         need("head_mask", (b, a), np.uint8)
     lib = N.lib()
-    ws = POOL.get(ws_key, lib.ssdg_detect_workspace_bytes(b, a, c, top_k))
+    ws = (pool or POOL).get(ws_key, lib.ssdg_detect_workspace_bytes(b, a, c, top_k))
     args = (pred_cls.ptr, pred_box.ptr, priors.ptr, _code(priors.dtype), b, a, c, float(score_thresh),
             int(top_k), float(iou_thresh), out["kept"].ptr, out["count"].ptr, _p(out.get("kept_score")),
             _p(out.get("boxes")), _p(out.get("probs")),

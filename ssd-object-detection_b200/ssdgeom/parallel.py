@@ -95,10 +95,10 @@ def distributed_loss(result_block_tensor, group=None, mode="pooled"):
 
 
 def global_mining_loss(staged, allreduce):
-    """Drive a staged loss (``ops.StagedLoss`` or anything with run / exchange / finish) through the four
+    """Drive a staged loss (``ops.StagedLoss`` or anything with run / exchange / finish) through the
     stages of the cross-shard mining protocol.  ``allreduce(buf)`` sums one exchange buffer over the shards
     in place; every shard must call this function collectively.  Returns (total, info) of the whole batch."""
-    for stage in range(4):
+    for stage in range(getattr(staged, "n_stages", 4)):     # 5 with gradients: they run after the last exchange
         staged.run(stage)
         for buf in staged.exchange(stage):
             allreduce(buf)

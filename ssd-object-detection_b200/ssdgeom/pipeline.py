@@ -1,7 +1,7 @@
 """The chained hot path (target assignment -> multibox loss, and decode -> per-class NMS) with
 preallocated buffers and explicit streams: the call a data-parallel trainer/evaluator makes per
 batch.  The two branches only share the predictions, so they run on separate streams: the
-matcher is ALU-bound and the loss/filter passes are HBM-bound, so they overlap."""
+matcher is latency-bound and the loss/filter passes are HBM-bound, so they overlap."""
 from __future__ import annotations
 
 import numpy as np
@@ -11,29 +11,33 @@ from . import device as D
 from . import ops
 from .models.ssd_model import SSD300
 
+INPUT_NAMES = ("gt_boxes", "gt_cls", "gt_off", "pred_cls", "pred_box")
+
 
 class HotPath:
     def __init__(self, table=None, batch=256, max_gt=100, classes=81, thresh=0.5, neg_ratio=3,
                  score_thresh=0.01, top_k=200, iou_thresh=0.45, total_gt=None, mining="shard", global_priors=None,
-                 allreduce=None):
+                 allreduce=None, comm=None):
         """mining: "shard" -- the hard-negative threshold is mined over this process's batch (what the reference
-        does per slice under split_batch); "global" -- over the batches of all data-parallel processes
-        (ops.StagedLoss; ``allreduce(buf, stream)`` must sum a device buffer over the processes in stream order
-        and ``global_priors`` is the total number of priors over all of them)."""
+        does per slice under split_batch, models/ssd_model.py:235-256); "global" -- over the batches of all
+        data-parallel processes (ops.StagedLoss; ``global_priors`` is the total number of priors over all of them).
+
+        Data-parallel exchange: ``comm`` (ssdgeom.comm.Comm, the library's own NCCL entry points) sums the additive
+        loss words -- or the mining histograms -- over the processes; alternatively ``allreduce(buf, stream)`` /
+        ``loss_exchange(stream)`` callables (a torch.distributed or gloo stand-in) do."""
         table = SSD300 if table is None else table
         self.batch, self.max_gt, self.classes = int(batch), int(max_gt), int(classes)
         self.thresh, self.neg_ratio = float(thresh), int(neg_ratio)
         self.score_thresh, self.top_k, self.iou_thresh = float(score_thresh), int(top_k), float(iou_thresh)
+        self.pool = ops.WorkspacePool()                  # this pipeline's own scratch (never shared)
         self.priors = ops.prior_boxes(table["sizes"], table["s_k_refer"], table["aspect_ratio"], table["input_size"])
         self.A = a = int(self.priors.shape[0])
         ops.prior_index(self.priors)                     # one-off, like the priors themselves
         b, c = self.batch, self.classes
         n_gt = int(total_gt if total_gt is not None else b * self.max_gt)
-        self.gt_boxes = D.empty((n_gt, 4), np.float32)
-        self.gt_cls = D.empty((n_gt,), np.float32)
-        self.gt_off = D.empty((b + 1,), np.int32)
-        self.pred_cls = D.empty((b, a, c), np.float32)
-        self.pred_box = D.empty((b, a, 4), np.float32)
+        self.total_gt = n_gt
+        self._sets = [self._alloc_inputs()]
+        self._bind(self._sets[0])
         self.tgt = {"cls": D.empty((b, a), np.int32), "loc": D.empty((b, a, 4), np.float32),
                     "mask": D.empty((b, a), np.uint8)}
         self.loss = {"result": D.empty((N.LOSS_RESULT_LEN,), np.float64)}
@@ -57,49 +61,88 @@ class HotPath:
         self.det_stats = {"row_ml": D.empty((b, a, 2), np.float32), "row_negbg": D.empty((b, a), np.float32)}
         if mining not in ("shard", "global"):
             raise ValueError("mining must be 'shard' or 'global'")
-        self.mining, self.allreduce = mining, allreduce
+        self.mining, self.comm = mining, comm
+        if comm is not None and allreduce is None:
+            allreduce = comm.allreduce
+        self.allreduce = allreduce
         # optional callable(stream): the data-parallel exchange of the additive loss sums (per-shard mining),
-        # enqueued on the loss stream right behind the loss so that it hides under the NMS of the other branch
+        # enqueued on a stream of its own right behind the loss so that it hides under the NMS of the other branch
         self.loss_exchange = None
+        if comm is not None and mining == "shard" and comm.world > 1:
+            r = self.loss["result"]
+            sums = D.DeviceArray((7,), np.float64, ptr=r.ptr + 4 * 8, owner=r)    # result[4..10], include/ssdgeom.h
+            self.loss_exchange = lambda stream: comm.allreduce(sums, stream)
         self.staged = None
         if mining == "global":
             if allreduce is None or not global_priors:
-                raise ValueError("global mining needs allreduce and global_priors")
+                raise ValueError("global mining needs comm / allreduce and global_priors")
             self.staged = ops.StagedLoss(self.tgt["cls"], self.tgt["loc"], self.tgt["mask"], self.pred_box, self.pred_cls,
                                          int(global_priors), self.neg_ratio, out=self.loss)
         # search, match | lossprep (or ce), select x2, final | filter, bucket, nms per slice of the post-processing
         self.kernel_launches_per_step = 6 + 3 * self.detect_parts
-        self.h2d_bytes = (self.gt_boxes.nbytes + self.gt_cls.nbytes + self.gt_off.nbytes + self.pred_cls.nbytes +
-                          self.pred_box.nbytes)
-        self.d2h_bytes = self.loss["result"].nbytes + self.det["kept"].nbytes + self.det["count"].nbytes
+        self.memsets_per_step = 2                       # matcher head + loss histograms (cudaMemsetAsync)
+        self.h2d_bytes = sum(self._sets[0][k].nbytes for k in INPUT_NAMES)
+        # results + the matcher's status word
+        self.d2h_bytes = self.loss["result"].nbytes + self.det["kept"].nbytes + self.det["count"].nbytes + 4
+        self._status_host = D.PinnedArray((2,), np.uint32)
+        self._status_host.array[...] = 0
+        self._match_out = None
+
+    # ---- input buffers --------------------------------------------------------------------------------------
+    def _alloc_inputs(self):
+        b, a, c = self.batch, self.A, self.classes
+        return {"gt_boxes": D.empty((self.total_gt, 4), np.float32), "gt_cls": D.empty((self.total_gt,), np.float32),
+                "gt_off": D.empty((b + 1,), np.int32), "pred_cls": D.empty((b, a, c), np.float32),
+                "pred_box": D.empty((b, a, 4), np.float32)}
+
+    def _bind(self, s):
+        for k in INPUT_NAMES:
+            setattr(self, k, s[k])
+        if getattr(self, "staged", None) is not None:
+            self.staged.pred_box, self.staged.pred_cls = self.pred_box, self.pred_cls
+
+    def add_input_set(self) -> int:
+        """Another resident copy of the input buffers (distinct batches to rotate over); returns its index."""
+        self._sets.append(self._alloc_inputs())
+        return len(self._sets) - 1
+
+    def use_set(self, k: int):
+        """Make input set ``k`` the one the next step / upload works on (host-side pointer swap)."""
+        self._bind(self._sets[k])
 
     # ---- stages (asynchronous on the given stream) ---------------------------------------------------
     def assign(self, stream):
-        ops.match_encode(self.gt_boxes, self.gt_cls, self.gt_off, self.priors, self.batch, self.max_gt, self.thresh,
-                         want=(), out=self.tgt, stream=stream)
+        self._match_out = ops.match_encode(self.gt_boxes, self.gt_cls, self.gt_off, self.priors, self.batch, self.max_gt,
+                                           self.thresh, want=(), out=self.tgt, stream=stream, pool=self.pool)
 
     def loss_stage(self, stream, stats=False):
         if stats and self.staged is None:
             ops.multibox_loss(self.tgt["cls"], self.tgt["loc"], self.tgt["mask"], self.pred_box, self.pred_cls,
-                              self.neg_ratio, out=self.loss, stream=stream,
+                              self.neg_ratio, out=self.loss, stream=stream, pool=self.pool,
                               row_stats=(self.det_stats["row_ml"], self.det_stats["row_negbg"]))
             return
         if self.staged is not None:
             self.staged.stream = stream
             self.staged.row_stats = (self.det_stats["row_ml"], self.det_stats["row_negbg"]) if stats else None
-            for stage in range(4):
+            for stage in range(self.staged.n_stages):
                 self.staged.run(stage)
-                for buf in self.staged.exchange(stage):
-                    self.allreduce(buf, stream)
+                bufs = self.staged.exchange(stage)
+                if not bufs:
+                    continue
+                if self.comm is not None:
+                    self.comm.allreduce_multi(bufs, stream)       # one NCCL group per stage
+                else:
+                    for buf in bufs:
+                        self.allreduce(buf, stream)
             return
         ops.multibox_loss(self.tgt["cls"], self.tgt["loc"], self.tgt["mask"], self.pred_box, self.pred_cls,
-                          self.neg_ratio, out=self.loss, stream=stream)
+                          self.neg_ratio, out=self.loss, stream=stream, pool=self.pool)
 
     def detect_stage(self, stream, stage=None, stats=False, part=None):
         out = dict(self.det, **self.det_stats) if stats else self.det
         if part is None:
             ops.detect(self.pred_cls, self.pred_box, self.priors, self.score_thresh, self.top_k, self.iou_thresh,
-                       out=out, stream=stream, stage=stage, want_row_stats=stats)
+                       out=out, stream=stream, stage=stage, want_row_stats=stats, pool=self.pool)
             return
         # images [lo, hi) of the batch, with a workspace of their own
         lo = self.batch * part // self.detect_parts
@@ -111,7 +154,7 @@ class HotPath:
 
         ops.detect(rows(self.pred_cls), rows(self.pred_box), self.priors, self.score_thresh, self.top_k,
                    self.iou_thresh, out={k: rows(v) for k, v in out.items()}, stream=stream, stage=stage,
-                   want_row_stats=stats, ws_key="detect%d" % part)
+                   want_row_stats=stats, ws_key="detect%d" % part, pool=self.pool)
 
     def step(self):
         """One pass of the chain over the resident batch; work is ordered on ``s_main``.
@@ -165,8 +208,23 @@ class HotPath:
         D.stream_wait_event(self.s_main, self.ev_d)
 
     # ---- host-facing -------------------------------------------------------------------------------------
+    def _check_gt(self, gt_off):
+        """The reference matches every ground-truth box of every image (utils/bbox.py:44-91) and asserts T <= A
+        (:50): a batch this pipeline was not sized for is an error here, not a silent all-unmatched image."""
+        counts = np.diff(np.asarray(gt_off))
+        if counts.size != self.batch:
+            raise AssertionError("gt_off must have batch + 1 entries")
+        if counts.size and int(counts.min()) < 0:
+            raise ValueError("gt_off must be non-decreasing")
+        if counts.size and int(counts.max()) > self.A:
+            raise AssertionError("number of default boxes should greater than the number of targets")   # utils/bbox.py:50
+        if counts.size and int(counts.max()) > self.max_gt:
+            raise ValueError("an image has %d ground-truth boxes; this HotPath was built with max_gt=%d" %
+                             (int(counts.max()), self.max_gt))
+
     def upload(self, gt_boxes, gt_cls, gt_off, pred_cls, pred_box, stream=None):
         """Host (ideally pinned) -> device copies of one batch, asynchronous on ``stream`` (s_main)."""
+        self._check_gt(gt_off)
         st = self.s_main if stream is None else stream
         lib = N.lib()
         for dst, src in ((self.gt_boxes, gt_boxes), (self.gt_cls, gt_cls), (self.gt_off, gt_off),
@@ -185,18 +243,29 @@ class HotPath:
         lib = N.lib()
         for src, dst in ((self.loss["result"], out_result), (self.det["kept"], out_kept), (self.det["count"], out_count)):
             N.check(lib.ssdg_memcpy_d2h(dst.ctypes.data, src.ptr, src.nbytes, D.stream_handle(st)), "d2h")
+        if self._match_out is not None:      # the matcher's status word travels with the results (include/ssdgeom.h)
+            ws = self._match_out["_match_ws"]
+            N.check(lib.ssdg_memcpy_d2h(self._status_host.ptr, ws.ptr, 8, D.stream_handle(st)), "d2h")
+
+    def check_status(self, sync=False):
+        """Raise if the device had to skip an image or saw a stale prior index: from the status word the last
+        ``download`` brought back (after a synchronisation), or -- ``sync=True`` -- read now (synchronises)."""
+        if sync:
+            if self._match_out is not None:
+                ops.raise_for_match_status(ops.match_status(self._match_out, self.s_main))
+            return
+        ops.raise_for_match_status(int(self._status_host.array[1]))
 
     # Pipelined end to end: two device copies of the inputs, the H2D copy of batch k+1 (PCIe-bound, ~14 ms) runs on
     # its own stream under the compute and D2H of batch k.
-    def _input_sets(self):
-        if getattr(self, "_sets", None) is None:
-            names = ("gt_boxes", "gt_cls", "gt_off", "pred_cls", "pred_box")
-            first = {k: getattr(self, k) for k in names}
-            second = {k: D.empty(v.shape, v.dtype) for k, v in first.items()}
-            self._sets, self._n_sub = [first, second], 0
+    def _submit_state(self):
+        if getattr(self, "_sub", None) is None:
+            while len(self._sets) < 2:
+                self.add_input_set()
+            self._n_sub = 0
             self.s_copy = D.Stream()
             self.ev_up, self.ev_done, self._done_valid = [D.Event(), D.Event()], [D.Event(), D.Event()], [False, False]
-        return self._sets
+            self._sub = True
 
     def submit(self, host_in, host_out):
         """Enqueue one end-to-end step (host inputs -> host results) and return without waiting; call ``drain()``
@@ -204,12 +273,11 @@ class HotPath:
         to be kept.  Not available with cross-process mining (the staged loss holds its input buffers)."""
         if self.staged is not None:
             raise RuntimeError("submit() is not available with mining='global'; use step_host()")
-        sets = self._input_sets()
+        self._submit_state()
         slot = self._n_sub % 2
         if self._done_valid[slot]:      # the slot's inputs were read by the step two submits ago
             D.stream_wait_event(self.s_copy, self.ev_done[slot])
-        for k, v in sets[slot].items():
-            setattr(self, k, v)
+        self.use_set(slot)
         self.upload(*host_in, stream=self.s_copy)
         self.ev_up[slot].record(self.s_copy)
         D.stream_wait_event(self.s_main, self.ev_up[slot])
@@ -221,6 +289,7 @@ class HotPath:
 
     def drain(self):
         self.s_main.sync()
+        self.check_status()
 
     def step_host(self, gt_boxes, gt_cls, gt_off, pred_cls, pred_box, out_result, out_kept, out_count):
         """End to end: host inputs in, host results out (synchronises)."""
@@ -228,3 +297,4 @@ class HotPath:
         self.step()
         self.download(out_result, out_kept, out_count)
         self.s_main.sync()
+        self.check_status()

@@ -323,3 +323,27 @@ def test_filter_partial_sum_prefilter_is_necessary():
         must = p[:, :80] > 0.01 * (1 + 1e-5)
         assert not np.any(must & ~passed)
         assert passed.sum() < 2.2 * max(must.sum(), 1) or bias == 0.0
+
+
+# ---- the vectorised NMS restatement bench.py's CPU arm uses ------------------------------------------------------
+def test_iou_all_pairs_is_the_iou_formula_bit_for_bit():
+    rng = np.random.default_rng(3)
+    b = rng.normal(size=(4, 50, 4)).astype(np.float32)          # includes negative / tiny sizes
+    b[0, :5, 2:] = 0.0
+    with np.errstate(all="ignore"):
+        want = O.iou(b[:, :, None, :], b[:, None, :, :], dtype=np.float32)
+        got = O.iou_all_pairs(b)
+    assert got.dtype == np.float32 and np.array_equal(got, want, equal_nan=True)
+
+
+@pytest.mark.parametrize("bias,thr,topk,iou_thr", [(7.0, 0.01, 200, 0.45), (0.0, 0.01, 200, 0.45), (5.0, 0.02, 50, 0.3),
+                                                    (3.0, 0.5, 10, 0.6)])
+def test_nms_batched_equals_per_class(bias, thr, topk, iou_thr):
+    priors = O.build_prior_box()
+    pred_cls, pred_box = synth.make_predictions(77, 1, priors.shape[0], bg_bias=bias)
+    probs = O.softmax(pred_cls[0])
+    boxes = O.decode_bbox(pred_box[0] * np.float32(0.4), priors, scale=1.0, exp_dtype=np.float64)
+    k0, c0 = O.nms_per_class(probs, boxes, thr, topk, iou_thr)
+    k1, c1 = O.nms_per_class_batched(probs, boxes, thr, topk, iou_thr)
+    assert np.array_equal(c0, c1) and np.array_equal(k0, k1)
+    assert c0.sum() > 0 or thr >= 0.5

@@ -3,7 +3,7 @@ import numpy as np
 sys.path.insert(0, os.path.join(os.environ.get("GRAFT_REPO_ROOT", "."), "ssd-object-detection_b200"))
 from ssdgeom import device as D, synth
 from ssdgeom.pipeline import HotPath
-b = 256
+b = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 boxes, cls, off = synth.make_gt(100, b, 100, "max")
 hp = HotPath(synth.TABLES["ssd300"], batch=b, max_gt=100, total_gt=boxes.shape[0])
 pc = np.empty((b, hp.A, hp.classes), np.float32); pb = np.empty((b, hp.A, 4), np.float32)
@@ -18,4 +18,4 @@ for _ in range(30):
     hp.s_main.sync()
     t0 = time.perf_counter(); hp.step(); t1 = time.perf_counter()
     ts.append((t1 - t0) * 1e6)
-print("host enqueue per step: median %.1f us  min %.1f  max %.1f" % (statistics.median(ts), min(ts), max(ts)))
+print("batch", b, "host enqueue per step: median %.1f us  min %.1f  max %.1f" % (statistics.median(ts), min(ts), max(ts)))
