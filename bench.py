@@ -119,6 +119,24 @@ def _cpu_nms(task):
     return int(count.sum()), time.perf_counter() - t0
 
 
+def _cpu_loss(task):
+    """_ssd_loss on one slice of the batch: the reference's shipped configuration calls it per `split_batch` slice
+    of 4 images and averages (models/ssd_model.py:235-256, config/default.yml:40-42)."""
+    (table, lo, hi, y_true) = task
+    ref, _ = _worker_state(table)
+    pred_box, pred_cls = _W["pred"]
+    t0 = time.perf_counter()
+    if ref is not None:
+        total, _ = ref.ssd_loss(y_true, (pred_box[lo:hi], pred_cls[lo:hi]))              # models/ssd_model.py:341-396
+    else:
+        from oracle import ssd_oracle as O
+        total, _ = O.ssd_loss(y_true, (pred_box[lo:hi], pred_cls[lo:hi]))
+    return float(np.asarray(total)), time.perf_counter() - t0
+
+
+SPLIT_BATCH = 4          # config/default.yml:40-42
+
+
 class CpuArm:
     def __init__(self, args, images):
         import multiprocessing as mp
@@ -133,7 +151,7 @@ class CpuArm:
         pred_cls, pred_box = synth.make_predictions(1234, self.images, a)
         self.t_assign = [(args.table, cls[off[i]:off[i + 1]], boxes[off[i]:off[i + 1]]) for i in range(self.images)]
         self.t_nms = [(args.table, pred_cls[i], pred_box[i]) for i in range(self.images)]
-        self.pred = (pred_box, pred_cls)
+        _W["pred"] = (pred_box, pred_cls)            # inherited by the forked workers
         self.procs = min(self.cores, self.images)
         self.pool = mp.get_context("fork").Pool(self.procs)
         self.wall = {"assign": 0.0, "loss": 0.0, "nms": 0.0}
@@ -146,18 +164,17 @@ class CpuArm:
         res = self.pool.map(_cpu_assign, self.t_assign, chunksize=1)
         t1 = time.perf_counter()
         y_true = tuple(np.stack([r[k] for r in res]) for k in range(3))
-        if ref is not None:
-            total, _ = ref.ssd_loss(y_true, self.pred)                                # models/ssd_model.py:341-396
-        else:
-            from oracle import ssd_oracle as O
-            total, _ = O.ssd_loss(y_true, self.pred)
+        slices = [(self.table, lo, min(lo + SPLIT_BATCH, self.images), tuple(v[lo:lo + SPLIT_BATCH] for v in y_true))
+                  for lo in range(0, self.images, SPLIT_BATCH)]
+        losses = self.pool.map(_cpu_loss, slices, chunksize=1)
+        total = float(np.mean([l[0] for l in losses]))                                # accumulate-and-average, :251-256
         t2 = time.perf_counter()
         det = self.pool.map(_cpu_nms, self.t_nms, chunksize=1)
         t3 = time.perf_counter()
         if record:
             self.steps += 1
             self.wall["assign"] += t1 - t0; self.wall["loss"] += t2 - t1; self.wall["nms"] += t3 - t2
-            self.cpu["assign"] += sum(r[3] for r in res); self.cpu["loss"] += t2 - t1; self.cpu["nms"] += sum(d[1] for d in det)
+            self.cpu["assign"] += sum(r[3] for r in res); self.cpu["loss"] += sum(l[1] for l in losses); self.cpu["nms"] += sum(d[1] for d in det)
         return float(np.asarray(total))
 
     def close(self):
@@ -168,10 +185,11 @@ class CpuArm:
         n = self.images * max(self.steps, 1)
         wall_all = sum(self.wall.values())
         wall_ref = self.wall["assign"] + self.wall["loss"]
-        src = ("the reference's own match_bbox + apply_anchor_box per image and _ssd_loss on the sample (unmodified modules, "
+        src = ("the reference's own match_bbox + apply_anchor_box per image and _ssd_loss per split_batch slice of 4 "
+               "images, averaged (models/ssd_model.py:235-256, config/default.yml:40-42) (unmodified modules, "
                "byte-compiled from the reference tree; TensorFlow is absent, so its dozen ops run on a NumPy stand-in, "
                "oracle/tf_shim.py)") if self.kind == "reference" else \
-              "NumPy port of match_bbox + apply_anchor_box (the reference's arg-max sweeps) and _ssd_loss (oracle/ssd_oracle.py)"
+              "NumPy port of match_bbox + apply_anchor_box (the reference's arg-max sweeps) and _ssd_loss per slice of 4 images (oracle/ssd_oracle.py)"
         return {"value": n / wall_all if wall_all else 0.0, "unit": "images/s", "cores": self.procs, "kind": self.kind,
                 "sample": "%d %s images per step x %d steps (GT mode %s, <=%d GT): %s in a %d-process pool; plus the "
                           "builder-written decode + per-class NMS restatement (the reference has no NMS)" %

@@ -2,7 +2,7 @@
 ``/root/reference`` under the NumPy ``tensorflow`` shim (oracle/tf_shim.py).
 
 ``/root/reference`` exists only in the build container.  On the GPU box the same modules are imported from
-``oracle/_ref`` -- source-less ``.pyc`` files byte-compiled from ``/root/reference`` by ``oracle/build_ref.py``
+``oracle/_ref`` -- source-less byte-code files byte-compiled (``.rbc``) from ``/root/reference`` by ``oracle/build_ref.py``
 (git-ignored build artefacts that travel with the snapshot, like the built ``.so``).  It is used by
 
 * ``oracle/make_golden.py`` to generate ``tests/golden/*.npz``,
@@ -24,6 +24,9 @@ Reference entry points exposed (file:line in /root/reference):
 from __future__ import annotations
 
 import importlib
+import importlib.abc
+import importlib.machinery
+import importlib.util
 import os
 import sys
 import types
@@ -36,9 +39,31 @@ def root() -> str | None:
     """Where the reference's modules can be imported from: its source tree, else the byte-compiled copy."""
     if os.path.isfile(os.path.join(REFERENCE_ROOT, "utils", "bbox.py")):
         return REFERENCE_ROOT
-    if os.path.isfile(os.path.join(COMPILED_ROOT, "utils", "bbox.pyc")):
+    if os.path.isfile(os.path.join(COMPILED_ROOT, "utils", "bbox.rbc")):
         return COMPILED_ROOT
     return None
+
+
+class _CompiledFinder(importlib.abc.MetaPathFinder):
+    """Imports ``utils`` / ``models`` / ``data_loaders`` from the byte-code files oracle/build_ref.py wrote."""
+
+    def __init__(self, base):
+        self.base = base
+
+    def find_spec(self, fullname, path=None, target=None):
+        parts = fullname.split(".")
+        if parts[0] not in ("utils", "models", "data_loaders"):
+            return None
+        where = os.path.join(self.base, *parts)
+        init = os.path.join(where, "__init__.rbc")
+        if os.path.isfile(init):
+            return importlib.util.spec_from_file_location(
+                fullname, init, loader=importlib.machinery.SourcelessFileLoader(fullname, init),
+                submodule_search_locations=[where])
+        if os.path.isfile(where + ".rbc"):
+            return importlib.util.spec_from_file_location(
+                fullname, where + ".rbc", loader=importlib.machinery.SourcelessFileLoader(fullname, where + ".rbc"))
+        return None
 
 
 def available() -> bool:
@@ -63,12 +88,19 @@ def load():
     for name in list(sys.modules):
         if name.split(".")[0] in ("utils", "models", "data_loaders"):
             raise RuntimeError("a module named %r is already imported; cannot load the reference" % name)
-    sys.path.insert(0, where)
+    hook = _CompiledFinder(where) if where == COMPILED_ROOT else None
+    if hook is not None:
+        sys.meta_path.insert(0, hook)
+    else:
+        sys.path.insert(0, where)
     try:
         bbox = importlib.import_module("utils.bbox")
         ssd_model = importlib.import_module("models.ssd_model")
     finally:
-        sys.path.remove(where)
+        if hook is not None:
+            sys.meta_path.remove(hook)
+        else:
+            sys.path.remove(where)
     model_cls = ssd_model.SSDObjectDetectionModel
 
     def build_prior_box(size_list, input_size=300):

@@ -254,7 +254,7 @@ def multibox_loss(gt_cls, gt_box, gt_mask, pred_box, pred_cls, neg_ratio: int = 
     # models/ssd_model.py:347-351
     if not (gt_cls.size == b * a and gt_mask.size == b * a and gt_box.size == b * a * 4 and pred_box.size == b * a * 4):
         raise AssertionError("y_true / y_pred disagree in shape")
-    out = dict(out or {})
+    out = {k: (D.as_device(v) if D.is_device(v) else v) for k, v in (out or {}).items()}   # torch tensors etc.: zero-copy views
     if "result" not in out:
         out["result"] = D.empty((N.LOSS_RESULT_LEN,), np.float64)
     if want_neg_mask and "neg_mask" not in out:
