@@ -807,7 +807,8 @@ def report(args, R, comm, b, M, detail_cfg):
              "chain_hbm_roofline_frac": chain_bytes_per_image(a, c, fused) * b / (ms_step * 1e-3) / 1e9 / peak,
              "sustained": sustained,
              "exchange": ("ssdg_comm (libssdgeom NCCL entry points)" if comm is not None else "torch.distributed") if world > 1 else None,
-             "loss": ({"total": res[0], "num_pos": res[4], "num_neg": res[5], "status": res[7], "scope": "this rank"}
+             "loss": ({"total": res[0], "num_pos": res[4], "num_neg": res[5], "status": res[7],
+                       "scope": "this rank" if world == 1 else "total: this rank's shard; num_pos / num_neg: pooled over the ranks by the exchange"}
                       if args.mining == "shard" or world == 1 else
                       {"total": (res[8] + res[10]) / res[11] + res[9] / res[5], "num_pos": res[11], "num_neg": res[5],
                        "status": res[7], "scope": "all ranks (exact-global mining)"})}
