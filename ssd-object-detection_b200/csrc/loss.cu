@@ -487,9 +487,13 @@ __global__ void __launch_bounds__(256) final_kernel(LossParams P) {
 // ---- gradient (models/ssd_model.py:248 through :355-386) ---------------------------------------------
 //   d/d logits = softmax * (pos/Npos + neg/Nneg) - onehot(gt)*pos/Npos - onehot(bg)*neg/Nneg
 //   d/d pred_box = sign(pred - gt) * pos/Npos
-// One warp per prior row group, coalesced over the class axis; rows that are neither positive nor
-// mined negative are written as zeros without reading the logits.
-__global__ void __launch_bounds__(256) grad_kernel(LossParams P) {
+// The output is as large as the logits but only the positives and the mined negatives (a few percent of the rows each)
+// are non-zero: the array is zero-filled by a stream-ordered memset (write bandwidth, no read of the logits), and this
+// kernel then visits the non-zero rows only -- one warp per group of 32 priors finds them by ballot and computes them
+// row by row, the loads of up to four rows in flight at once.
+constexpr int kGradThreads = 256;
+
+__global__ void __launch_bounds__(kGradThreads) grad_kernel(LossParams P) {
   const double* r = P.result;
   const bool bad = r[7] != 0.0 || r[12] != 0.0;
   const float wpos = bad ? CUDART_NAN_F : (float)(1.0 / r[4]);
@@ -499,39 +503,96 @@ __global__ void __launch_bounds__(256) grad_kernel(LossParams P) {
   const int lane = threadIdx.x & 31;
   const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long n = gw; n < P.N; n += nw) {
-    const bool pos = P.gt_mask[n] != 0;
-    const bool neg = !bad && key32(P.neg_ce[n]) >= kth;
-    float* g = P.grad_cls + (size_t)n * C;
-    if (!(pos || neg) && !bad) {
-      for (int c = lane; c < C; c += 32) __stcs(&g[c], 0.f);
-    } else {
-      const float* x = P.pred_cls + (size_t)n * C;
-      float m = -CUDART_INF_F;
-      for (int c = lane; c < C; c += 32) m = fmaxf(m, x[c]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(SSDG_FULL, m, o));
-      float s = 0.f;
-      for (int c = lane; c < C; c += 32) s += __expf(x[c] - m);
-      s = warp_sum(s);
-      const float w = (pos ? wpos : 0.f) + (neg ? wneg : 0.f);
-      const float inv = w / s;
-      int lab = P.gt_cls[n];
-      lab = lab < 0 ? 0 : (lab >= C ? C - 1 : lab);   // (out-of-range labels make the whole result `bad`)
-      for (int c = lane; c < C; c += 32) {
-        float v = __expf(x[c] - m) * inv;
-        if (pos && c == lab) v -= wpos;
-        if (neg && c == C - 1) v -= wneg;
-        __stcs(&g[c], v);
-      }
-    }
-    if (lane < 4) {
-      float v = 0.f;
+  const long long groups = (P.N + 31) >> 5;
+  constexpr int kRows = 4;     // rows whose logits are loaded together
+  constexpr int kPer = 4;      // classes per lane held in registers (C <= 128; more classes take the plain loop)
+  for (long long g = gw; g < groups; g += nw) {
+    const long long n = (g << 5) + lane;
+    const bool in = n < P.N;
+    const bool pos = in && P.gt_mask[n] != 0;
+    const bool neg = in && !bad && key32(P.neg_ce[n]) >= kth;
+    if (in) {   // lane = row: d / d pred_box
+      float4 gb4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (pos) {
-        const float d = P.pred_box[n * 4 + lane] - P.gt_box[n * 4 + lane];
-        v = d > 0.f ? wpos : (d < 0.f ? -wpos : 0.f);
+        const float4 pb = __ldg(reinterpret_cast<const float4*>(P.pred_box) + n);
+        const float4 gb = __ldg(reinterpret_cast<const float4*>(P.gt_box) + n);
+        auto sg = [&](float d) { return d > 0.f ? wpos : (d < 0.f ? -wpos : 0.f); };
+        gb4 = make_float4(sg(pb.x - gb.x), sg(pb.y - gb.y), sg(pb.z - gb.z), sg(pb.w - gb.w));
       }
-      P.grad_box[n * 4 + lane] = v;
+      reinterpret_cast<float4*>(P.grad_box)[n] = gb4;
+    }
+    int lab = pos ? P.gt_cls[n] : 0;
+    lab = lab < 0 ? 0 : (lab >= C ? C - 1 : lab);   // (out-of-range labels make the whole result `bad`)
+    u32 act = __ballot_sync(SSDG_FULL, in && (pos || neg || bad));
+    while (act) {
+      int rows[kRows];
+      int nr = 0;
+#pragma unroll
+      for (int k = 0; k < kRows; ++k) {
+        rows[k] = -1;
+        if (act) { rows[k] = __ffs(act) - 1; act &= act - 1; ++nr; }
+      }
+      if (C <= 32 * kPer) {
+        float x[kRows][kPer];
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) {
+          const float* src = P.pred_cls + (size_t)((g << 5) + (rows[k] < 0 ? 0 : rows[k])) * C;
+#pragma unroll
+          for (int q = 0; q < kPer; ++q) {
+            const int c = lane + 32 * q;
+            x[k][q] = (rows[k] >= 0 && c < C) ? __ldg(src + c) : -CUDART_INF_F;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) {
+          if (rows[k] < 0) break;      // warp-uniform
+          const int rr = rows[k];
+          const bool rp = __shfl_sync(SSDG_FULL, (int)pos, rr) != 0, rn = __shfl_sync(SSDG_FULL, (int)neg, rr) != 0;
+          const int rl = __shfl_sync(SSDG_FULL, lab, rr);
+          float m = fmaxf(fmaxf(x[k][0], x[k][1]), fmaxf(x[k][2], x[k][3]));
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(SSDG_FULL, m, o));
+          float e[kPer], sum = 0.f;
+#pragma unroll
+          for (int q = 0; q < kPer; ++q) { e[q] = __expf(x[k][q] - m); sum += e[q]; }   // exp(-inf) = 0 beyond C
+          sum = warp_sum(sum);
+          const float w = (rp ? wpos : 0.f) + (rn ? wneg : 0.f);
+          const float inv = w / sum;
+          float* dst = P.grad_cls + (size_t)((g << 5) + rr) * C;
+#pragma unroll
+          for (int q = 0; q < kPer; ++q) {
+            const int c = lane + 32 * q;
+            if (c < C) {
+              float v = e[q] * inv;
+              if (rp && c == rl) v -= wpos;
+              if (rn && c == C - 1) v -= wneg;
+              __stcs(&dst[c], v);
+            }
+          }
+        }
+      } else {
+        for (int k = 0; k < nr; ++k) {
+          const int rr = rows[k];
+          const bool rp = __shfl_sync(SSDG_FULL, (int)pos, rr) != 0, rn = __shfl_sync(SSDG_FULL, (int)neg, rr) != 0;
+          const int rl = __shfl_sync(SSDG_FULL, lab, rr);
+          const float* x = P.pred_cls + (size_t)((g << 5) + rr) * C;
+          float m = -CUDART_INF_F;
+          for (int c = lane; c < C; c += 32) m = fmaxf(m, x[c]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(SSDG_FULL, m, o));
+          float sum = 0.f;
+          for (int c = lane; c < C; c += 32) sum += __expf(x[c] - m);
+          sum = warp_sum(sum);
+          const float inv = ((rp ? wpos : 0.f) + (rn ? wneg : 0.f)) / sum;
+          float* dst = P.grad_cls + (size_t)((g << 5) + rr) * C;
+          for (int c = lane; c < C; c += 32) {
+            float v = __expf(x[c] - m) * inv;
+            if (rp && c == rl) v -= wpos;
+            if (rn && c == C - 1) v -= wneg;
+            __stcs(&dst[c], v);
+          }
+        }
+      }
     }
   }
 }
@@ -628,8 +689,13 @@ static int loss_run(int stages, int global, long long n_all, const float* row_ml
   }
   if ((stages & 16) && grad_cls) {
     prof_begin(SSDG_PROF_GRAD, st);
-    int ggrid = sm_count() * 8;
-    grad_kernel<<<ggrid, 256, 0, st>>>(P);
+    SSDG_CUDA_TRY(cudaMemsetAsync(grad_cls, 0, (size_t)P.N * n_classes * sizeof(float), st));
+    {
+      int ggrid = sm_count() * 8;
+      const long long gneed = (((P.N + 31) >> 5) * 32 + kGradThreads - 1) / kGradThreads;
+      if (gneed < ggrid) ggrid = (int)(gneed > 0 ? gneed : 1);
+      grad_kernel<<<ggrid, kGradThreads, 0, st>>>(P);
+    }
     prof_end(SSDG_PROF_GRAD, st);
     SSDG_LAUNCH_CHECK();
   }

@@ -50,6 +50,8 @@ constexpr int kCandCap = 8192;          // listed (row, prior) pairs above the t
 constexpr int kABits = 21;
 constexpr int kMaxGT = 2048;
 constexpr int kTileSmemMax = 1024;      // tile statistics staged in shared memory up to this many tiles
+constexpr int kSuper = 8;               // tiles per super-tile (two-level bound of the row search)
+constexpr int kSuperRegs = kTileSmemMax / kSuper / 32;   // super-tile bounds a lane keeps in registers (4)
 constexpr int kElimSmemWords = 4096;    // 16 KB: bitmaps in shared memory up to 131072 priors
 
 struct TileStat {
@@ -86,6 +88,7 @@ struct MatchParams {
   int* ws_colt;             // per CTA A
   u32* ws_bits;             // per CTA 2*elim_words (knocked-out columns, touched columns) when not in smem
   const TileStat* tiles;    // [ntiles]
+  const TileStat* supers;   // [ceil(ntiles / kSuper)] statistics of kSuper consecutive tiles each
   const int* perm;          // [ntiles*32] slot -> prior index (-1: padding); NULL: identity
   const void* pprior;       // [ntiles*32,4] the priors in slot order (same dtype); NULL: gather through perm
   const float4* unmatched;  // [A] encoding of an all-zero box per prior; NULL: compute
@@ -215,6 +218,21 @@ __global__ void __launch_bounds__(256) tile_stats_kernel(const void* __restrict_
   if (lane == 0) out[tile] = st;
 }
 
+// statistics of kSuper consecutive tiles: every field moves the way that can only raise the tile bound
+__global__ void __launch_bounds__(128) super_stats_kernel(const TileStat* __restrict__ tiles, int ntiles, TileStat* __restrict__ out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s * kSuper >= ntiles) return;
+  TileStat u = tiles[s * kSuper];
+  for (int k = 1; k < kSuper && s * kSuper + k < ntiles; ++k) {
+    const TileStat v = tiles[s * kSuper + k];
+    u.x1 = fminf(u.x1, v.x1); u.y1 = fminf(u.y1, v.y1); u.x2 = fmaxf(u.x2, v.x2); u.y2 = fmaxf(u.y2, v.y2);
+    u.wmax = fmaxf(u.wmax, v.wmax); u.hmax = fmaxf(u.hmax, v.hmax); u.amin = fminf(u.amin, v.amin);
+    u.safe = u.safe & v.safe;
+    u.cx1 = fminf(u.cx1, v.cx1); u.cy1 = fminf(u.cy1, v.cy1); u.cx2 = fmaxf(u.cx2, v.cx2); u.cy2 = fmaxf(u.cy2, v.cy2);
+  }
+  out[s] = u;
+}
+
 // encoding of an all-zero (unmatched) box against every prior (utils/bbox.py:85,98-99)
 template <typename TP>
 __global__ void __launch_bounds__(256) unmatched_kernel(const void* __restrict__ priors, int A, float4* __restrict__ out) {
@@ -276,16 +294,14 @@ static size_t match_smem_bytes(int tm, int ntiles_s, int bit_words) {
 constexpr int kSearchThreads = 128;
 constexpr int kSearchWarps = kSearchThreads / 32;
 
-template <typename TG, typename TP, bool kCached>   // kCached: per-warp shared-memory cache of the row's tile bounds
+template <typename TG, typename TP, bool kHier>   // kHier: two-level bound (super-tiles of kSuper tiles, then tiles); up to kTileSmemMax tiles
 __global__ void __launch_bounds__(kSearchThreads, 8) search_kernel(MatchParams P) {
   typedef typename Promote<TG, TP>::type R;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x & 31;
   const int A = P.A, ntiles = P.ntiles;
-  constexpr bool cached = kCached;
   // the tile statistics stay in global memory (L1/L2-resident, 14 KB for SSD300): staging them per CTA costs
   // shared memory that decides how many of these CTAs fit beside a streaming kernel of the other branch
-  float* ubw = reinterpret_cast<float*>(smem_raw) + (size_t)warp * (cached ? ntiles : 0);
   const TileStat* tiles = P.tiles;
   const R EPS = (R)1e-10;
   const u64 thr_key = key64((double)(R)P.thresh);
@@ -362,6 +378,64 @@ __global__ void __launch_bounds__(kSearchThreads, 8) search_kernel(MatchParams P
         rowlo = fmaxf(f_down(unkey64((u64)mhi << 32)), 0.f);
       }
     };
+    auto tile_ub = [&](const TileStat& ts) {
+      float iub, dlb;
+      iou_bound(gb, galo, ts, iub, dlb);
+      return (ts.safe && dlb > 0.f) ? __fdividef(iub, dlb) * 1.0002f : CUDART_INF_F;   // always > 0
+    };
+    if (kHier) {
+      // Two levels.  A ground-truth box can reach min(thresh, its row maximum) only in a handful of the ~300 tiles, and
+      // tiles are ordered shape by shape, block by block: bounding kSuper consecutive tiles at once (their joint
+      // statistics) discards most of them in one test.  Lane l keeps the bounds of super-tiles l, 32 + l, ... in registers.
+      const int nsuper = (ntiles + kSuper - 1) / kSuper;
+      float sub[kSuperRegs];
+      float smax = -1.f;
+      int sbest = 0x7fffffff;
+#pragma unroll
+      for (int q = 0; q < kSuperRegs; ++q) {
+        const int sp = q * 32 + lane;
+        sub[q] = -1.f;                          // < 0: nothing pending
+        if (sp < nsuper) {
+          sub[q] = tile_ub(P.supers[sp]);
+          if (sub[q] > smax) { smax = sub[q]; sbest = sp; }
+        }
+      }
+      {
+        const u32 m = __reduce_max_sync(SSDG_FULL, key32(smax));
+        sbest = (int)__reduce_min_sync(SSDG_FULL, key32(smax) == m ? (u32)sbest : 0x7fffffffu);
+      }
+      // the member tile with the highest bound of the best super-tile seeds the running maximum
+      int stile;
+      {
+        const int tile = sbest * kSuper + (lane & (kSuper - 1));
+        const float ub = (lane < kSuper && tile < ntiles) ? tile_ub(tiles[tile]) : -1.f;
+        const u32 m = __reduce_max_sync(SSDG_FULL, key32(ub));
+        stile = (int)__reduce_min_sync(SSDG_FULL, key32(ub) == m ? (u32)tile : 0x7fffffffu);
+      }
+      evaluate(stile);
+      // every super-tile whose bound still reaches min(thresh, running maximum): its members, same test
+#pragma unroll
+      for (int q = 0; q < kSuperRegs; ++q) {
+        if (q * 32 >= nsuper) break;
+        for (;;) {
+          const bool reach = sub[q] >= 0.f && !(sub[q] < fminf(thr_lo, rowlo));
+          const u32 m = __ballot_sync(SSDG_FULL, reach);
+          if (!m) break;
+          const int l = __ffs(m) - 1;
+          if (lane == l) sub[q] = -1.f;
+          const int tile = (q * 32 + l) * kSuper + (lane & (kSuper - 1));
+          float ub = (lane < kSuper && tile < ntiles && tile != stile) ? tile_ub(tiles[tile]) : -1.f;
+          for (;;) {
+            const bool r2 = ub >= 0.f && !(ub < fminf(thr_lo, rowlo));
+            const u32 m2 = __ballot_sync(SSDG_FULL, r2);
+            if (!m2) break;
+            const int l2 = __ffs(m2) - 1;
+            if (lane == l2) ub = -1.f;
+            evaluate((q * 32 + l) * kSuper + l2);
+          }
+        }
+      }
+    } else {
     // pass 1: bound every tile; the highest bound seeds the running maximum
     float sub = -1.f;
     int stile = 0x7fffffff;
@@ -369,11 +443,7 @@ __global__ void __launch_bounds__(kSearchThreads, 8) search_kernel(MatchParams P
     for (int tb = 0; tb < ntiles; tb += 32) {
       const int tile = tb + lane;
       if (tile < ntiles) {
-        const TileStat ts = tiles[tile];
-        float iub, dlb;
-        iou_bound(gb, galo, ts, iub, dlb);
-        const float ub = (ts.safe && dlb > 0.f) ? __fdividef(iub, dlb) * 1.0002f : CUDART_INF_F;
-        if (cached) ubw[tile] = ub;
+        const float ub = tile_ub(tiles[tile]);
         if (ub > sub) { sub = ub; stile = tile; }
       }
     }
@@ -387,21 +457,19 @@ __global__ void __launch_bounds__(kSearchThreads, 8) search_kernel(MatchParams P
     for (int tb = 0; tb < ntiles; tb += 32) {
       const int tile = tb + lane;
       bool pending = tile < ntiles && tile != stile;
-      float ub = 0.f;
       TileStat ts;
       ts.x1 = ts.y1 = ts.x2 = ts.y2 = ts.wmax = ts.hmax = ts.amin = ts.cx1 = ts.cy1 = ts.cx2 = ts.cy2 = 0.f; ts.safe = 1u;
-      if (pending) {
-        if (cached) ub = ubw[tile]; else ts = tiles[tile];
-      }
+      if (pending) ts = tiles[tile];
       for (;;) {
         const float bound = fminf(thr_lo, rowlo);
-        const bool reach = pending && (cached ? !(ub < bound) : may_reach(gb, galo, ts, bound));
+        const bool reach = pending && may_reach(gb, galo, ts, bound);
         const u32 m = __ballot_sync(SSDG_FULL, reach);
         if (!m) break;
         const int l = __ffs(m) - 1;
         if (lane == l) pending = false;
         evaluate(tb + l);
       }
+    }
     }
     warp_argmax_u64(best_key, best_a);
     if (lane == 0) {
@@ -844,6 +912,8 @@ static int launch_match(const MatchParams& P, int grid, size_t smem, cudaStream_
   if (!P.perm) {
     tile_stats_kernel<TP><<<(P.ntiles * 32 + 255) / 256, 256, 0, st>>>(P.priors, P.A, nullptr, P.ntiles,
                                                                        const_cast<TileStat*>(P.tiles));
+    const int nsuper = (P.ntiles + kSuper - 1) / kSuper;
+    super_stats_kernel<<<(nsuper + 127) / 128, 128, 0, st>>>(P.tiles, P.ntiles, const_cast<TileStat*>(P.supers));
     SSDG_LAUNCH_CHECK();
   }
   if (smem > 48 * 1024)
@@ -852,9 +922,13 @@ static int launch_match(const MatchParams& P, int grid, size_t smem, cudaStream_
   SSDG_CUDA_TRY(cudaFuncSetAttribute(match_kernel<TG, TP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   prof_begin(SSDG_PROF_MATCH, st);
   {
-    const bool cached = P.ntiles <= kTileSmemMax;
-    const size_t ssm = cached ? (size_t)P.ntiles * kSearchWarps * 4 : 0;
-    auto skern = cached ? search_kernel<TG, TP, true> : search_kernel<TG, TP, false>;
+#ifdef SSDG_SEARCH_FLAT
+    const bool hier = false;
+#else
+    const bool hier = P.ntiles <= kTileSmemMax;
+#endif
+    const size_t ssm = 0;
+    auto skern = hier ? search_kernel<TG, TP, true> : search_kernel<TG, TP, false>;
     SSDG_CUDA_TRY(cudaFuncSetAttribute(skern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     static const char* env = getenv("SSDG_SEARCH_CTAS_PER_SM");   // experiment knob
     long long sgrid = (long long)sm_count() * (env ? atoi(env) : 8);
@@ -888,6 +962,7 @@ struct MatchWs {
   int* colt;
   u32* bits;
   TileStat* tiles;
+  TileStat* supers;
 };
 static int match_tm(int max_gt) {
   const int tm = ((max_gt + 31) / 32) * 32;
@@ -915,6 +990,8 @@ static size_t match_ws_layout(int batch, int n_priors, int max_gt, int ctas, Mat
   o += align_up((size_t)ctas * 2 * words * 4, 256);
   if (out) out->tiles = (TileStat*)(base + o);
   o += align_up(words * sizeof(TileStat), 256);
+  if (out) out->supers = (TileStat*)(base + o);
+  o += align_up((words / kSuper + 1) * sizeof(TileStat), 256);
   return o;
 }
 
@@ -928,8 +1005,11 @@ static std::unordered_map<const void*, IndexInfo> g_index;   // index device poi
 static size_t index_slots(int n_priors) { return ((size_t)n_priors + 31) / 32 * 32 + (size_t)kIndexMaxShapes * 32; }
 static size_t index_perm_offset() { return 256; }
 static size_t index_tiles_offset(int n_priors) { return 256 + align_up(index_slots(n_priors) * 4, 256); }
-static size_t index_unmatched_offset(int n_priors) {
+static size_t index_supers_offset(int n_priors) {
   return index_tiles_offset(n_priors) + align_up(index_slots(n_priors) / 32 * sizeof(TileStat), 256);
+}
+static size_t index_unmatched_offset(int n_priors) {
+  return index_supers_offset(n_priors) + align_up((index_slots(n_priors) / 32 / kSuper + 1) * sizeof(TileStat), 256);
 }
 static size_t index_pprior_offset(int n_priors) { return index_unmatched_offset(n_priors) + align_up((size_t)n_priors * 16, 256); }
 
@@ -1015,6 +1095,7 @@ extern "C" int ssdg_prior_index_build(const void* priors, int32_t prior_dtype, i
     SSDG_CUDA_TRY(cudaStreamSynchronize(st));
   }
   TileStat* tiles = (TileStat*)(base + index_tiles_offset(n_priors));
+  TileStat* supers = (TileStat*)(base + index_supers_offset(n_priors));
   float4* unmatched = (float4*)(base + index_unmatched_offset(n_priors));
   const int* dperm = (const int*)(base + index_perm_offset());
   if (prior_dtype == SSDG_F64) {
@@ -1024,6 +1105,7 @@ extern "C" int ssdg_prior_index_build(const void* priors, int32_t prior_dtype, i
     tile_stats_kernel<float><<<(ntiles * 32 + 255) / 256, 256, 0, st>>>(priors, n_priors, dperm, ntiles, tiles);
     unmatched_kernel<float><<<(n_priors + 255) / 256, 256, 0, st>>>(priors, n_priors, unmatched);
   }
+  super_stats_kernel<<<((ntiles + kSuper - 1) / kSuper + 127) / 128, 128, 0, st>>>(tiles, ntiles, supers);
   SSDG_LAUNCH_CHECK();
   SSDG_CUDA_TRY(cudaStreamSynchronize(st));
   u64 sum = 0ull;
@@ -1077,7 +1159,7 @@ extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const f
   P.out_cls = out_cls; P.out_box = out_box; P.out_loc = out_loc; P.out_mask = out_mask; P.out_match = out_match;
   P.elim_words = (n_priors + 31) / 32;
   P.ws_head = ws.head; P.ws_ncand = ws.ncand; P.ws_rowkey = ws.rowkey; P.ws_rowcol = ws.rowcol; P.ws_cand = ws.cand; P.ws_colkey = ws.colkey; P.ws_colt = ws.colt; P.ws_bits = ws.bits;
-  P.tiles = ws.tiles; P.perm = nullptr; P.unmatched = nullptr; P.pprior = nullptr; P.ntiles = (n_priors + 31) / 32;
+  P.tiles = ws.tiles; P.supers = ws.supers; P.perm = nullptr; P.unmatched = nullptr; P.pprior = nullptr; P.ntiles = (n_priors + 31) / 32;
   P.index_sum = 0ull;
   P.prior_words = (long long)n_priors * 4 * (prior_dtype == SSDG_F64 ? 8 : 4) / 8;
   if (prior_index) {
@@ -1096,6 +1178,7 @@ extern "C" int ssdg_match_encode(const void* gt_boxes, int32_t gt_dtype, const f
     const unsigned char* ib = (const unsigned char*)prior_index;
     P.perm = (const int*)(ib + index_perm_offset());
     P.tiles = (const TileStat*)(ib + index_tiles_offset(n_priors));
+    P.supers = (const TileStat*)(ib + index_supers_offset(n_priors));
     P.unmatched = (const float4*)(ib + index_unmatched_offset(n_priors));
     P.pprior = ib + index_pprior_offset(n_priors);
     P.ntiles = info.ntiles;

@@ -42,17 +42,23 @@ class HotPath:
                     "mask": D.empty((b, a), np.uint8)}
         self.loss = {"result": D.empty((N.LOSS_RESULT_LEN,), np.float64)}
         self.det = {"kept": D.empty((b, c - 1, self.top_k), np.int32), "count": D.empty((b, c - 1), np.int32)}
-        # the post-processing branch is the longer one: its CTAs are scheduled first, the assignment/loss
-        # branch fills the gaps
-        self.s_main, self.s_a, self.s_d = D.Stream(), D.Stream("low"), D.Stream("high")
-        self.s_n, self.s_l = D.Stream("low"), D.Stream("high")
+        # filter + bucketing, the matcher and the loss at high priority, the NMS (20 480 small CTAs that would otherwise
+        # occupy every SM ahead of everything else) at low.  With the matcher at low priority a step of 128 images per
+        # GPU -- where the assignment chain is the longer one -- took 0.370 instead of 0.347 ms; at 256 images there is
+        # no difference (profiles/r15_stream_priorities.txt).
+        import os
+
+        def prio(name, default):          # SSDGEOM_PRIO_A / _D / _N / _L: "high", "low" or levels below the highest (measurements)
+            v = os.environ.get("SSDGEOM_PRIO_" + name, default)
+            return int(v) if v.lstrip("-").isdigit() else v
+        self.s_main, self.s_a, self.s_d = D.Stream(), D.Stream(prio("A", "high")), D.Stream(prio("D", "high"))
+        self.s_n, self.s_l = D.Stream(prio("N", "low")), D.Stream(prio("L", "high"))
         self.s_x, self.ev_x, self._x_pending = D.Stream("high"), D.Event(), False   # loss exchange (data parallel)
         self.ev_begin, self.ev_a, self.ev_d, self.ev_mid, self.ev_m = (D.Event() for _ in range(5))
         self.split = True
         # the post-processing chain can run in `detect_parts` slices of the batch: the NMS of a slice then overlaps
         # the filter pass of the next one (kernels bound by different resources) instead of waiting for the whole
         # batch.  SSDGEOM_DETECT_PARTS overrides for measurements.
-        import os
         self.detect_parts = max(1, min(int(os.environ.get("SSDGEOM_DETECT_PARTS", "1")), self.batch))
         self.ev_parts = [D.Event() for _ in range(self.detect_parts)]
         # one pass over the logits serves both branches: the filter leaves per-prior softmax statistics and the
