@@ -346,14 +346,22 @@ __global__ void SSDG_FILTER_BOUNDS filter_kernel(DetectParams P, int warps_per_c
   // One tile in flight per warp; the other 15 warps of the CTA hide its latency.  That alone leaves too few bytes in
   // flight towards DRAM (a buffer that is being computed on requests nothing): the warp also asks L2 for the tile it
   // will load `prefetch` rounds later, so the bulk copy into shared memory finds its lines in L2.
-  auto prefetch_tile = [&](long long t) {  // lane 0 only
-    if (t >= ntiles) return;
-    const int ib = (int)(t / tpi), ij = (int)(t - (long long)ib * tpi);
+  // (image, tile) of the tile `prefetch` + 1 rounds ahead, walked like (b, j)
+  int pb = 0, pj = 0;
+  {
+    const long long tp = gw + (long long)(prefetch + 1) * stride;
+    pb = (int)(tp / tpi); pj = (int)(tp - (long long)pb * tpi);
+  }
+  auto prefetch_at = [&](int ib, int ij) {  // lane 0 only
+    if (ib >= P.B) return;
     prefetch_l2_bulk(P.pred_cls + ((size_t)ib * A + (size_t)ij * 32) * C, (u32)min(32, A - ij * 32) * (u32)C * 4u);
   };
   if (P.tma_ok && lane == 0 && gw < ntiles) {
     issue(b, j);
-    for (int d = 1; d <= prefetch; ++d) prefetch_tile(gw + d * stride);
+    for (int d = 1; d <= prefetch; ++d) {
+      const long long tp = gw + d * stride;
+      prefetch_at((int)(tp / tpi), (int)(tp % tpi));
+    }
   }
   int k = 0;
   for (long long t = gw; t < ntiles; t += stride, ++k) {
@@ -378,8 +386,10 @@ __global__ void SSDG_FILTER_BOUNDS filter_kernel(DetectParams P, int warps_per_c
     if (j >= tpi) { j -= tpi; ++b; }
     if (P.tma_ok && lane == 0 && t + stride < ntiles) {
       issue(b, j);
-      if (prefetch > 0) prefetch_tile(t + (long long)(prefetch + 1) * stride);
+      if (prefetch > 0) prefetch_at(pb, pj);
     }
+    pb += step_b; pj += step_j;
+    if (pj >= tpi) { pj -= tpi; ++pb; }
   }
 }
 
