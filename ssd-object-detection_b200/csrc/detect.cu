@@ -497,6 +497,10 @@ struct NmsParams {
   int* out_kept;
   int* out_count;
   float* out_score;
+  // host-computed constants of the join (nms2_kernel)
+  int B;
+  int fast_ok;         // 0 < iou_thresh < 1e6: the division-free pre-test exists
+  float q, tq0, inv_l; // thr/(1+thr); shrink factor of the slab intervals; 1 / log2 of the size-class ratio
 };
 
 // The NMS kernel is instruction-cache sensitive (12 CTAs per SM in different phases): its block-stride loops
@@ -944,6 +948,466 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
   if (tid == 0) P.out_count[list] = total;
 }
 
+// ---- per-(image, class) NMS, second generation ------------------------------------------------------------
+// Same algorithm and the same exactness arguments as nms_kernel above (select, bucketed rank sort, slab interval
+// join with size classes, cheap float test with a margin, the IEEE formula for the survivors, fixed-point
+// resolution) with the instruction count cut where the profile showed it (profiles/r20_*: 8.7 k warp-instructions
+// per list, 78 % issue utilisation -- the kernel is issue-bound):
+//   * the join only ANDs the six table words per (row, column word) and PUSHES the surviving candidate pairs into a
+//     per-warp queue (ballot + popc, no atomics); the pair tests then run densely, one pair per thread, instead of
+//     every lane looping over its own candidates (the loop ran to the longest lane: 47 trips of 22 instructions for
+//     198 pairs per list).  A full queue tests the pair in place -- no input can overflow anything.
+//   * only the rare real suppressions touch the matrix (atomicOr into a zeroed triangle) and an `open rows` bitset;
+//     rows that stay closed are kept at once, the open ones are listed by the resolving warp.
+//   * row groups are dealt to the warps in pairs (last + first, ...): the triangular join costs g+1 words for group
+//     g, so every warp gets the same number of word steps.
+//   * thresholds, shrink factor and class scale come from the host; the slab scale is an approximate reciprocal
+//     (any positive scale keeps the slab map monotone, which is all the join needs).
+template <int kW>   // kW: words of 32 rows (top_k rounded up / 32) as a constant, 0 = any
+__global__ void __launch_bounds__(kNmsThreads, 12) nms2_kernel(NmsParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sortn = P.sortn, mcap = (P.top_k + 31) & ~31, W = mcap >> 5, RL = (4 * W) | 1;
+  const int RS = (2 * W) | 1;
+  const int tabn = (max(512, kSlabs * RL) + kSizeCls * RS + 3) & ~3;   // words, whole uint4s
+  const int supn = 16 * W * (W + 1);
+  u64* keys = reinterpret_cast<u64*>(smem_raw);                 // [sortn]
+  float4* crn = reinterpret_cast<float4*>(keys + sortn);        // [mcap] x1,y1,x2,y2 (sort scratch: sortn keys)
+  u32* hist = reinterpret_cast<u32*>(crn + mcap);               // [256] sort / select histogram
+  u32* bstart = hist + 256;                                     // [256] rank sort: first slot of each bucket
+  u32* tab = hist;                                              // [kSlabs][RL] interval tables of the join (after the sort)
+  u32* stab = tab + max(512, kSlabs * RL);                      // [kSizeCls][RS] width / height class neighbourhoods
+  float* qlo = reinterpret_cast<float*>(tab + tabn);            // [mcap] q*area*0.9999
+  float* area = qlo + mcap;                                     // [mcap]
+  u32* slidx = reinterpret_cast<u32*>(area + mcap);             // [mcap] slab intervals and size classes of the box
+  u32* sup = slidx + mcap;                                      // lower triangle, [group g][word w <= g][row of the group]
+  u32* unres = sup + supn;                                      // [mcap] the open rows, listed
+  float* dom = reinterpret_cast<float*>(unres + mcap);          // [4*kNmsWarps] per-warp extents of the boxes
+  u32* mm = reinterpret_cast<u32*>(dom + 4 * kNmsWarps);        // [4*kNmsWarps] per-warp min/max of the score and prior words
+  u32* keptw = mm + 4 * kNmsWarps;                              // [W]
+  u32* remw = keptw + W;                                        // [W]
+  u32* openw = remw + W;                                        // [W] rows with at least one suppressor
+  __shared__ u64 sel_prefix;
+  __shared__ int sel_k, sel_fill;
+
+  const int b = (int)(blockIdx.z * 65535u + blockIdx.y);        // grid (class, image mod 65535, image / 65535)
+  if (b >= P.B) return;
+  const size_t list = (size_t)b * P.n_fg + blockIdx.x;
+  int n = (int)P.cls_cnt[list];
+  const bool selected = n > P.sortn;   // more candidates than the sort takes: radix select first
+  const u64* cl = P.sorted + (size_t)b * P.img_stride + P.cls_off[list];
+
+  u32 hmin = ~0u, hmax = 0u, lmin = ~0u, lmax = 0u;   // range of the score and prior words of the keys
+  if (n <= sortn) {
+    NMS_LOOP
+    for (int i = tid; i < n; i += kNmsThreads) {
+      const u64 v = cl[i];
+      keys[i] = v;
+      hmin = min(hmin, (u32)(v >> 32)); hmax = max(hmax, (u32)(v >> 32));
+      lmin = min(lmin, (u32)v); lmax = max(lmax, (u32)v);
+    }
+  } else {
+    // Radix select of the top_k-th largest composite key (keys are unique), 8 bits per pass.
+    if (tid == 0) { sel_prefix = 0ull; sel_k = P.top_k; sel_fill = 0; }
+    __syncthreads();
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      NMS_LOOP
+      for (int i = tid; i < 256; i += kNmsThreads) hist[i] = 0u;
+      __syncthreads();
+      const u64 pre = sel_prefix;
+      const u64 hmask = shift == 56 ? 0ull : (~0ull << (shift + 8));
+      NMS_LOOP
+      for (int i = tid; i < n; i += kNmsThreads) {
+        const u64 v = cl[i];
+        if ((v & hmask) == pre) atomicAdd(&hist[(u32)(v >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int k = sel_k, acc = 0, d = 255;
+        for (; d > 0; --d) {
+          if (acc + (int)hist[d] >= k) break;
+          acc += (int)hist[d];
+        }
+        sel_k = k - acc;
+        sel_prefix = pre | ((u64)d << shift);
+      }
+      __syncthreads();
+    }
+    const u64 kth = sel_prefix;
+    NMS_LOOP
+    for (int i = tid; i < n; i += kNmsThreads) {
+      const u64 v = cl[i];
+      if (v >= kth) {
+        const int p = atomicAdd(&sel_fill, 1);
+        if (p < sortn) keys[p] = v;
+      }
+    }
+    __syncthreads();
+    n = min(sel_fill, sortn);
+  }
+  // Rank sort, descending (keys are unique): see nms_kernel.
+  {
+    u64* tmp = reinterpret_cast<u64*>(crn);   // [n] keys grouped by bucket; crn is filled after the sort
+    NMS_LOOP
+    for (int i = tid; i < 256; i += kNmsThreads) hist[i] = 0u;
+    if (selected) {   // the keys came out of the select: scan them
+      NMS_LOOP
+      for (int i = tid; i < n; i += kNmsThreads) {
+        const u64 v = keys[i];
+        hmin = min(hmin, (u32)(v >> 32)); hmax = max(hmax, (u32)(v >> 32));
+        lmin = min(lmin, (u32)v); lmax = max(lmax, (u32)v);
+      }
+    }
+    hmin = __reduce_min_sync(SSDG_FULL, hmin); hmax = __reduce_max_sync(SSDG_FULL, hmax);
+    lmin = __reduce_min_sync(SSDG_FULL, lmin); lmax = __reduce_max_sync(SSDG_FULL, lmax);
+    if (lane == 0) reinterpret_cast<uint4*>(mm)[warp] = make_uint4(hmin, hmax, lmin, lmax);
+    __syncthreads();
+    {
+      const uint4 p0 = reinterpret_cast<const uint4*>(mm)[0];
+      hmin = p0.x; hmax = p0.y; lmin = p0.z; lmax = p0.w;
+#pragma unroll
+      for (int w = 1; w < kNmsWarps; ++w) {
+        const uint4 pw = reinterpret_cast<const uint4*>(mm)[w];
+        hmin = min(hmin, pw.x); hmax = max(hmax, pw.y); lmin = min(lmin, pw.z); lmax = max(lmax, pw.w);
+      }
+    }
+    const bool byscore = hmax > hmin;
+    const u32 kbase = byscore ? hmin : lmin;
+    const float kscale = __fdividef(256.f, (float)((byscore ? hmax : lmax) - kbase) + 1.f) * 0.999f;   // any monotone map sorts
+    auto bucket = [&](u64 v) {   // conversions, the product and the truncation are all monotone
+      const u32 x = (byscore ? (u32)(v >> 32) : (u32)v) - kbase;
+      return min(255, (int)((float)x * kscale));
+    };
+    NMS_LOOP
+    for (int i = tid; i < n; i += kNmsThreads) atomicAdd(&hist[bucket(keys[i])], 1u);
+    __syncthreads();
+    if (warp == 0) {   // start[b] = number of keys in buckets above b; lane l owns buckets 255-8l .. 248-8l
+      u32 c[8], tot = 0u;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { c[r] = hist[255 - 8 * lane - r]; tot += c[r]; }
+      u32 incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 v = __shfl_up_sync(SSDG_FULL, incl, o);
+        if (lane >= o) incl += v;
+      }
+      u32 run = incl - tot;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { bstart[255 - 8 * lane - r] = run; hist[255 - 8 * lane - r] = run; run += c[r]; }
+    }
+    __syncthreads();
+    NMS_LOOP
+    for (int i = tid; i < n; i += kNmsThreads) {
+      const u64 v = keys[i];
+      tmp[atomicAdd(&hist[bucket(v)], 1u)] = v;   // hist[b] ends as the end of bucket b
+    }
+    __syncthreads();
+    NMS_LOOP
+    for (int i = tid; i < n; i += kNmsThreads) {
+      const u64 v = tmp[i];
+      const int bk = bucket(v);
+      const int s0 = (int)bstart[bk], s1 = (int)hist[bk];
+      int r = s0;
+      for (int t = s0; t < s1; ++t) r += tmp[t] > v;
+      keys[r] = v;
+    }
+    __syncthreads();
+  }
+  const int m = min(n, P.top_k);
+  const int mpad = (m + 31) & ~31;
+  const int ngroups = mpad >> 5;
+
+  // Decoded boxes; corners in the formula's own float32 operations (utils/bbox.py:13-21); see nms_kernel.
+  const float thr = P.iou_thresh;
+  const bool fast_ok = P.fast_ok != 0;
+  const float q = P.q;
+  int inexact = 0;
+  float x1 = CUDART_INF_F, y1 = CUDART_INF_F, x2 = -CUDART_INF_F, y2 = -CUDART_INF_F;   // extents of the sane boxes
+  NMS_LOOP
+  for (int i = tid; i < mpad; i += kNmsThreads) {
+    float4 cr = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ar = 0.f, qa = CUDART_INF_F;
+    if (i < m) {
+      const int a = (int)(~(u32)keys[i]);
+      const float4 bx = __ldg(reinterpret_cast<const float4*>(P.boxes) + (size_t)b * P.A + a);
+      const float hw = __fmul_rn(bx.z, 0.5f), hh = __fmul_rn(bx.w, 0.5f);
+      cr = make_float4(__fsub_rn(bx.x, hw), __fsub_rn(bx.y, hh), __fadd_rn(bx.x, hw), __fadd_rn(bx.y, hh));
+      ar = __fmul_rn(bx.z, bx.w);
+      const bool sane = bx.z > 0.f && bx.w > 0.f && isfinite(cr.x) && isfinite(cr.y) && isfinite(cr.z) &&
+                        isfinite(cr.w) && isfinite(ar);
+      if (sane) {
+        qa = q * (ar + 0.5e-10f);
+        const float pr = (cr.z - cr.x) * (cr.w - cr.y);
+        inexact |= !(ar >= 0.999f * pr && ar <= 1.001f * pr);
+        x1 = fminf(x1, cr.x); y1 = fminf(y1, cr.y); x2 = fmaxf(x2, cr.z); y2 = fmaxf(y2, cr.w);
+      }
+    }
+    crn[i] = cr;
+    area[i] = ar;
+    qlo[i] = qa * 0.9999f;
+  }
+  {
+    const u32 k1 = __reduce_min_sync(SSDG_FULL, key32(x1)), k2 = __reduce_min_sync(SSDG_FULL, key32(y1));
+    const u32 k3 = __reduce_max_sync(SSDG_FULL, key32(x2)), k4 = __reduce_max_sync(SSDG_FULL, key32(y2));
+    if (lane == 0) reinterpret_cast<float4*>(dom)[warp] = make_float4(unkey32(k1), unkey32(k2), unkey32(k3), unkey32(k4));
+  }
+  NMS_LOOP
+  for (int i = tid; i < W; i += kNmsThreads) { remw[i] = 0u; openw[i] = 0u; }
+  // the sort is done with hist / bstart: the join tables take their place
+  NMS_LOOP
+  for (int i = tid; i < (tabn >> 2); i += kNmsThreads) reinterpret_cast<uint4*>(tab)[i] = make_uint4(0u, 0u, 0u, 0u);
+  inexact = __syncthreads_or(inexact);
+
+  if (fast_ok) {
+    // Slab join + size classes: the derivation is in nms_kernel.
+    float dx0, dy0, dsx, dsy, lwx, lwy;
+    {
+      float4 e = reinterpret_cast<const float4*>(dom)[0];
+#pragma unroll
+      for (int w = 1; w < kNmsWarps; ++w) {
+        const float4 f = reinterpret_cast<const float4*>(dom)[w];
+        e.x = fminf(e.x, f.x); e.y = fminf(e.y, f.y); e.z = fmaxf(e.z, f.z); e.w = fmaxf(e.w, f.w);
+      }
+      dx0 = e.x; dy0 = e.y;
+      // any positive scale keeps the slab map monotone; 0.999 keeps the largest coordinate inside the last slab
+      dsx = (e.z > e.x) ? __fdividef((float)kSlabs * 0.999f, e.z - e.x) : 0.f;
+      dsy = (e.w > e.y) ? __fdividef((float)kSlabs * 0.999f, e.w - e.y) : 0.f;
+      lwx = (e.z > e.x) ? __log2f(e.z - e.x) : 0.f;
+      lwy = (e.w > e.y) ? __log2f(e.w - e.y) : 0.f;
+    }
+    auto slab = [&](float v, float o, float sc) {   // monotone in v
+      const float f = (v - o) * sc;
+      return f >= (float)(kSlabs - 1) ? kSlabs - 1 : (f > 0.f ? (int)f : 0);
+    };
+    const float tq = inexact ? 0.f : P.tq0;
+    const float inv_l = inexact ? 0.f : P.inv_l;
+    auto size_cls = [&](float ext, float lref) {   // monotone in ext, clamped (clamping only merges classes)
+      const float f = (lref - __log2f(ext)) * inv_l;
+      return f >= (float)(kSizeCls - 1) ? kSizeCls - 1 : (f > 0.f ? (int)f : 0);
+    };
+    NMS_LOOP
+    for (int i = tid; i < m; i += kNmsThreads) {
+      if (!isfinite(qlo[i])) { slidx[i] = 0u; continue; }
+      const float4 c = crn[i];
+      const u32 bit = 1u << (i & 31);
+      const int wi = i >> 5;
+      const float sx = tq * (c.z - c.x) - 1e-6f * (fabsf(c.x) + fabsf(c.z));
+      const float sy = tq * (c.w - c.y) - 1e-6f * (fabsf(c.y) + fabsf(c.w));
+      const int ax = slab(c.x + sx, dx0, dsx), bx = max(slab(c.z - sx, dx0, dsx), ax);
+      const int ay = slab(c.y + sy, dy0, dsy), by = max(slab(c.w - sy, dy0, dsy), ay);
+      const int cw = inv_l > 0.f ? size_cls(c.z - c.x, lwx) : 0, ch = inv_l > 0.f ? size_cls(c.w - c.y, lwy) : 0;
+      slidx[i] = (u32)ax | ((u32)bx << 5) | ((u32)ay << 10) | ((u32)by << 15) | ((u32)cw << 20) | ((u32)ch << 24) | 0x80000000u;
+      atomicOr(&tab[ax * RL + wi], bit);
+      atomicOr(&tab[bx * RL + W + wi], bit);
+      atomicOr(&tab[ay * RL + 2 * W + wi], bit);
+      atomicOr(&tab[by * RL + 3 * W + wi], bit);
+      atomicOr(&stab[cw * RS + wi], bit);
+      atomicOr(&stab[ch * RS + W + wi], bit);
+    }
+    __syncthreads();
+    NMS_LOOP
+    for (int col = tid; col < 6 * W; col += kNmsThreads) {
+      if (col < 4 * W) {
+        const bool up = ((col / W) & 1) == 0;   // LE: ascending running OR, GE: descending
+        u32 acc = 0u;
+#pragma unroll 8
+        for (int k = 0; k < kSlabs; ++k) {
+          const int sl = up ? k : kSlabs - 1 - k;
+          acc |= tab[sl * RL + col];
+          tab[sl * RL + col] = acc;
+        }
+      } else {
+        u32* sc = stab + (col - 4 * W);
+        u32 prev = 0u, cur = sc[0];
+#pragma unroll 4
+        for (int k = 0; k < kSizeCls; ++k) {
+          const u32 nxt = k + 1 < kSizeCls ? sc[(k + 1) * RS] : 0u;
+          sc[k * RS] = prev | cur | nxt;
+          prev = cur; cur = nxt;
+        }
+      }
+    }
+    __syncthreads();
+    // The join proper, per group of 32 rows (lane = row), in two passes over the column words w <= g:
+    //   A  candidate words = AND of the six table words -- straight-line code when the word count is a template
+    //      constant (immediate offsets, no address arithmetic), parked in the row's slots of the triangle;
+    //   B  the candidates of each word get the cheap float test (1e-4 margin), survivors the formula itself -- IEEE
+    //      float32, no contraction (utils/bbox.py:13-25); the word is rewritten with the real suppressions.
+    // Rows that end without a suppressor stay closed (kept at once); the others are opened for the resolution.
+    const u32 ltmask = (1u << lane) - 1u;
+    auto join_group = [&](int gi) {
+      const int i = (gi << 5) + lane;
+      const bool live = i < m;
+      const u32 si = live ? slidx[i] : 0u;
+      const u32 smask = (u32)((int)si >> 31);                    // insane / padding rows: no candidates
+      const u32* lex = tab + ((si >> 5) & 31u) * RL;             // LEx[b_i]
+      const u32* gex = tab + (si & 31u) * RL + W;                // GEx[a_i]
+      const u32* ley = tab + ((si >> 15) & 31u) * RL + 2 * W;    // LEy[b_i]
+      const u32* gey = tab + ((si >> 10) & 31u) * RL + 3 * W;    // GEy[a_i]
+      const u32* szw = stab + ((si >> 20) & 15u) * RS;           // width classes next to the row's
+      const u32* szh = stab + ((si >> 24) & 15u) * RS + W;       // height classes
+      u32* myrow = sup + 16 * gi * (gi + 1) + lane;              // slot of word w: myrow[32 w]
+      u32 any = 0u;
+      if (kW > 0) {
+#pragma unroll
+        for (int w = 0; w < kW; ++w) {
+          if (w <= gi) {
+            u32 cand = lex[w] & gex[w] & ley[w] & gey[w] & szw[w] & szh[w] & smask;
+            if (w == gi) cand &= ltmask;
+            myrow[w << 5] = cand;
+            any |= cand;
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int w = 0; w <= gi; ++w) {
+          u32 cand = lex[w] & gex[w] & ley[w] & gey[w] & szw[w] & szh[w] & smask;
+          if (w == gi) cand &= ltmask;
+          myrow[w << 5] = cand;
+          any |= cand;
+        }
+      }
+      if (!__any_sync(SSDG_FULL, any != 0u)) return;
+      const float4 bi = live ? crn[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float qi_lo = live ? qlo[i] : 0.f;
+      const float ai = live ? area[i] : 0.f;
+      any = 0u;
+#pragma unroll 1
+      for (int w = 0; w <= gi; ++w) {
+        u32 cand = myrow[w << 5];
+        if (!__any_sync(SSDG_FULL, cand != 0u)) continue;
+        u32 bits = 0u;
+        while (cand) {
+          const int jj = __ffs(cand) - 1;
+          cand &= cand - 1;
+          const int j = (w << 5) + jj;
+          const float4 bj = crn[j];
+          const float lox = fmaxf(bi.x, bj.x), hix = fminf(bi.z, bj.z), loy = fmaxf(bi.y, bj.y), hiy = fminf(bi.w, bj.w);
+          const float fx = hix - lox, fy = hiy - loy;
+          if (!(fx > 0.f && fx * fy >= qi_lo + qlo[j])) continue;
+          const float ex = fmaxf(0.f, __fsub_rn(hix, lox));
+          const float ey = fmaxf(0.f, __fsub_rn(hiy, loy));
+          const float inter = __fmul_rn(ex, ey);
+          const float den = __fadd_rn(__fsub_rn(__fadd_rn(area[j], ai), inter), 1e-10f);
+          if (__fdiv_rn(inter, den) > thr) bits |= 1u << jj;
+        }
+        myrow[w << 5] = bits;
+        any |= bits;
+      }
+      const u32 open_rows = __ballot_sync(SSDG_FULL, any != 0u);
+      if (lane == 0) openw[gi] = open_rows;
+    };
+    // group g costs g + 1 words: dealt in pairs (last + first, ...) every warp gets the same number of word steps
+    for (int k = warp; 2 * k < ngroups; k += kNmsWarps) {
+      join_group(ngroups - 1 - k);
+      if (k != ngroups - 1 - k) join_group(k);
+    }
+  } else {
+    // No division-free test for this threshold: all pairs, the formula itself.
+    // Task (g, w<=g): lane = row 32g+lane, loop over the 32 columns of group w (uniform shared loads).
+    const int ntasks = ngroups * (ngroups + 1) / 2;
+    for (int task = warp; task < ntasks; task += kNmsWarps) {
+      int g = 0;
+      while ((g + 1) * (g + 2) / 2 <= task) ++g;
+      const int w = task - g * (g + 1) / 2;
+      const int i = (g << 5) + lane;
+      const float4 bi = crn[i];
+      u32 bits = 0u;
+      if (i < m) {
+        const int jend = w == g ? lane : 32;
+        for (int jj = 0; jj < jend; ++jj) {   // IEEE float32, no contraction (utils/bbox.py:13-25)
+          const int j = (w << 5) + jj;
+          if (j >= m) break;
+          const float4 bj = crn[j];
+          const float ex = fmaxf(0.f, __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
+          const float ey = fmaxf(0.f, __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
+          const float inter = __fmul_rn(ex, ey);
+          const float den = __fadd_rn(__fsub_rn(__fadd_rn(area[j], area[i]), inter), 1e-10f);
+          if (__fdiv_rn(inter, den) > thr) bits |= 1u << jj;
+        }
+      }
+      sup[16 * g * (g + 1) + (w << 5) + lane] = bits;
+    }
+    NMS_LOOP
+    for (int g = tid; g < W; g += kNmsThreads)   // every live row is open
+      openw[g] = m >= 32 * (g + 1) ? ~0u : (m > 32 * g ? (1u << (m - 32 * g)) - 1u : 0u);
+  }
+  __syncthreads();
+
+  // Closed rows are kept at once.  The open ones: fixed point of  kept(i) <=> no kept j < i with sup(i, j);
+  // removed(i) <=> some kept j < i with sup(i, j), by one warp (a handful of rows per list: no CTA-wide barrier per
+  // round); then hist[w] = kept boxes before word w for the output.
+  if (warp == 0) {
+    const u32 ow = lane < W ? openw[lane] : 0u;
+    const u32 lm = m >= 32 * (lane + 1) ? ~0u : (m > 32 * lane ? (1u << (m - 32 * lane)) - 1u : 0u);
+    if (lane < W) keptw[lane] = lm & ~ow;
+    const int oc = __popc(ow);
+    int oincl = oc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(SSDG_FULL, oincl, o);
+      if (lane >= o) oincl += v;
+    }
+    const int nu = __shfl_sync(SSDG_FULL, oincl, 31);
+    {
+      u32 t = ow;
+      int p = oincl - oc;
+      while (t) {
+        unres[p++] = (u32)((lane << 5) + __ffs(t) - 1);
+        t &= t - 1;
+      }
+    }
+    __syncwarp();
+    for (;;) {
+      bool unknown = false;
+      for (int k = lane; k < nu; k += 32) {
+        const int i = (int)unres[k], gi = i >> 5;
+        const u32 bit = 1u << (i & 31);
+        if ((keptw[gi] | remw[gi]) & bit) continue;
+        bool hit_kept = false, all_removed = true;
+        const int sbase = 16 * gi * (gi + 1) + (i & 31);
+        for (int w = 0; w <= gi; ++w) {
+          const u32 sb = sup[sbase + (w << 5)];
+          if (sb & keptw[w]) hit_kept = true;
+          if (sb & ~remw[w]) all_removed = false;
+        }
+        if (hit_kept) atomicOr(&remw[gi], bit);
+        else if (all_removed) atomicOr(&keptw[gi], bit);
+        else unknown = true;
+      }
+      __syncwarp();
+      if (!__any_sync(SSDG_FULL, unknown)) break;
+    }
+    const int c = lane < W ? __popc(keptw[lane]) : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(SSDG_FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane < W) hist[lane] = (u32)(incl - c);   // W <= 32 (shared memory limits sortn to 1024)
+    if (lane == 31) hist[W] = (u32)incl;
+  }
+  __syncthreads();
+  int* ok = P.out_kept + list * (size_t)P.top_k;
+  float* os = P.out_score ? P.out_score + list * (size_t)P.top_k : nullptr;
+  const int total = (int)hist[W];
+  for (int i = total + tid; i < P.top_k; i += kNmsThreads) {
+    ok[i] = -1;
+    if (os) os[i] = 0.f;
+  }
+  NMS_LOOP
+  for (int i = tid; i < m; i += kNmsThreads) {
+    const u32 kw = keptw[i >> 5], bit = 1u << (i & 31);
+    if (kw & bit) {
+      const int rank = (int)hist[i >> 5] + __popc(kw & (bit - 1u));
+      ok[rank] = (int)(~(u32)keys[i]);
+      if (os) os[rank] = unkey32((u32)(keys[i] >> 32));
+    }
+  }
+  if (tid == 0) P.out_count[list] = total;
+}
+
 static int f_warps_for(int C) {
   const size_t budget = 220 * 1024;
   int w = (int)((budget - (size_t)kFWarps * 32 * 8) / ((size_t)32 * C * 4 + 8));
@@ -957,8 +1421,8 @@ static int next_pow2(int v) {
 static size_t nms_smem_bytes(int sortn, int top_k) {
   const int mcap = (top_k + 31) & ~31, W = mcap / 32, RL = (4 * W) | 1;
   const size_t tab = (size_t)kSlabs * RL > 512 ? (size_t)kSlabs * RL : 512;   // hist + bstart, then the join tables
-  return (size_t)sortn * 8 + (size_t)mcap * (16 + 4 + 4 + 4) + (size_t)16 * W * (W + 1) * 4 + 2 * W * 4 +
-         (size_t)mcap * 4 + 8 * kNmsWarps * 4 + tab * 4 + (size_t)kSizeCls * ((2 * W) | 1) * 4 + 16 + 128;
+  return (size_t)sortn * 8 + (size_t)mcap * (16 + 4 + 4 + 4) + (size_t)16 * W * (W + 1) * 4 + 3 * W * 4 +
+         (size_t)mcap * 4 + 9 * kNmsWarps * 4 + tab * 4 + (size_t)kSizeCls * ((2 * W) | 1) * 4 + 16 + 128;
 }
 
 struct DetectWs {
@@ -1032,16 +1496,43 @@ static int run_nms(const DetectWs& ws, const float* boxes, long long batch, int 
   Q.boxes = boxes; Q.A = A; Q.n_fg = C - 1; Q.top_k = top_k;
   Q.sortn = next_pow2(top_k); Q.iou_thresh = iou_thresh;
   Q.out_kept = out_kept; Q.out_count = out_count; Q.out_score = out_score;
+  Q.B = (int)batch;
+  Q.fast_ok = (iou_thresh > 0.f && iou_thresh < 1e6f) ? 1 : 0;
+  Q.q = Q.fast_ok ? iou_thresh / (1.f + iou_thresh) : 0.f;
+  Q.tq0 = fminf(0.98f * Q.q, 0.49f);
+  {
+    const float tp = 0.99f * iou_thresh / (1.f + 0.001f * iou_thresh);
+    Q.inv_l = (Q.fast_ok && tp < 0.98f) ? -1.f / log2f(tp) : 0.f;
+  }
   const size_t smem = nms_smem_bytes(Q.sortn, top_k);
   if ((int)smem > max_smem_optin()) return SSDG_ERR_LIMIT;
-  if (smem > 48 * 1024)
-    SSDG_CUDA_TRY(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long lists = batch * (C - 1);
   if (lists > 0x7fffffffll) return SSDG_ERR_LIMIT;
-  SSDG_CUDA_TRY(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  prof_begin(SSDG_PROF_NMS, st);
-  nms_kernel<<<(unsigned)lists, kNmsThreads, smem, st>>>(Q);
-  prof_end(SSDG_PROF_NMS, st);
+  static const char* env_v1 = getenv("SSDG_NMS_V1");   // the first-generation kernel, for A/B measurements
+  auto go = [&](auto kern, dim3 grid) -> int {
+    if (smem > 48 * 1024)
+      SSDG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSDG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    prof_begin(SSDG_PROF_NMS, st);
+    kern<<<grid, kNmsThreads, smem, st>>>(Q);
+    prof_end(SSDG_PROF_NMS, st);
+    return SSDG_OK;
+  };
+  int rc;
+  const dim3 grid2((unsigned)(C - 1), (unsigned)(batch < 65535 ? batch : 65535), (unsigned)((batch + 65534) / 65535));
+  if (env_v1 && atoi(env_v1)) rc = go(nms_kernel, dim3((unsigned)lists));
+  else {
+    switch ((top_k + 31) / 32) {   // the common list lengths get the join's word loop as straight-line code
+      case 1: rc = go(nms2_kernel<1>, grid2); break;
+      case 2: rc = go(nms2_kernel<2>, grid2); break;
+      case 3: rc = go(nms2_kernel<3>, grid2); break;
+      case 4: rc = go(nms2_kernel<4>, grid2); break;
+      case 7: rc = go(nms2_kernel<7>, grid2); break;
+      case 8: rc = go(nms2_kernel<8>, grid2); break;
+      default: rc = go(nms2_kernel<0>, grid2); break;
+    }
+  }
+  if (rc != SSDG_OK) return rc;
   SSDG_LAUNCH_CHECK();
   return SSDG_OK;
 }

@@ -863,6 +863,12 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
       }
     };
     {
+      // Positives are ~3 % of the priors and their encoding is ~300 float64 instructions (two logarithms, four
+      // divisions): inside the prior-order sweep nearly every warp would run that path for one or two lanes.  So the
+      // sweep writes every prior as unmatched, and the positives are then taken DENSELY from the image's pair list
+      // (the entry that won its column: maximum key, then lowest row).  With an overflown list the sweep decides by
+      // the touch bits as before.
+      const bool dense_pos = !cand_overflow;
       const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
       int a = tid;
       for (; a + 3 * kMatchThreads < A; a += 4 * kMatchThreads) {   // four independent priors per iteration
@@ -871,14 +877,21 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int aq = a + q * kMatchThreads;
-          p4[q] = bit_test(touch, aq) != 0;
+          p4[q] = !dense_pos && bit_test(touch, aq) != 0;
           u[q] = (P.unmatched && P.out_loc) ? __ldg(P.unmatched + aq) : z4;
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) emit_prior(a + q * kMatchThreads, p4[q], u[q]);
       }
       for (; a < A; a += kMatchThreads)
-        emit_prior(a, bit_test(touch, a) != 0, (P.unmatched && P.out_loc) ? __ldg(P.unmatched + a) : z4);
+        emit_prior(a, !dense_pos && bit_test(touch, a) != 0, (P.unmatched && P.out_loc) ? __ldg(P.unmatched + a) : z4);
+      if (dense_pos) {
+        __syncthreads();
+        for (int e = tid; e < ncand; e += kMatchThreads) {
+          const Cand c = cand[e];
+          if (c.key == colkey[c.a] && c.t == colt[c.a]) emit_prior(c.a, true, z4);
+        }
+      }
     }
     __syncthreads();
     // phase-1 pairs (utils/bbox.py:87-90; later pairs win)
