@@ -59,6 +59,8 @@ struct DetectParams {
   u32* cls_cnt;            // [B][C-1]
   u32* cls_off;            // [B][C-1] start of the class list inside the image's sorted buffer
   u64* sorted;             // [B][tpi*32*(C-1)] (score key << 32) | ~prior, class-major
+  u64* lists;              // direct mode (no bucketing pass): [B][C-1][list_cap] (score key << 32) | ~prior; else null
+  size_t list_cap;         // tpi*32: a class list can hold every prior of the image
   float* boxes;            // [B*A,4] decoded
   float* probs;            // optional [B*A,C]
   float head_thresh;
@@ -253,6 +255,82 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
     const float2 ax = aux[r];
     return (kWrite ? *p : exp2_ftz(fmaf(*p, SSDG_LOG2E, ax.x))) * ax.y;
   };
+  auto side_outputs = [&]() {   // score head (models/ssd_model.py:481-488) and the decoded box of the lane's row
+    if (kProbs || !valid) return;
+    if (kWrite && (P.head_score || P.head_cls || P.head_mask)) {
+      // max foreground probability, arg-max over all classes (first max)
+      float best = row[0];
+      int arg = 0;
+      float fg = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float v = row[c];
+        if (v > best) { best = v; arg = c; }
+        if (c < C - 1) fg = fmaxf(fg, v);
+      }
+      const float score = fg * inv_s;
+      const float pbg = row[C - 1] * inv_s;
+      if (P.head_score) P.head_score[n] = score;
+      if (P.head_cls) P.head_cls[n] = arg;
+      if (P.head_mask) P.head_mask[n] = (score > P.head_thresh && !(pbg > P.head_thresh)) ? 1 : 0;
+    }
+    if (P.boxes) reinterpret_cast<float4*>(P.boxes)[n] = decode_row<TP>(tbox, P.priors, a);
+  };
+  if (P.lists) {
+    // Straight into the per-(image, class) lists the NMS reads -- no bucketing pass.  The exact test comes first
+    // (a pre-filter hit whose score fails leaves nothing), then ONE atomic per lane and class word reserves the
+    // lane's run in the class list of this image, the side outputs of the row run while the atomics are in
+    // flight, and the appends recompute the (bitwise identical) scores.  The order inside a list depends on the
+    // arrival of the tiles; the NMS sorts by the unique (score, prior) key, so the result does not.
+    constexpr bool kStash = !kProbs && !kWrite;   // the tile element is free to hold the score once it has been tested
+    auto exact = [&](u32 rb, int c) {
+      u32 keep = 0u;
+      while (rb) {
+        const int r = __ffs(rb) - 1;
+        rb &= rb - 1;
+        float* p = tile + r * C + c;
+        const float score = score_at(p, r);
+        if (score > thr) {
+          keep |= 1u << r;
+          if (kStash) *p = score;
+        }
+      }
+      return keep;
+    };
+    int c2 = 64 + lane;
+    if (nfg > 64 && nfg <= 80) {   // at most 16 classes in the third word: two lanes share a class, 16 rows each
+      const u32 lo = __shfl_sync(SSDG_FULL, t2, lane & 15);
+      t2 = lane < 16 ? (t2 & 0xffffu) : (lo & 0xffff0000u);
+      c2 = 64 + (lane & 15);
+    }
+    u32* cc = P.cls_cnt + (size_t)b * nfg;
+    u32 p0 = 0u, p1 = 0u, p2 = 0u;
+    const u32 x0 = exact(t0, lane);
+    if (x0) p0 = atomicAdd(cc + lane, (u32)__popc(x0));
+    const u32 x1 = nfg > 32 ? exact(t1, 32 + lane) : 0u;
+    if (x1) p1 = atomicAdd(cc + 32 + lane, (u32)__popc(x1));
+    const u32 x2 = nfg > 64 ? exact(t2, c2) : 0u;
+    if (x2) p2 = atomicAdd(cc + c2, (u32)__popc(x2));
+    side_outputs();
+    u64* lb = P.lists + (size_t)b * nfg * P.list_cap;
+    const u32 nbase = ~(u32)(j * 32);   // ~(32 j + r) = ~(32 j) - r
+    auto append = [&](u32 xb, int c, u32 pos) {
+      u64* dst = lb + (size_t)c * P.list_cap + pos;
+      while (xb) {
+        const int r = __ffs(xb) - 1;
+        xb &= xb - 1;
+        float* p = tile + r * C + c;
+        const float score = kStash ? *p : score_at(p, r);
+        const u32 sk = kProbs ? key32(score) : (__float_as_uint(score) | 0x80000000u);   // softmax scores are >= +0
+        *dst++ = ((u64)sk << 32) | (u64)(nbase - (u32)r);
+      }
+    };
+    append(x0, lane, p0); append(x1, 32 + lane, p1); append(x2, c2, p2);
+    if (valid)
+      for (int c = 96; c < nfg; ++c) {   // classes beyond the bit words: one atomic per candidate
+        const float score = kProbs ? row[c] : row[c] * inv_s;
+        if (score > thr) lb[(size_t)c * P.list_cap + atomicAdd(cc + c, 1u)] = ((u64)key32(score) << 32) | (u64)(~(u32)a);
+      }
+  } else {
   // One loop per class word tests and appends: the segment position of a lane comes from its number of
   // PRE-FILTER hits, and the rare hit whose exact score fails (the pre-filter keeps a 0.1% margin) leaves a
   // hole -- an entry of the class one past the last, which the bucketing pass drops.
@@ -285,24 +363,9 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
       const float score = kProbs ? row[c] : row[c] * inv_s;
       if (score > thr) *dst++ = ((u64)key32(score) << 32) | (u64)(((u32)c << kABitsD) | (u32)a);
     }
-  if (kProbs || !valid) return;
-  if (kWrite && (P.head_score || P.head_cls || P.head_mask)) {
-    // models/ssd_model.py:481-488: max foreground probability, arg-max over all classes (first max)
-    float best = row[0];
-    int arg = 0;
-    float fg = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float v = row[c];
-      if (v > best) { best = v; arg = c; }
-      if (c < C - 1) fg = fmaxf(fg, v);
-    }
-    const float score = fg * inv_s;
-    const float pbg = row[C - 1] * inv_s;
-    if (P.head_score) P.head_score[n] = score;
-    if (P.head_cls) P.head_cls[n] = arg;
-    if (P.head_mask) P.head_mask[n] = (score > P.head_thresh && !(pbg > P.head_thresh)) ? 1 : 0;
+  side_outputs();
   }
-  if (P.boxes) reinterpret_cast<float4*>(P.boxes)[n] = decode_row<TP>(tbox, P.priors, a);
+  if (kProbs || !valid) return;
   if (kWrite && P.probs)
     for (int c = 0; c < C; ++c) row[c] *= inv_s;
 }
@@ -314,7 +377,7 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* gsrc, u32 bytes) {
 }
 
 template <typename TP, bool kProbs, bool kWrite>
-__global__ void SSDG_FILTER_BOUNDS filter_kernel(DetectParams P, int warps_per_cta, int prefetch) {   // <= 64 registers: leaves room for a matcher CTA
+__global__ void SSDG_FILTER_BOUNDS filter_kernel(DetectParams P, int warps_per_cta, int prefetch, int chunked) {   // <= 64 registers: leaves room for a matcher CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int C = P.C, A = P.A, tpi = P.tpi;
   const size_t tile_floats = (size_t)32 * C;
@@ -328,9 +391,19 @@ __global__ void SSDG_FILTER_BOUNDS filter_kernel(DetectParams P, int warps_per_c
   }
   __syncthreads();
   if (warp >= warps_per_cta) return;
-  const long long ntiles = (long long)P.B * tpi;
-  const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
-  const long long stride = (long long)gridDim.x * warps_per_cta;
+  // Tile walk.  Interleaved: warp g of the grid takes tiles g, g + G, ... (G warps in the grid).  Chunked: every CTA
+  // owns one contiguous run of tiles and its warps interleave inside it -- the tiles of an image then come from two
+  // or three CTAs spread over the whole kernel instead of from 273 warps at the same moment, which keeps the atomics
+  // on the image's class counters (direct lists) uncontended.
+  long long ntiles = (long long)P.B * tpi;
+  long long gw = (long long)blockIdx.x * warps_per_cta + warp;
+  long long stride = (long long)gridDim.x * warps_per_cta;
+  if (chunked) {
+    const long long chunk = (ntiles + gridDim.x - 1) / gridDim.x;
+    gw = (long long)blockIdx.x * chunk + warp;
+    ntiles = min(ntiles, (long long)(blockIdx.x + 1) * chunk);
+    stride = warps_per_cta;
+  }
   float* tile = bufs + (size_t)warp * tile_floats;
   u64* mybar = bars + warp;
   const u64 pol = evict_first_policy();
@@ -352,6 +425,7 @@ __global__ void SSDG_FILTER_BOUNDS filter_kernel(DetectParams P, int warps_per_c
     const long long tp = gw + (long long)(prefetch + 1) * stride;
     pb = (int)(tp / tpi); pj = (int)(tp - (long long)pb * tpi);
   }
+  long long tpf = gw + (long long)(prefetch + 1) * stride;   // index of the tile (pb, pj)
   auto prefetch_at = [&](int ib, int ij) {  // lane 0 only
     if (ib >= P.B) return;
     prefetch_l2_bulk(P.pred_cls + ((size_t)ib * A + (size_t)ij * 32) * C, (u32)min(32, A - ij * 32) * (u32)C * 4u);
@@ -360,7 +434,7 @@ __global__ void SSDG_FILTER_BOUNDS filter_kernel(DetectParams P, int warps_per_c
     issue(b, j);
     for (int d = 1; d <= prefetch; ++d) {
       const long long tp = gw + d * stride;
-      prefetch_at((int)(tp / tpi), (int)(tp % tpi));
+      if (tp < ntiles) prefetch_at((int)(tp / tpi), (int)(tp % tpi));
     }
   }
   int k = 0;
@@ -386,8 +460,9 @@ __global__ void SSDG_FILTER_BOUNDS filter_kernel(DetectParams P, int warps_per_c
     if (j >= tpi) { j -= tpi; ++b; }
     if (P.tma_ok && lane == 0 && t + stride < ntiles) {
       issue(b, j);
-      if (prefetch > 0) prefetch_at(pb, pj);
+      if (prefetch > 0 && tpf < ntiles) prefetch_at(pb, pj);
     }
+    tpf += stride;
     pb += step_b; pj += step_j;
     if (pj >= tpi) { pj -= tpi; ++pb; }
   }
@@ -536,7 +611,8 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
   const int b = (int)(blockIdx.x / (u32)P.n_fg);
   int n = (int)P.cls_cnt[list];
   const bool selected = n > P.sortn;   // more candidates than the sort takes: radix select first
-  const u64* cl = P.sorted + (size_t)b * P.img_stride + P.cls_off[list];
+  const u64* cl = P.cls_off ? P.sorted + (size_t)b * P.img_stride + P.cls_off[list]
+                            : P.sorted + list * P.img_stride;   // direct mode: one list per (image, class)
 
   u32 hmin = ~0u, hmax = 0u, lmin = ~0u, lmax = 0u;   // range of the score and prior words of the keys
   if (n <= sortn) {
@@ -995,7 +1071,8 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms2_kernel(NmsParams P) {
   const size_t list = (size_t)b * P.n_fg + blockIdx.x;
   int n = (int)P.cls_cnt[list];
   const bool selected = n > P.sortn;   // more candidates than the sort takes: radix select first
-  const u64* cl = P.sorted + (size_t)b * P.img_stride + P.cls_off[list];
+  const u64* cl = P.cls_off ? P.sorted + (size_t)b * P.img_stride + P.cls_off[list]
+                            : P.sorted + list * P.img_stride;   // direct mode: one list per (image, class)
 
   u32 hmin = ~0u, hmax = 0u, lmin = ~0u, lmax = 0u;   // range of the score and prior words of the keys
   if (n <= sortn) {
@@ -1459,13 +1536,15 @@ static int run_filter(DetectParams& P, int prior_dtype, cudaStream_t st) {
   const long long need = (tiles + warps - 1) / warps;
   if (need < grid) grid = (int)need;
   P.tma_ok = (((long long)P.A * P.C) % 4 == 0) && (((uintptr_t)P.pred_cls & 15) == 0);
+  if (P.lists) SSDG_CUDA_TRY(cudaMemsetAsync(P.cls_cnt, 0, (size_t)P.B * (P.C - 1) * 4, st));   // the class lists start empty
   prof_begin(SSDG_PROF_FILTER, st);
   // kWrite: the rows must hold exp(x - max) after the pass (probabilities output, score head)
   const bool wr = !kProbs && (P.probs || P.head_score || P.head_cls || P.head_mask);
   auto go = [&](auto kern) -> int {
     SSDG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const char* env_pf = getenv("SSDG_FILTER_PREFETCH");   // tiles of L2 prefetch distance per warp; experiment knob
-    kern<<<grid, kFThreads, smem, st>>>(P, warps, env_pf ? atoi(env_pf) : 1);
+    static const char* env_ch = getenv("SSDG_FILTER_CHUNKED");    // tile walk; experiment knob
+    kern<<<grid, kFThreads, smem, st>>>(P, warps, env_pf ? atoi(env_pf) : 1, env_ch ? atoi(env_ch) : 0);
     return SSDG_OK;
   };
   int rc;
@@ -1474,6 +1553,7 @@ static int run_filter(DetectParams& P, int prior_dtype, cudaStream_t st) {
   if (rc != SSDG_OK) return rc;
   prof_end(SSDG_PROF_FILTER, st);
   SSDG_LAUNCH_CHECK();
+  if (P.lists) return SSDG_OK;   // direct mode: the filter has appended to the class lists itself
   SSDG_CUDA_TRY(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   {
     const size_t bsm = ((size_t)2 * P.C + P.tpi + 1) * 4;
@@ -1488,11 +1568,17 @@ static int run_filter(DetectParams& P, int prior_dtype, cudaStream_t st) {
   return SSDG_OK;
 }
 
+static bool detect_direct() {   // experiment switch: SSDG_DETECT_BUCKET=1 restores the per-tile segments + bucketing pass
+  static const char* e = getenv("SSDG_DETECT_BUCKET");
+  return !(e && atoi(e));
+}
+
 static int run_nms(const DetectWs& ws, const float* boxes, long long batch, int A, int C, int top_k, float iou_thresh,
                    int* out_kept, int* out_count, float* out_score, cudaStream_t st) {
   NmsParams Q;
   Q.cls_cnt = ws.cls_cnt; Q.cls_off = ws.cls_off; Q.sorted = ws.sorted;
   Q.img_stride = (size_t)((A + 31) / 32) * 32 * (size_t)(C - 1);
+  if (detect_direct()) { Q.cls_off = nullptr; Q.sorted = ws.seg; Q.img_stride = (size_t)((A + 31) / 32) * 32; }
   Q.boxes = boxes; Q.A = A; Q.n_fg = C - 1; Q.top_k = top_k;
   Q.sortn = next_pow2(top_k); Q.iou_thresh = iou_thresh;
   Q.out_kept = out_kept; Q.out_count = out_count; Q.out_score = out_score;
@@ -1540,6 +1626,8 @@ static int run_nms(const DetectWs& ws, const float* boxes, long long batch, int 
 static void fill_params(DetectParams& P, const DetectWs& ws, long long batch, int A, int C) {
   P.B = (int)batch; P.A = A; P.C = C; P.tpi = (A + 31) / 32;
   P.tile_cnt = ws.tile_cnt; P.seg = ws.seg; P.cls_cnt = ws.cls_cnt; P.cls_off = ws.cls_off; P.sorted = ws.sorted;
+  P.lists = detect_direct() ? ws.seg : nullptr;
+  P.list_cap = (size_t)P.tpi * 32;
 }
 
 }  // namespace ssdg
