@@ -675,10 +675,10 @@ def headline(R, args, comm, sampler, b):
     head = hp._match_out["_match_ws"].view((8,), np.uint32).to_host(hp.s_main)
     tiles_evaluated = int(head[3])
     time_stage("loss_ms", hp.loss_stage, [N.PROF_CE, N.PROF_LOSS_TAIL])
-    time_stage("detect_ms", hp.detect_stage, [N.PROF_FILTER, N.PROF_BUCKET, N.PROF_NMS])
+    time_stage("detect_ms", hp.detect_stage, [N.PROF_FILTER, N.PROF_NMS])
     ce_alone_ms, filter_alone_ms = kernel_ms.get(N.PROF_CE, 0.0), kernel_ms.get(N.PROF_FILTER, 0.0)
     if hp.fused:   # the variants the chained step actually launches
-        time_stage("detect_with_row_stats_ms", lambda s: hp.detect_stage(s, stats=True), [N.PROF_FILTER, N.PROF_BUCKET, N.PROF_NMS])
+        time_stage("detect_with_row_stats_ms", lambda s: hp.detect_stage(s, stats=True), [N.PROF_FILTER, N.PROF_NMS])
         time_stage("loss_from_row_stats_ms", lambda s: hp.loss_stage(s, stats=True), [N.PROF_CE, N.PROF_LOSS_TAIL])
     grad_ms = None
     if not args.no_detail and world == 1:
@@ -795,7 +795,8 @@ def report(args, R, comm, b, M, detail_cfg):
              "ce_kernel_gbs_standalone": b * a * (c * 4 + 16 + 16 + 4 + 1) / (ce_ms * 1e-3) / 1e9 if ce_ms > 0 else None,
              "kernels_ms": {"match_kernel": m_ms, "search_kernel": kernel_ms.get(N.PROF_SEARCH), "ce_kernel": ce_ms,
                             "filter_kernel": f_ms, "nms_kernel": kernel_ms.get(N.PROF_NMS),
-                            "bucket_kernel": kernel_ms.get(N.PROF_BUCKET), "loss_tail": kernel_ms.get(N.PROF_LOSS_TAIL),
+                            "bucket_kernel": None,   # gone: the filter appends straight to the class lists
+                            "loss_tail": kernel_ms.get(N.PROF_LOSS_TAIL),
                             "filter_kernel_with_row_stats": kernel_ms.get(N.PROF_FILTER) if fused else None,
                             "lossprep_kernel": kernel_ms.get(N.PROF_CE) if fused else None,
                             "grad_kernel": grad_ms},

@@ -99,7 +99,7 @@ SSDG_API int ssdg_event_elapsed_ms(void* start, void* stop, float* ms); /* synch
 #define SSDG_PROF_CE 1
 #define SSDG_PROF_FILTER 2
 #define SSDG_PROF_NMS 3
-#define SSDG_PROF_BUCKET 4      /* bucket_kernel */
+#define SSDG_PROF_BUCKET 4      /* unused (the bucketing pass is gone: the filter appends to the class lists) */
 #define SSDG_PROF_SEARCH 5      /* search_kernel (SSDG_PROF_MATCH covers search + per-image kernel) */
 #define SSDG_PROF_LOSS_TAIL 6   /* select_kernel x2 + final_kernel */
 #define SSDG_PROF_GRAD 7        /* grad_kernel */
@@ -312,7 +312,11 @@ SSDG_API int ssdg_loc_scale(const float* in, float* out, int64_t rows, float sca
  *   out_boxes  float [B,A,4] decoded cxcywh (relative units)
  *   out_probs  float [B,A,C] softmax (parity / debugging; large)
  *   head_*: score float [B,A], cls int32 [B,A], mask uint8 [B,A] at head_thresh (:481-488)
- * Limits: top_k <= 1024.
+ * Limits: top_k <= 1024, batch * ceil(A/32) < 2^31.
+ * Workspace: one candidate list per (image, class) with room for EVERY prior (no input can overflow it) --
+ *   batch * (C-1) * ceil(A/32)*32 * 8 bytes (1.4 GB at SSD300 B=256, 23 GB at SSD512 B=1024; only the part that holds
+ *   candidates, ~33 MB, is ever touched) -- plus the decoded boxes.  The size depends on the current device's SM count
+ *   (the filter's launch geometry); query it on the device the call will run on.
  */
 SSDG_API size_t ssdg_detect_workspace_bytes(int64_t batch, int32_t n_priors, int32_t n_classes, int32_t top_k);
 SSDG_API int ssdg_detect(const float* pred_cls, const float* pred_box, const void* priors,
@@ -322,7 +326,7 @@ SSDG_API int ssdg_detect(const float* pred_cls, const float* pred_box, const voi
                 float head_thresh, float* head_score, int32_t* head_cls, uint8_t* head_mask,
                 void* workspace, size_t workspace_bytes, void* stream);
 /* The same call in two stream-ordered stages sharing the workspace: stage 0 = softmax filter, decode and
- * candidate bucketing (the pass over the logits, HBM-bound), stage 1 = per-class NMS (instruction-bound).  A
+ * the per-class candidate lists (the pass over the logits, HBM-bound), stage 1 = per-class NMS (instruction-bound).  A
  * pipeline can enqueue them on different streams -- ordered by an event -- so that the NMS shares the SMs
  * with an HBM-bound kernel of another branch (ssdgeom/pipeline.py).  out_row_ml float [B*A,2] / out_row_negbg
  * float [B*A] (both or neither, stage 0): per-prior softmax statistics for ssdg_multibox_loss_fused. */

@@ -39,16 +39,16 @@ def timed(label, branches, reps=15):
 filt = lambda s: hp.detect_stage(s, stage=0, stats=True)
 nms = lambda s: hp.detect_stage(s, stage=1, stats=True)
 loss = lambda s: hp.loss_stage(s, stats=True)
-timed("filter+bucket", [(hp.s_d, [filt])])
+timed("filter", [(hp.s_d, [filt])])
 timed("match", [(hp.s_a, [hp.assign])])
-timed("filter+bucket || match", [(hp.s_d, [filt]), (hp.s_a, [hp.assign])])
+timed("filter || match", [(hp.s_d, [filt]), (hp.s_a, [hp.assign])])
 timed("nms", [(hp.s_n, [nms])])
 timed("loss", [(hp.s_l, [loss])])
 timed("nms(low) || loss(high)", [(hp.s_n, [nms]), (hp.s_l, [loss])])
 timed("nms(high) || loss(low)", [(hp.s_d, [nms]), (hp.s_a, [loss])])
 timed("nms || match", [(hp.s_n, [nms]), (hp.s_a, [hp.assign])])
-timed("filter+bucket || loss", [(hp.s_d, [filt]), (hp.s_l, [loss])])
-timed("filter+bucket+nms || match+loss", [(hp.s_d, [filt, nms]), (hp.s_a, [hp.assign, loss])])
+timed("filter || loss", [(hp.s_d, [filt]), (hp.s_l, [loss])])
+timed("filter+nms || match+loss", [(hp.s_d, [filt, nms]), (hp.s_a, [hp.assign, loss])])
 
 def full():
     e0, e1 = D.Event(), D.Event()

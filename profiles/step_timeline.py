@@ -18,7 +18,7 @@ for _ in range(3):
     hp.step()
 hp.s_main.sync()
 N.lib().ssdg_profile_enable(1)
-names = {N.PROF_FILTER: "filter", N.PROF_BUCKET: "bucket", N.PROF_NMS: "nms", N.PROF_SEARCH: "search",
+names = {N.PROF_FILTER: "filter", N.PROF_NMS: "nms", N.PROF_SEARCH: "search",
          N.PROF_MATCH: "search+match", N.PROF_CE: "ce/lossprep", N.PROF_LOSS_TAIL: "select+final"}
 spans = {k: [] for k in names}
 tot = []

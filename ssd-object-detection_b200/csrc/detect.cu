@@ -2,25 +2,26 @@
 // per-class score-threshold / top-k / greedy NMS the reference lacks (spec: oracle/ssd_oracle.py
 // nms_per_class, IoU formula utils/bbox.py:13-25 in float32).
 //
-//   filter_kernel  one streaming pass over the logits [B,A,C].  Tiles are 32 priors of ONE image; each
-//                  of the 16 warps of a CTA owns one shared-memory tile filled by 1-D bulk TMA
-//                  (cp.async.bulk + mbarrier).  Row phase, lane r owns row r (stride C words: conflict-free
-//                  for odd C): e_c = 2^((x_c - ref) log2e) with the background logit as reference (one pass;
-//                  rows that would overflow or lose precision are redone with their maximum), the sum, one
-//                  pre-filter bit per class.  Class phase, after a warp transpose of the bit matrices lane l
-//                  owns classes l, 32+l, 64+l: exact score e_c * (1/sum) > score_thresh and append to the
-//                  tile's private segment of the candidate buffer in one loop (failures leave holes).  No
-//                  atomics, one count word per tile.  Optionally leaves per-prior (ref, log sum) and the
-//                  background CE for the loss, the probabilities, and the reference's score head.
-//   bucket_kernel  one CTA per image: counting sort of the image's candidates by class (shared-memory
-//                  histogram, scan, scatter) into contiguous per-class lists; drops the holes.
+//   filter_kernel  one streaming pass over the logits [B,A,C].  Tiles are 32 priors of ONE image; every CTA owns
+//                  one contiguous run of tiles and each of its 16 warps one shared-memory tile at a time, filled
+//                  by 1-D bulk TMA (cp.async.bulk + mbarrier).  Row phase, lane r owns row r (stride C words:
+//                  conflict-free for odd C): e_c = 2^((x_c - ref) log2e) with the background logit as reference
+//                  (one pass; rows that would overflow or lose precision are redone with their maximum), the
+//                  sum, one pre-filter bit per class.  Class phase, after a warp transpose of the bit matrices
+//                  lane l owns classes l, 32+l, 64+l: exact score e_c * (1/sum) > score_thresh, one shared-memory
+//                  atomic per lane and class word reserves slots, and the candidates go STRAIGHT into the
+//                  per-(image, class) lists the NMS reads (laid out in prior space, so the CTA's slots cannot
+//                  collide with another CTA's): no bucketing pass, no global atomics, nothing to zero.
+//                  Optionally leaves per-prior (ref, log sum) and the background CE for the loss, the
+//                  probabilities, and the reference's score head.
 //   nms_kernel     one CTA per (image, class): exact top-k by (score desc, prior asc) -- radix select when the
 //                  list is longer than the sort width, then a bucketed rank sort; the lower-triangle
 //                  suppression bits from an interval join (cumulative slab bitsets per axis + width / height
 //                  class neighbourhoods, cheap float test with a margin, the exact IEEE formula for the
-//                  survivors); rows without suppressors are kept by ballot, the rest resolved by one warp
+//                  survivors); rows without suppressors are kept at once, the rest resolved by one warp
 //                  iterating "kept(i) <=> no kept j < i suppresses i" to its fixed point.
 #include <math_constants.h>
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
@@ -44,8 +45,7 @@ constexpr int kNmsThreads = 128;
 constexpr int kNmsWarps = kNmsThreads / 32;
 constexpr int kSlabs = 32;   // slabs per axis of the NMS candidate join
 constexpr int kSizeCls = 16; // width / height classes of the join
-constexpr int kBucketThreads = 512;
-constexpr int kABitsD = 21;     // prior index bits in a staged candidate (A < 2^21, C <= 2048)
+constexpr int kABitsD = 21;     // limit on the prior index (A < 2^21) kept from the staged format
 
 struct DetectParams {
   const float* pred_cls;   // logits (filter) or probabilities (kProbs)
@@ -54,13 +54,16 @@ struct DetectParams {
   int B, A, C, tpi;        // tpi: tiles per image
   int tma_ok;              // every tile start / size is 16-byte aligned
   float score_thresh;
-  u32* tile_cnt;           // [B*tpi] candidates of the tile
-  u64* seg;                // [B*tpi][32*(C-1)] (score key << 32) | (class << 21) | prior
-  u32* cls_cnt;            // [B][C-1]
-  u32* cls_off;            // [B][C-1] start of the class list inside the image's sorted buffer
-  u64* sorted;             // [B][tpi*32*(C-1)] (score key << 32) | ~prior, class-major
-  u64* lists;              // direct mode (no bucketing pass): [B][C-1][list_cap] (score key << 32) | ~prior; else null
-  size_t list_cap;         // tpi*32: a class list can hold every prior of the image
+  // Candidate lists, one per (image, class), laid out in PRIOR space: [B][C-1][tpi*32] entries
+  // (score key << 32) | ~prior.  Every filter CTA owns one contiguous run of `chunk` tiles; inside the list of
+  // (image b, class c) it appends to the slots of its own tiles of b -- [32 * first tile, ...) -- through a
+  // shared-memory counter, and leaves the count in run_cnt[image][slot][class], slot = CTA - first CTA of the image.
+  // No global atomics, no zeroing, no bucketing pass: the NMS reads the one or two (max_slots) runs of its list.
+  u64* lists;
+  u32* run_cnt;            // [B][max_slots][C-1]
+  int chunk, max_li;       // tiles per CTA; images a run can touch (chunk / tpi + 2)
+  int max_slots;           // runs an image can be split into (tpi / chunk + 2)
+  size_t list_cap;         // tpi*32
   float* boxes;            // [B*A,4] decoded
   float* probs;            // optional [B*A,C]
   float head_thresh;
@@ -127,7 +130,7 @@ __device__ __forceinline__ u32 warp_transpose32(u32 x, int lane) {
 // recomputed for the few pre-filtered classes.  kProbs: the rows already hold probabilities.
 template <typename TP, bool kProbs, bool kWrite>
 __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j, int rows, float* tile, float2* aux,
-                                            int lane) {
+                                            int lane, u32* cc, u32 run_off) {   // cc: the CTA's class counters of image b
   const int C = P.C, nfg = P.C - 1;
   const bool valid = lane < rows;
   const int a = j * 32 + lane;
@@ -275,23 +278,31 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
     }
     if (P.boxes) reinterpret_cast<float4*>(P.boxes)[n] = decode_row<TP>(tbox, P.priors, a);
   };
-  if (P.lists) {
-    // Straight into the per-(image, class) lists the NMS reads -- no bucketing pass.  The exact test comes first
-    // (a pre-filter hit whose score fails leaves nothing), then ONE atomic per lane and class word reserves the
-    // lane's run in the class list of this image, the side outputs of the row run while the atomics are in
-    // flight, and the appends recompute the (bitwise identical) scores.  The order inside a list depends on the
-    // arrival of the tiles; the NMS sorts by the unique (score, prior) key, so the result does not.
+  {
+    // Straight into the per-(image, class) lists the NMS reads.  The exact test comes first (a pre-filter hit whose
+    // score fails leaves nothing; a passing score is parked in the tile element it came from), then ONE shared-memory
+    // atomic per lane and class word reserves the lane's slots in the CTA's run of the class list, then the appends.
+    // The order inside a run depends on the warps' timing; the NMS sorts by the unique (score, prior) key, so the
+    // result does not.
     constexpr bool kStash = !kProbs && !kWrite;   // the tile element is free to hold the score once it has been tested
-    auto exact = [&](u32 rb, int c) {
+    auto exact = [&](u32 rb, int c) {   // two hits per trip: the chain load -> exp2 -> compare is latency-bound
       u32 keep = 0u;
       while (rb) {
-        const int r = __ffs(rb) - 1;
+        const int ra = __ffs(rb) - 1;
         rb &= rb - 1;
-        float* p = tile + r * C + c;
-        const float score = score_at(p, r);
-        if (score > thr) {
-          keep |= 1u << r;
-          if (kStash) *p = score;
+        const bool two = rb != 0u;
+        const int rb2 = two ? __ffs(rb) - 1 : ra;
+        rb &= rb - 1;
+        float* pa = tile + ra * C + c;
+        float* pb = tile + rb2 * C + c;
+        const float sa = score_at(pa, ra), sb = score_at(pb, rb2);
+        if (sa > thr) {
+          keep |= 1u << ra;
+          if (kStash) *pa = sa;
+        }
+        if (two && sb > thr) {
+          keep |= 1u << rb2;
+          if (kStash) *pb = sb;
         }
       }
       return keep;
@@ -302,7 +313,6 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
       t2 = lane < 16 ? (t2 & 0xffffu) : (lo & 0xffff0000u);
       c2 = 64 + (lane & 15);
     }
-    u32* cc = P.cls_cnt + (size_t)b * nfg;
     u32 p0 = 0u, p1 = 0u, p2 = 0u;
     const u32 x0 = exact(t0, lane);
     if (x0) p0 = atomicAdd(cc + lane, (u32)__popc(x0));
@@ -310,18 +320,26 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
     if (x1) p1 = atomicAdd(cc + 32 + lane, (u32)__popc(x1));
     const u32 x2 = nfg > 64 ? exact(t2, c2) : 0u;
     if (x2) p2 = atomicAdd(cc + c2, (u32)__popc(x2));
-    side_outputs();
-    u64* lb = P.lists + (size_t)b * nfg * P.list_cap;
+    u64* lb = P.lists + (size_t)b * nfg * P.list_cap + run_off;
     const u32 nbase = ~(u32)(j * 32);   // ~(32 j + r) = ~(32 j) - r
     auto append = [&](u32 xb, int c, u32 pos) {
       u64* dst = lb + (size_t)c * P.list_cap + pos;
-      while (xb) {
-        const int r = __ffs(xb) - 1;
-        xb &= xb - 1;
+      auto entry = [&](int r) {
         float* p = tile + r * C + c;
         const float score = kStash ? *p : score_at(p, r);
         const u32 sk = kProbs ? key32(score) : (__float_as_uint(score) | 0x80000000u);   // softmax scores are >= +0
-        *dst++ = ((u64)sk << 32) | (u64)(nbase - (u32)r);
+        return ((u64)sk << 32) | (u64)(nbase - (u32)r);
+      };
+      while (xb) {
+        const int ra = __ffs(xb) - 1;
+        xb &= xb - 1;
+        const bool two = xb != 0u;
+        const int rb2 = two ? __ffs(xb) - 1 : ra;
+        xb &= xb - 1;
+        const u64 ea = entry(ra), eb = entry(rb2);
+        dst[0] = ea;
+        if (two) dst[1] = eb;
+        dst += 2;
       }
     };
     append(x0, lane, p0); append(x1, 32 + lane, p1); append(x2, c2, p2);
@@ -330,40 +348,7 @@ __device__ __forceinline__ void filter_tile(const DetectParams& P, int b, int j,
         const float score = kProbs ? row[c] : row[c] * inv_s;
         if (score > thr) lb[(size_t)c * P.list_cap + atomicAdd(cc + c, 1u)] = ((u64)key32(score) << 32) | (u64)(~(u32)a);
       }
-  } else {
-  // One loop per class word tests and appends: the segment position of a lane comes from its number of
-  // PRE-FILTER hits, and the rare hit whose exact score fails (the pre-filter keeps a 0.1% margin) leaves a
-  // hole -- an entry of the class one past the last, which the bucketing pass drops.
-  int extra = 0;   // classes beyond 96 (row phase layout): counted here, emitted below
-  if (valid)
-    for (int c = 96; c < nfg; ++c) extra += ((kProbs ? row[c] : row[c] * inv_s) > thr) ? 1 : 0;
-  const int mine = __popc(t0) + __popc(t1) + __popc(t2) + extra;
-  int incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(SSDG_FULL, incl, o);
-    if (lane >= o) incl += v;
-  }
-  const size_t tix = (size_t)b * P.tpi + j;
-  if (lane == 31) P.tile_cnt[tix] = (u32)incl;
-  u64* dst = P.seg + tix * (size_t)(32 * nfg) + (incl - mine);
-  auto emit = [&](u32 rb, int c) {
-    while (rb) {
-      const int r = __ffs(rb) - 1;
-      rb &= rb - 1;
-      const float score = score_at(tile + r * C + c, r);
-      const u32 sk = kProbs ? key32(score) : (__float_as_uint(score) | 0x80000000u);   // softmax scores are >= +0
-      const u32 cls = score > thr ? (u32)c : (u32)nfg;
-      *dst++ = ((u64)sk << 32) | (u64)((cls << kABitsD) | (u32)(j * 32 + r));
-    }
-  };
-  emit(t0, lane); emit(t1, 32 + lane); emit(t2, 64 + lane);
-  if (valid)
-    for (int c = 96; c < nfg; ++c) {
-      const float score = kProbs ? row[c] : row[c] * inv_s;
-      if (score > thr) *dst++ = ((u64)key32(score) << 32) | (u64)(((u32)c << kABitsD) | (u32)a);
-    }
-  side_outputs();
+    side_outputs();
   }
   if (kProbs || !valid) return;
   if (kWrite && P.probs)
@@ -377,202 +362,113 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* gsrc, u32 bytes) {
 }
 
 template <typename TP, bool kProbs, bool kWrite>
-__global__ void SSDG_FILTER_BOUNDS filter_kernel(DetectParams P, int warps_per_cta, int prefetch, int chunked) {   // <= 64 registers: leaves room for a matcher CTA
+__global__ void SSDG_FILTER_BOUNDS filter_kernel(DetectParams P, int warps_per_cta, int prefetch) {   // <= 64 registers: leaves room for a matcher CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int C = P.C, A = P.A, tpi = P.tpi;
+  const int C = P.C, A = P.A, tpi = P.tpi, nfg = P.C - 1;
   const size_t tile_floats = (size_t)32 * C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* bufs = reinterpret_cast<float*>(smem_raw);
   u64* bars = reinterpret_cast<u64*>(smem_raw + (size_t)warps_per_cta * tile_floats * 4);
   float2* aux = reinterpret_cast<float2*>(bars + kFWarps) + 32 * warp;   // per row: -max*log2e, 1/sum
+  u32* scnt = reinterpret_cast<u32*>(reinterpret_cast<float2*>(bars + kFWarps) + 32 * kFWarps);   // [max_li][C-1] class counters of the run
+  const int ncnt = P.max_li * nfg;
+  for (int i = tid; i < ncnt; i += kFThreads) scnt[i] = 0u;
   if (tid == 0) {
     for (int i = 0; i < warps_per_cta; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
   }
   __syncthreads();
-  if (warp >= warps_per_cta) return;
-  // Tile walk.  Interleaved: warp g of the grid takes tiles g, g + G, ... (G warps in the grid).  Chunked: every CTA
-  // owns one contiguous run of tiles and its warps interleave inside it -- the tiles of an image then come from two
-  // or three CTAs spread over the whole kernel instead of from 273 warps at the same moment, which keeps the atomics
-  // on the image's class counters (direct lists) uncontended.
-  long long ntiles = (long long)P.B * tpi;
-  long long gw = (long long)blockIdx.x * warps_per_cta + warp;
-  long long stride = (long long)gridDim.x * warps_per_cta;
-  if (chunked) {
-    const long long chunk = (ntiles + gridDim.x - 1) / gridDim.x;
-    gw = (long long)blockIdx.x * chunk + warp;
-    ntiles = min(ntiles, (long long)(blockIdx.x + 1) * chunk);
-    stride = warps_per_cta;
-  }
-  float* tile = bufs + (size_t)warp * tile_floats;
-  u64* mybar = bars + warp;
-  const u64 pol = evict_first_policy();
+  // The CTA's run: tiles [run0, run1) of the batch; the warps interleave inside it.
+  const long long run0 = (long long)blockIdx.x * P.chunk;
+  const long long run1 = min((long long)P.B * tpi, run0 + P.chunk);
+  const int img0 = (int)(run0 / tpi);                 // first image of the run
+  const int j0 = (int)(run0 - (long long)img0 * tpi); // its first tile inside that image
+  if (warp < warps_per_cta) {
+    const long long gw = run0 + warp;
+    const int stride = warps_per_cta;
+    float* tile = bufs + (size_t)warp * tile_floats;
+    u64* mybar = bars + warp;
+    const u64 pol = evict_first_policy();
 
-  // (image, tile of the image) of the warp's current tile, advanced without divisions
-  int b = (int)(gw / tpi), j = (int)(gw - (long long)b * tpi);
-  const int step_b = (int)(stride / tpi), step_j = (int)(stride - (long long)step_b * tpi);
-  auto issue = [&](int ib, int ij) {  // lane 0 only
-    const u32 bytes = (u32)min(32, A - ij * 32) * (u32)C * 4u;
-    mbar_arrive_expect_tx(mybar, bytes);
-    tma_load_hint(tile, P.pred_cls + ((size_t)ib * A + (size_t)ij * 32) * C, bytes, mybar, pol);
-  };
-  // One tile in flight per warp; the other 15 warps of the CTA hide its latency.  That alone leaves too few bytes in
-  // flight towards DRAM (a buffer that is being computed on requests nothing): the warp also asks L2 for the tile it
-  // will load `prefetch` rounds later, so the bulk copy into shared memory finds its lines in L2.
-  // (image, tile) of the tile `prefetch` + 1 rounds ahead, walked like (b, j)
-  int pb = 0, pj = 0;
-  {
-    const long long tp = gw + (long long)(prefetch + 1) * stride;
-    pb = (int)(tp / tpi); pj = (int)(tp - (long long)pb * tpi);
-  }
-  long long tpf = gw + (long long)(prefetch + 1) * stride;   // index of the tile (pb, pj)
-  auto prefetch_at = [&](int ib, int ij) {  // lane 0 only
-    if (ib >= P.B) return;
-    prefetch_l2_bulk(P.pred_cls + ((size_t)ib * A + (size_t)ij * 32) * C, (u32)min(32, A - ij * 32) * (u32)C * 4u);
-  };
-  if (P.tma_ok && lane == 0 && gw < ntiles) {
-    issue(b, j);
-    for (int d = 1; d <= prefetch; ++d) {
-      const long long tp = gw + d * stride;
-      if (tp < ntiles) prefetch_at((int)(tp / tpi), (int)(tp % tpi));
-    }
-  }
-  int k = 0;
-  for (long long t = gw; t < ntiles; t += stride, ++k) {
-    const int rows = min(32, A - j * 32);
-    if (P.tma_ok) {
-      mbar_wait(mybar, (u32)(k & 1));
-    } else {  // unaligned shapes: plain cooperative copy
-      const float* g = P.pred_cls + ((size_t)b * A + (size_t)j * 32) * C;
-      for (int i = lane; i < rows * C; i += 32) tile[i] = g[i];
-      __syncwarp();
-    }
-    filter_tile<TP, kProbs, kWrite>(P, b, j, rows, tile, aux, lane);
-    // the next bulk copy (async proxy) overwrites rows this warp has just written
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    if (!kProbs && kWrite && P.probs) {  // the tile layout in shared memory equals the layout in global memory
-      float* dst = P.probs + ((size_t)b * A + (size_t)j * 32) * C;
-      for (int i = lane; i < rows * C; i += 32) __stcs(&dst[i], tile[i]);
-      __syncwarp();
-    }
-    b += step_b; j += step_j;
-    if (j >= tpi) { j -= tpi; ++b; }
-    if (P.tma_ok && lane == 0 && t + stride < ntiles) {
+    // (image, tile of the image) of the warp's current tile, advanced without divisions
+    int b = (int)(gw / tpi), j = (int)(gw - (long long)b * tpi);
+    const int step_b = stride / tpi, step_j = stride - step_b * tpi;
+    auto issue = [&](int ib, int ij) {  // lane 0 only
+      const u32 bytes = (u32)min(32, A - ij * 32) * (u32)C * 4u;
+      mbar_arrive_expect_tx(mybar, bytes);
+      tma_load_hint(tile, P.pred_cls + ((size_t)ib * A + (size_t)ij * 32) * C, bytes, mybar, pol);
+    };
+    // One tile in flight per warp; the other 15 warps of the CTA hide its latency.  That alone leaves too few bytes
+    // in flight towards DRAM (a buffer that is being computed on requests nothing): the warp also asks L2 for the
+    // tile it will load `prefetch` rounds later, so the bulk copy into shared memory finds its lines in L2.
+    // (image, tile) of the tile `prefetch` + 1 rounds ahead, walked like (b, j)
+    long long tpf = gw + (long long)(prefetch + 1) * stride;
+    int pb = (int)(tpf / tpi), pj = (int)(tpf - (long long)pb * tpi);
+    auto prefetch_at = [&](int ib, int ij) {  // lane 0 only
+      prefetch_l2_bulk(P.pred_cls + ((size_t)ib * A + (size_t)ij * 32) * C, (u32)min(32, A - ij * 32) * (u32)C * 4u);
+    };
+    if (P.tma_ok && lane == 0 && gw < run1) {
       issue(b, j);
-      if (prefetch > 0 && tpf < ntiles) prefetch_at(pb, pj);
-    }
-    tpf += stride;
-    pb += step_b; pj += step_j;
-    if (pj >= tpi) { pj -= tpi; ++pb; }
-  }
-}
-
-// Counting sort of one image's candidates by class (shared-memory histogram, scan, scatter).
-__global__ void __launch_bounds__(kBucketThreads, 2) bucket_kernel(DetectParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int nfg = P.C - 1, tpi = P.tpi, b = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nb = nfg;                             // entries of class nfg are the holes of the filter pass: dropped
-  u32* hist = reinterpret_cast<u32*>(smem_raw);   // [nb]
-  u32* off = hist + nb;                           // [nb]
-  u32* tpre = off + nb;                          // [tpi + 1] exclusive prefix of the tile counts
-  for (int c = tid; c < nb; c += kBucketThreads) hist[c] = 0u;
-  const u32* tcnt = P.tile_cnt + (size_t)b * tpi;
-  const size_t tstride = (size_t)32 * nfg;
-  const u64* seg = P.seg + (size_t)b * tpi * tstride;
-  if (warp == 0) {
-    u32 running = 0u;
-    for (int j0 = 0; j0 < tpi; j0 += 32) {
-      const int j = j0 + lane;
-      const u32 cnt = j < tpi ? tcnt[j] : 0u;
-      u32 incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u32 v = __shfl_up_sync(SSDG_FULL, incl, o);
-        if (lane >= o) incl += v;
-      }
-      if (j < tpi) tpre[j] = running + incl - cnt;
-      running += __shfl_sync(SSDG_FULL, incl, 31);
-    }
-    if (lane == 0) tpre[tpi] = running;
-  }
-  __syncthreads();
-  // Each warp takes four tiles at a time: the first 128 entries of each (nearly all of them, for trained-like scores:
-  // ~57 candidates + ~34 holes per tile) are loaded up front, so sixteen independent loads per lane are in flight.
-  constexpr int kBW = kBucketThreads / 32;
-  constexpr int kUp = 4;
-  auto for_tiles = [&](auto&& visit) {
-    for (int j0 = warp * 4; j0 < tpi; j0 += kBW * 4) {
-      u64 v[4][kUp];
-      int cnt[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int j = j0 + q;
-        cnt[q] = j < tpi ? (int)(tpre[j + 1] - tpre[j]) : 0;
-        const u64* sp = seg + (size_t)j * tstride;
-#pragma unroll
-        for (int u = 0; u < kUp; ++u) v[q][u] = lane + 32 * u < cnt[q] ? sp[lane + 32 * u] : 0ull;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-#pragma unroll
-        for (int u = 0; u < kUp; ++u)
-          if (lane + 32 * u < cnt[q]) visit(v[q][u]);
-        if (cnt[q] > 32 * kUp) {
-          const u64* sp = seg + (size_t)(j0 + q) * tstride;
-          for (int e = lane + 32 * kUp; e < cnt[q]; e += 32) visit(sp[e]);
-        }
+      for (int d = 1; d <= prefetch; ++d) {
+        const long long tp = gw + (long long)d * stride;
+        if (tp < run1) prefetch_at((int)(tp / tpi), (int)(tp % tpi));
       }
     }
-  };
-  for_tiles([&](u64 v) {
-    const u32 c = (u32)v >> kABitsD;
-    if (c < (u32)nfg) atomicAdd(&hist[c], 1u);
-  });
-  __syncthreads();
-  if (warp == 0) {
-    u32 running = 0u;
-    for (int c0 = 0; c0 < nb; c0 += 32) {
-      const int c = c0 + lane;
-      const u32 cnt = c < nb ? hist[c] : 0u;
-      u32 incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u32 v = __shfl_up_sync(SSDG_FULL, incl, o);
-        if (lane >= o) incl += v;
+    int k = 0;
+    for (long long t = gw; t < run1; t += stride, ++k) {
+      const int rows = min(32, A - j * 32);
+      if (P.tma_ok) {
+        mbar_wait(mybar, (u32)(k & 1));
+      } else {  // unaligned shapes: plain cooperative copy
+        const float* g = P.pred_cls + ((size_t)b * A + (size_t)j * 32) * C;
+        for (int i = lane; i < rows * C; i += 32) tile[i] = g[i];
+        __syncwarp();
       }
-      if (c < nb) off[c] = running + incl - cnt;
-      if (c < nfg) {
-        P.cls_cnt[(size_t)b * nfg + c] = cnt;
-        P.cls_off[(size_t)b * nfg + c] = running + incl - cnt;
+      // the run's slots in the lists of image b start at its first tile of b
+      filter_tile<TP, kProbs, kWrite>(P, b, j, rows, tile, aux, lane, scnt + (b - img0) * nfg, b == img0 ? (u32)j0 * 32u : 0u);
+      // the next bulk copy (async proxy) overwrites rows this warp has just written
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (!kProbs && kWrite && P.probs) {  // the tile layout in shared memory equals the layout in global memory
+        float* dst = P.probs + ((size_t)b * A + (size_t)j * 32) * C;
+        for (int i = lane; i < rows * C; i += 32) __stcs(&dst[i], tile[i]);
+        __syncwarp();
       }
-      running += __shfl_sync(SSDG_FULL, incl, 31);
+      b += step_b; j += step_j;
+      if (j >= tpi) { j -= tpi; ++b; }
+      if (P.tma_ok && lane == 0 && t + stride < run1) {
+        issue(b, j);
+        if (prefetch > 0 && tpf < run1) prefetch_at(pb, pj);
+      }
+      tpf += stride;
+      pb += step_b; pj += step_j;
+      if (pj >= tpi) { pj -= tpi; ++pb; }
     }
   }
   __syncthreads();
-  u64* out = P.sorted + (size_t)b * tpi * tstride;
-  for_tiles([&](u64 v) {
-    const u32 low = (u32)v;
-    if ((low >> kABitsD) >= (u32)nfg) return;
-    const u32 pos = atomicAdd(&off[low >> kABitsD], 1u);
-    out[pos] = (v & 0xffffffff00000000ull) | (u64)(~(low & ((1u << kABitsD) - 1u)));
-  });
+  // the counts of the run, per image it touched
+  const int img1 = run1 > run0 ? (int)((run1 - 1) / tpi) : img0 - 1;
+  for (int li = 0; li <= img1 - img0; ++li) {
+    const int bi = img0 + li;
+    const int slot = (int)blockIdx.x - (int)(((long long)bi * tpi) / P.chunk);
+    u32* out = P.run_cnt + ((size_t)bi * P.max_slots + slot) * nfg;
+    for (int i = tid; i < nfg; i += kFThreads) out[i] = scnt[li * nfg + i];
+  }
 }
 
 // ---- per-(image, class) NMS ---------------------------------------------------------------------------
 struct NmsParams {
-  const u32* cls_cnt;
-  const u32* cls_off;
-  const u64* sorted;
-  size_t img_stride;   // candidates capacity per image in `sorted`
+  const u64* lists;    // [B][C-1][list_cap], see DetectParams
+  const u32* run_cnt;  // [B][max_slots][C-1]
+  size_t list_cap;
+  int tpi, chunk, max_slots;
   const float* boxes;  // [B,A,4]
   int A, n_fg, top_k, sortn;  // sortn: power of two >= max(top_k, 32)
   float iou_thresh;
   int* out_kept;
   int* out_count;
   float* out_score;
-  // host-computed constants of the join (nms2_kernel)
+  // host-computed constants of the join (nms_kernel)
   int B;
   int fast_ok;         // 0 < iou_thresh < 1e6: the division-free pre-test exists
   float q, tq0, inv_l; // thr/(1+thr); shrink factor of the slab intervals; 1 / log2 of the size-class ratio
@@ -581,466 +477,38 @@ struct NmsParams {
 // The NMS kernel is instruction-cache sensitive (12 CTAs per SM in different phases): its block-stride loops
 // stay rolled (3280 -> 2240 SASS instructions, 7% faster).
 #define NMS_LOOP _Pragma("unroll 1")
-__global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // sortn keys take part in the sort; only the first mcap = top_k rounded up to 32 boxes exist afterwards
-  const int sortn = P.sortn, mcap = (P.top_k + 31) & ~31, W = mcap >> 5, RL = (4 * W) | 1;
-  const int RS = (2 * W) | 1;
-  const int tabn = (max(512, kSlabs * RL) + kSizeCls * RS + 3) & ~3;   // words, whole uint4s
-  u64* keys = reinterpret_cast<u64*>(smem_raw);                 // [sortn]
-  float4* crn = reinterpret_cast<float4*>(keys + sortn);        // [mcap] x1,y1,x2,y2 (sort scratch: sortn keys)
-  u32* hist = reinterpret_cast<u32*>(crn + mcap);               // [256] sort / select histogram
-  u32* bstart = hist + 256;                                     // [256] rank sort: first slot of each bucket
-  u32* tab = hist;                                              // [kSlabs][RL] interval tables of the join (after the sort)
-  u32* stab = tab + max(512, kSlabs * RL);                      // [kSizeCls][RS] width / height class neighbourhoods
-  float* qlo = reinterpret_cast<float*>(tab + tabn);            // [mcap] q*area*0.9999
-  float* area = qlo + mcap;                                     // [mcap]
-  u32* slidx = reinterpret_cast<u32*>(area + mcap);             // [mcap] slab intervals and size classes of the box
-  u32* sup = slidx + mcap;                                      // lower triangle, [group g][word w <= g][row of the group]
-  u32* unres = sup + (size_t)16 * W * (W + 1);                  // [mcap] rows the join could not keep at once
-  float* dom = reinterpret_cast<float*>(unres + mcap);          // [4*kNmsWarps] per-warp extents of the boxes
-  u32* mm = reinterpret_cast<u32*>(dom + 4 * kNmsWarps);        // [4*kNmsWarps] per-warp min/max of the score and prior words
-  u32* keptw = mm + 4 * kNmsWarps;                              // [W]
-  u32* remw = keptw + W;                                        // [W]
-  __shared__ int n_unres;
-  __shared__ u64 sel_prefix;
-  __shared__ int sel_k, sel_fill;
-
-  const size_t list = blockIdx.x;
-  const int b = (int)(blockIdx.x / (u32)P.n_fg);
-  int n = (int)P.cls_cnt[list];
-  const bool selected = n > P.sortn;   // more candidates than the sort takes: radix select first
-  const u64* cl = P.cls_off ? P.sorted + (size_t)b * P.img_stride + P.cls_off[list]
-                            : P.sorted + list * P.img_stride;   // direct mode: one list per (image, class)
-
-  u32 hmin = ~0u, hmax = 0u, lmin = ~0u, lmax = 0u;   // range of the score and prior words of the keys
-  if (n <= sortn) {
-    NMS_LOOP
-    for (int i = tid; i < n; i += kNmsThreads) {
-      const u64 v = cl[i];
-      keys[i] = v;
-      hmin = min(hmin, (u32)(v >> 32)); hmax = max(hmax, (u32)(v >> 32));
-      lmin = min(lmin, (u32)v); lmax = max(lmax, (u32)v);
-    }
-  } else {
-    // Radix select of the top_k-th largest composite key (keys are unique), 8 bits per pass.
-    if (tid == 0) { sel_prefix = 0ull; sel_k = P.top_k; sel_fill = 0; }
-    __syncthreads();
-    for (int shift = 56; shift >= 0; shift -= 8) {
-      NMS_LOOP
-      for (int i = tid; i < 256; i += kNmsThreads) hist[i] = 0u;
-      __syncthreads();
-      const u64 pre = sel_prefix;
-      const u64 hmask = shift == 56 ? 0ull : (~0ull << (shift + 8));
-      NMS_LOOP
-      for (int i = tid; i < n; i += kNmsThreads) {
-        const u64 v = cl[i];
-        if ((v & hmask) == pre) atomicAdd(&hist[(u32)(v >> shift) & 255u], 1u);
-      }
-      __syncthreads();
-      if (tid == 0) {
-        int k = sel_k, acc = 0, d = 255;
-        for (; d > 0; --d) {
-          if (acc + (int)hist[d] >= k) break;
-          acc += (int)hist[d];
-        }
-        sel_k = k - acc;
-        sel_prefix = pre | ((u64)d << shift);
-      }
-      __syncthreads();
-    }
-    const u64 kth = sel_prefix;
-    NMS_LOOP
-    for (int i = tid; i < n; i += kNmsThreads) {
-      const u64 v = cl[i];
-      if (v >= kth) {
-        const int p = atomicAdd(&sel_fill, 1);
-        if (p < sortn) keys[p] = v;
-      }
-    }
-    __syncthreads();
-    n = min(sel_fill, sortn);
-  }
-  // Rank sort, descending (keys are unique).  256 buckets, monotone in the key: by the score word, scaled to
-  // the list's own [min, max] -- or by the prior word when every score is the same.  rank = elements in
-  // higher buckets + elements of the own bucket with a larger key; buckets hold a couple of keys each unless
-  // the scores are pathologically clustered (then the count loop gets long, the result stays exact).
-  {
-    u64* tmp = reinterpret_cast<u64*>(crn);   // [n] keys grouped by bucket; crn is filled after the sort
-    NMS_LOOP
-    for (int i = tid; i < 256; i += kNmsThreads) hist[i] = 0u;
-    if (selected) {   // the keys came out of the select: scan them
-      NMS_LOOP
-      for (int i = tid; i < n; i += kNmsThreads) {
-        const u64 v = keys[i];
-        hmin = min(hmin, (u32)(v >> 32)); hmax = max(hmax, (u32)(v >> 32));
-        lmin = min(lmin, (u32)v); lmax = max(lmax, (u32)v);
-      }
-    }
-    hmin = __reduce_min_sync(SSDG_FULL, hmin); hmax = __reduce_max_sync(SSDG_FULL, hmax);
-    lmin = __reduce_min_sync(SSDG_FULL, lmin); lmax = __reduce_max_sync(SSDG_FULL, lmax);
-    if (lane == 0) { mm[4 * warp] = hmin; mm[4 * warp + 1] = hmax; mm[4 * warp + 2] = lmin; mm[4 * warp + 3] = lmax; }
-    __syncthreads();
-    {
-      const uint4 p0 = reinterpret_cast<const uint4*>(mm)[0];
-      hmin = p0.x; hmax = p0.y; lmin = p0.z; lmax = p0.w;
-#pragma unroll
-      for (int w = 1; w < kNmsWarps; ++w) {
-        const uint4 pw = reinterpret_cast<const uint4*>(mm)[w];
-        hmin = min(hmin, pw.x); hmax = max(hmax, pw.y); lmin = min(lmin, pw.z); lmax = max(lmax, pw.w);
-      }
-    }
-    const bool byscore = hmax > hmin;
-    const u32 kbase = byscore ? hmin : lmin;
-    const float kscale = 256.f / ((float)((byscore ? hmax : lmax) - kbase) + 1.f);
-    auto bucket = [&](u64 v) {   // conversions, the product and the truncation are all monotone
-      const u32 x = (byscore ? (u32)(v >> 32) : (u32)v) - kbase;
-      return min(255, (int)((float)x * kscale));
-    };
-    NMS_LOOP
-    for (int i = tid; i < n; i += kNmsThreads) atomicAdd(&hist[bucket(keys[i])], 1u);
-    __syncthreads();
-    if (warp == 0) {   // start[b] = number of keys in buckets above b; lane l owns buckets 255-8l .. 248-8l
-      u32 c[8], tot = 0u;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) { c[r] = hist[255 - 8 * lane - r]; tot += c[r]; }
-      u32 incl = tot;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u32 v = __shfl_up_sync(SSDG_FULL, incl, o);
-        if (lane >= o) incl += v;
-      }
-      u32 run = incl - tot;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) { bstart[255 - 8 * lane - r] = run; hist[255 - 8 * lane - r] = run; run += c[r]; }
-    }
-    __syncthreads();
-    NMS_LOOP
-    for (int i = tid; i < n; i += kNmsThreads) {
-      const u64 v = keys[i];
-      tmp[atomicAdd(&hist[bucket(v)], 1u)] = v;   // hist[b] ends as the end of bucket b
-    }
-    __syncthreads();
-    NMS_LOOP
-    for (int i = tid; i < n; i += kNmsThreads) {
-      const u64 v = tmp[i];
-      const int bk = bucket(v);
-      const int s0 = (int)bstart[bk], s1 = (int)hist[bk];
-      int r = s0;
-      for (int t = s0; t < s1; ++t) r += tmp[t] > v;
-      keys[r] = v;
-    }
-    __syncthreads();
-  }
-  const int m = min(n, P.top_k);
-  const int mpad = (m + 31) & ~31;
-
-  // Decoded boxes; corners in the formula's own float32 operations (utils/bbox.py:13-21).
-  // qa = q*(area + 0.5e-10), q = thr/(1+thr):  iou > thr  <=>  inter > qa_i + qa_j  in exact arithmetic
-  // (positive denominator); boxes that can never overlap anything (w <= 0, h <= 0, non-finite, padding)
-  // get qa = +inf so the fast test rejects them exactly like the formula does (their intersection is 0).
-  const float thr = P.iou_thresh;
-  const bool fast_ok = thr > 0.f && thr < 1e6f;
-  const float q = fast_ok ? thr / (1.f + thr) : 0.f;
-  // The same pass collects what the join needs: the extents of all sane boxes (slab domain) and whether every
-  // box's corner extents reproduce its area to 0.1% (always, unless a box is a few ulps wide).
-  int inexact = 0;
-  u32 k1 = ~0u, k2 = ~0u, k3 = 0u, k4 = 0u;
-  NMS_LOOP
-  for (int i = tid; i < mpad; i += kNmsThreads) {
-    float4 cr = make_float4(0.f, 0.f, 0.f, 0.f);
-    float ar = 0.f, qa = CUDART_INF_F;
-    if (i < m) {
-      const int a = (int)(~(u32)keys[i]);
-      const float4 bx = __ldg(reinterpret_cast<const float4*>(P.boxes) + (size_t)b * P.A + a);
-      const float hw = __fmul_rn(bx.z, 0.5f), hh = __fmul_rn(bx.w, 0.5f);
-      cr = make_float4(__fsub_rn(bx.x, hw), __fsub_rn(bx.y, hh), __fadd_rn(bx.x, hw), __fadd_rn(bx.y, hh));
-      ar = __fmul_rn(bx.z, bx.w);
-      const bool sane = bx.z > 0.f && bx.w > 0.f && isfinite(cr.x) && isfinite(cr.y) && isfinite(cr.z) &&
-                        isfinite(cr.w) && isfinite(ar);
-      if (sane) {
-        qa = q * (ar + 0.5e-10f);
-        const float pr = (cr.z - cr.x) * (cr.w - cr.y);
-        inexact |= !(ar >= 0.999f * pr && ar <= 1.001f * pr);
-        k1 = min(k1, key32(cr.x)); k2 = min(k2, key32(cr.y)); k3 = max(k3, key32(cr.z)); k4 = max(k4, key32(cr.w));
-      }
-    }
-    crn[i] = cr;
-    area[i] = ar;
-    qlo[i] = qa * 0.9999f;
-  }
-  k1 = __reduce_min_sync(SSDG_FULL, k1); k2 = __reduce_min_sync(SSDG_FULL, k2);
-  k3 = __reduce_max_sync(SSDG_FULL, k3); k4 = __reduce_max_sync(SSDG_FULL, k4);
-  if (lane == 0) reinterpret_cast<float4*>(dom)[warp] = make_float4(unkey32(k1), unkey32(k2), unkey32(k3), unkey32(k4));
-  NMS_LOOP
-  for (int i = tid; i < W; i += kNmsThreads) { keptw[i] = 0u; remw[i] = 0u; }
-  if (tid == 0) n_unres = 0;
-  // the sort is done with hist / bstart: the join tables take their place
-  NMS_LOOP
-  for (int i = tid; i < (tabn >> 2); i += kNmsThreads) reinterpret_cast<uint4*>(tab)[i] = make_uint4(0u, 0u, 0u, 0u);
-  inexact = __syncthreads_or(inexact);
-
-  // Suppression bits, lower triangle: sup(i, w) bit l  <=>  iou(box_{32w+l}, box_i) > thresh, 32w+l < i.
-  if (fast_ok) {
-    // Slab join.  iou(i, j) > thr means inter > q (area_i + area_j) with q = thr / (1 + thr); the y overlap is
-    // at most min(h_i, h_j), so the x overlap exceeds q (w_i + w_j): the x extents of i and j, each SHRUNK by
-    // q times its width at both ends, still meet (and the same in y).  Every box gets the interval of slabs (32
-    // per axis) its shrunk extents touch; only the pairs whose intervals meet in both axes -- a few percent of
-    // all pairs -- get the overlap test.  The bound is stated in the formula's areas w*h; it carries over to
-    // the corner extents unless `inexact` -- then nothing is shrunk.
-    float dx0, dy0, dsx, dsy, lwx, lwy;
-    {
-      float4 e = reinterpret_cast<const float4*>(dom)[0];
-#pragma unroll
-      for (int w = 1; w < kNmsWarps; ++w) {
-        const float4 f = reinterpret_cast<const float4*>(dom)[w];
-        e.x = fminf(e.x, f.x); e.y = fminf(e.y, f.y); e.z = fmaxf(e.z, f.z); e.w = fmaxf(e.w, f.w);
-      }
-      dx0 = e.x; dy0 = e.y;
-      dsx = (e.z > e.x) ? (float)kSlabs / (e.z - e.x) : 0.f;
-      dsy = (e.w > e.y) ? (float)kSlabs / (e.w - e.y) : 0.f;
-      lwx = (e.z > e.x) ? __log2f(e.z - e.x) : 0.f;
-      lwy = (e.w > e.y) ? __log2f(e.w - e.y) : 0.f;
-    }
-    auto slab = [&](float v, float o, float sc) {   // monotone in v
-      const float f = (v - o) * sc;
-      return f >= (float)(kSlabs - 1) ? kSlabs - 1 : (f > 0.f ? (int)f : 0);
-    };
-    // 0.98: inter > q (a_i + a_j) and the 0.1% above leave ex > 0.997 q (w'_i + w'_j); the guard g covers the
-    // float rounding of the shrunk ends (a few ulps of the coordinates)
-    const float tq = inexact ? 0.f : fminf(0.98f * q, 0.49f);
-    // Every box has a slab interval [a, b] per axis; two intervals meet  <=>  a_j <= b_i  and  b_j >= a_i.
-    // Tables per axis, one bitset over the boxes per slab s:  LE[s] = {j : a_j <= s},  GE[s] = {j : b_j >= s}
-    // -- the boxes whose x interval meets box i's are  LE[b_i] & GE[a_i]:  two loads per axis whatever the
-    // width.  Built by registering each box at its two end slabs, then a running OR along the slabs.
-    // Layout tab[slab][RL], column = kind * W + word (kind: LEx, GEx, LEy, GEy); RL odd: lanes with different
-    // slabs (queries) or different columns (the running OR) hit different banks.
-    // Size classes.  iou > thr needs  inter > t' E_i  (E = extent product, within 0.1% of the formula's area;
-    // t' = 0.99 thr / (1 + 0.001 thr)) and inter <= w_j h_i:  the widths -- and the heights -- of a pair differ by
-    // less than a factor 1/t', so with classes of that ratio a pair's classes differ by at most one.  A box
-    // registers in its class; the neighbourhood {c-1, c, c+1} is ORed below; the query ANDs both dimensions.
-    const float tp = 0.99f * thr / (1.f + 0.001f * thr);
-    const float inv_l = (!inexact && tp < 0.98f) ? -1.f / __log2f(tp) : 0.f;
-    auto size_cls = [&](float ext, float lref) {   // monotone in ext, clamped (clamping only merges classes)
-      const float f = (lref - __log2f(ext)) * inv_l;
-      return f >= (float)(kSizeCls - 1) ? kSizeCls - 1 : (f > 0.f ? (int)f : 0);
-    };
-    NMS_LOOP
-    for (int i = tid; i < m; i += kNmsThreads) {
-      if (!isfinite(qlo[i])) { slidx[i] = 0u; continue; }
-      const float4 c = crn[i];
-      const u32 bit = 1u << (i & 31);
-      const int wi = i >> 5;
-      const float sx = tq * (c.z - c.x) - 1e-6f * (fabsf(c.x) + fabsf(c.z));
-      const float sy = tq * (c.w - c.y) - 1e-6f * (fabsf(c.y) + fabsf(c.w));
-      const int ax = slab(c.x + sx, dx0, dsx), bx = max(slab(c.z - sx, dx0, dsx), ax);
-      const int ay = slab(c.y + sy, dy0, dsy), by = max(slab(c.w - sy, dy0, dsy), ay);
-      const int cw = inv_l > 0.f ? size_cls(c.z - c.x, lwx) : 0, ch = inv_l > 0.f ? size_cls(c.w - c.y, lwy) : 0;
-      slidx[i] = (u32)ax | ((u32)bx << 5) | ((u32)ay << 10) | ((u32)by << 15) | ((u32)cw << 20) | ((u32)ch << 24);
-      atomicOr(&tab[ax * RL + wi], bit);
-      atomicOr(&tab[bx * RL + W + wi], bit);
-      atomicOr(&tab[ay * RL + 2 * W + wi], bit);
-      atomicOr(&tab[by * RL + 3 * W + wi], bit);
-      atomicOr(&stab[cw * RS + wi], bit);
-      atomicOr(&stab[ch * RS + W + wi], bit);
-    }
-    __syncthreads();
-    NMS_LOOP
-    for (int col = tid; col < 6 * W; col += kNmsThreads) {
-      if (col < 4 * W) {
-        const bool up = ((col / W) & 1) == 0;   // LE: ascending running OR, GE: descending
-        u32 acc = 0u;
-#pragma unroll 8
-        for (int k = 0; k < kSlabs; ++k) {
-          const int sl = up ? k : kSlabs - 1 - k;
-          acc |= tab[sl * RL + col];
-          tab[sl * RL + col] = acc;
-        }
-      } else {
-        u32* sc = stab + (col - 4 * W);
-        u32 prev = 0u, cur = sc[0];
-#pragma unroll 4
-        for (int k = 0; k < kSizeCls; ++k) {
-          const u32 nxt = k + 1 < kSizeCls ? sc[(k + 1) * RS] : 0u;
-          sc[k * RS] = prev | cur | nxt;
-          prev = cur; cur = nxt;
-        }
-      }
-    }
-    __syncthreads();
-    NMS_LOOP
-    for (int i = tid; i < mpad; i += kNmsThreads) {   // whole warps: rows 32g .. 32g+31
-      const int gi = i >> 5;
-      const bool live = i < m;
-      const float4 bi = live ? crn[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float qi_lo = live ? qlo[i] : CUDART_INF_F;
-      const bool sane = isfinite(qi_lo);
-      const u32 si = live ? slidx[i] : 0u;
-      const u32* lex = tab + ((si >> 5) & 31u) * RL;             // LEx[b_i]
-      const u32* gex = tab + (si & 31u) * RL + W;                // GEx[a_i]
-      const u32* ley = tab + ((si >> 15) & 31u) * RL + 2 * W;    // LEy[b_i]
-      const u32* gey = tab + ((si >> 10) & 31u) * RL + 3 * W;    // GEy[a_i]
-      const u32* szw = stab + ((si >> 20) & 15u) * RS;           // width classes next to the row's
-      const u32* szh = stab + (si >> 24) * RS + W;               // height classes
-      const float ai = live ? area[i] : 0.f;
-      u32 any = 0u;
-      auto word = [&](int w) {
-        u32 cand = sane ? (lex[w] & gex[w] & ley[w] & gey[w] & szw[w] & szh[w]) : 0u;
-        if (w == gi) cand &= (1u << (i & 31)) - 1u;
-        u32 bits = 0u;
-        while (cand) {
-          const int jj = __ffs(cand) - 1;
-          cand &= cand - 1;
-          const int j = (w << 5) + jj;
-          const float4 bj = crn[j];
-          const float fx = fminf(bi.z, bj.z) - fmaxf(bi.x, bj.x);
-          const float fy = fminf(bi.w, bj.w) - fmaxf(bi.y, bj.y);
-          if (!(fx > 0.f && fx * fy >= qi_lo + qlo[j])) continue;   // cheap float test, 1e-4 margin
-          // the formula itself: IEEE float32, no contraction (utils/bbox.py:13-25)
-          const float ex = fmaxf(0.f, __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
-          const float ey = fmaxf(0.f, __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
-          const float inter = __fmul_rn(ex, ey);
-          const float den = __fadd_rn(__fsub_rn(__fadd_rn(area[j], ai), inter), 1e-10f);
-          if (__fdiv_rn(inter, den) > thr) bits |= 1u << jj;
-        }
-        sup[16 * gi * (gi + 1) + (w << 5) + lane] = bits;
-        any |= bits;
-      };
-      // (a rolled loop: unrolling the words into immediates offsets measured 7% slower -- instruction cache)
-#pragma unroll 1
-      for (int w = 0; w <= gi; ++w) word(w);
-      // rows nobody suppresses are kept at once; the others are listed for the resolution below
-      const u32 free_rows = __ballot_sync(SSDG_FULL, live && any == 0u);
-      const u32 open_rows = __ballot_sync(SSDG_FULL, live && any != 0u);
-      if (lane == 0) keptw[gi] = free_rows;
-      if (open_rows) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&n_unres, __popc(open_rows));
-        base = __shfl_sync(SSDG_FULL, base, 0);
-        if (live && any != 0u) unres[base + __popc(open_rows & ((1u << lane) - 1u))] = (u32)i;
-      }
-    }
-  } else {
-  // No division-free test for this threshold: all pairs, the formula itself.
-  // Task (g, w<=g): lane = row 32g+lane, loop over the 32 columns of group w (uniform shared loads).
-  const int ngroups = mpad >> 5;
-  const int ntasks = ngroups * (ngroups + 1) / 2;
-  for (int task = warp; task < ntasks; task += kNmsWarps) {
-    int g = 0;
-    while ((g + 1) * (g + 2) / 2 <= task) ++g;
-    const int w = task - g * (g + 1) / 2;
-    const int i = (g << 5) + lane;
-    const float4 bi = crn[i];
-    // every pair that can exceed the threshold passes the cheap float test (1e-4 relative margin,
-    // float rounding is ~1e-7); the rare survivors are decided by the formula itself
-    u32 maybe = 0u;
-    const float qi_lo = qlo[i];
-#pragma unroll
-    for (int jj = 0; jj < 32; ++jj) {
-      const int j = (w << 5) + jj;
-      const float4 bj = crn[j];
-      const float ex = fminf(bi.z, bj.z) - fmaxf(bi.x, bj.x);
-      const float ey = fminf(bi.w, bj.w) - fmaxf(bi.y, bj.y);
-      const u32 hit = (u32)(ex > 0.f) & (u32)(ex * ey >= qi_lo + qlo[j]);   // no branch
-      maybe |= hit << jj;
-    }
-    if (!fast_ok) maybe = 0xffffffffu;
-    if (w == g) maybe &= (1u << lane) - 1u;
-    if (i >= m) maybe = 0u;
-    u32 bits = 0u;
-    while (maybe) {   // IEEE float32, no contraction (utils/bbox.py:13-25)
-      const int jj = __ffs(maybe) - 1;
-      maybe &= maybe - 1;
-      const int j = (w << 5) + jj;
-      if (j >= m) continue;
-      const float4 bj = crn[j];
-      const float ex = fmaxf(0.f, __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
-      const float ey = fmaxf(0.f, __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
-      const float inter = __fmul_rn(ex, ey);
-      const float den = __fadd_rn(__fsub_rn(__fadd_rn(area[j], area[i]), inter), 1e-10f);
-      if (__fdiv_rn(inter, den) > thr) bits |= 1u << jj;
-    }
-    sup[16 * g * (g + 1) + (w << 5) + lane] = bits;
-  }
-  NMS_LOOP
-  for (int i = tid; i < m; i += kNmsThreads) unres[i] = (u32)i;
-  if (tid == 0) n_unres = m;
-  }
-  __syncthreads();
-
-  // fixed point of  kept(i) <=> no kept j < i with sup(i, j);  removed(i) <=> some kept j < i with sup(i, j)
-  // over the listed rows, by one warp (a handful of rows per list: no CTA-wide barrier per round); then
-  // hist[w] = kept boxes before word w for the output
-  if (warp == 0) {
-    const int nu = n_unres;
-    for (;;) {
-      bool unknown = false;
-      for (int k = lane; k < nu; k += 32) {
-        const int i = (int)unres[k], gi = i >> 5;
-        const u32 bit = 1u << (i & 31);
-        if ((keptw[gi] | remw[gi]) & bit) continue;
-        bool hit_kept = false, all_removed = true;
-        const int sbase = 16 * gi * (gi + 1) + (i & 31);
-        for (int w = 0; w <= gi; ++w) {
-          const u32 sb = sup[sbase + (w << 5)];
-          if (sb & keptw[w]) hit_kept = true;
-          if (sb & ~remw[w]) all_removed = false;
-        }
-        if (hit_kept) atomicOr(&remw[gi], bit);
-        else if (all_removed) atomicOr(&keptw[gi], bit);
-        else unknown = true;
-      }
-      __syncwarp();
-      if (!__any_sync(SSDG_FULL, unknown)) break;
-    }
-    const int c = lane < W ? __popc(keptw[lane]) : 0;
-    int incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(SSDG_FULL, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane < W) hist[lane] = (u32)(incl - c);   // W <= 32 (shared memory limits sortn to 1024)
-    if (lane == 31) hist[W] = (u32)incl;
-  }
-  __syncthreads();
-  int* ok = P.out_kept + list * (size_t)P.top_k;
-  float* os = P.out_score ? P.out_score + list * (size_t)P.top_k : nullptr;
-  const int total = (int)hist[W];
-  for (int i = total + tid; i < P.top_k; i += kNmsThreads) {
-    ok[i] = -1;
-    if (os) os[i] = 0.f;
-  }
-  NMS_LOOP
-  for (int i = tid; i < m; i += kNmsThreads) {
-    const u32 kw = keptw[i >> 5], bit = 1u << (i & 31);
-    if (kw & bit) {
-      const int rank = (int)hist[i >> 5] + __popc(kw & (bit - 1u));
-      ok[rank] = (int)(~(u32)keys[i]);
-      if (os) os[rank] = unkey32((u32)(keys[i] >> 32));
-    }
-  }
-  if (tid == 0) P.out_count[list] = total;
-}
-
-// ---- per-(image, class) NMS, second generation ------------------------------------------------------------
-// Same algorithm and the same exactness arguments as nms_kernel above (select, bucketed rank sort, slab interval
-// join with size classes, cheap float test with a margin, the IEEE formula for the survivors, fixed-point
-// resolution) with the instruction count cut where the profile showed it (profiles/r20_*: 8.7 k warp-instructions
-// per list, 78 % issue utilisation -- the kernel is issue-bound):
-//   * the join only ANDs the six table words per (row, column word) and PUSHES the surviving candidate pairs into a
-//     per-warp queue (ballot + popc, no atomics); the pair tests then run densely, one pair per thread, instead of
-//     every lane looping over its own candidates (the loop ran to the longest lane: 47 trips of 22 instructions for
-//     198 pairs per list).  A full queue tests the pair in place -- no input can overflow anything.
-//   * only the rare real suppressions touch the matrix (atomicOr into a zeroed triangle) and an `open rows` bitset;
-//     rows that stay closed are kept at once, the open ones are listed by the resolving warp.
-//   * row groups are dealt to the warps in pairs (last + first, ...): the triangular join costs g+1 words for group
-//     g, so every warp gets the same number of word steps.
-//   * thresholds, shrink factor and class scale come from the host; the slab scale is an approximate reciprocal
-//     (any positive scale keeps the slab map monotone, which is all the join needs).
+// Structure (128 threads per list, ~17.8 KB shared memory, <= 40 registers => 12 CTAs per SM; the kernel is
+// issue- and barrier-bound, profiles/r20_*, r25_*):
+//   * the list is the concatenation of the runs the filter CTAs left in its slots; the counts of up to four runs
+//     are fetched together (one memory latency in front of the keys);
+//   * exact top-k: a list longer than the sort width goes through an 8-bit radix select of the composite key; then a
+//     BUCKETED RANK SORT -- 256 buckets monotone in the key, scaled to the list's own [min, max] score word (prior
+//     word when every score is equal); rank = keys in higher buckets + larger keys in the own bucket.  Exact for
+//     any input (clustered scores only lengthen a count loop);
+//   * suppression bits by an INTERVAL JOIN instead of all pairs.  iou(i, j) > t means inter > q (a_i + a_j),
+//     q = t / (1 + t); the y overlap is at most min(h_i, h_j), so the x overlap exceeds q (w_i + w_j): the x
+//     extents of i and j, each SHRUNK by q times its width at both ends, still meet (same in y).  Every box gets
+//     the interval [a, b] of the 32 slabs per axis its shrunk extents touch; two intervals meet <=> a_j <= b_i and
+//     b_j >= a_i.  Per axis two cumulative bitset tables over the boxes, LE[s] = {j : a_j <= s}, GE[s] = {j : b_j >= s}
+//     (each box registered at its two end slabs, then a running OR along the slabs), give the x partners of box i as
+//     LE[b_i] & GE[a_i]: two loads per axis whatever the width.  SIZE CLASSES prune further: iou > t needs
+//     inter > t' E_i and inter <= w_j h_i, so the widths -- and the heights -- of a pair differ by less than 1/t';
+//     with classes of that ratio a pair's classes differ by at most one, and two more tables (class
+//     neighbourhoods) join the AND.  Survivors get the branch-free float test inter >= 0.9999 q (a_i + a_j), then
+//     the formula itself in IEEE float32 (utils/bbox.py:13-25).  The bounds are stated in the formula's areas w*h;
+//     they carry over to the corner extents unless some box's extents do not reproduce its area to 0.1 % -- then
+//     nothing is shrunk and all boxes share one class.  Thresholds <= 0 or huge use all pairs with the formula;
+//   * the join runs per group of 32 rows in two passes (candidate words as straight-line code when the word count
+//     is a template constant, then the pair tests), the groups dealt to the warps in pairs (last + first, ...):
+//     group g costs g + 1 words, so every warp gets the same number of word steps;
+//   * rows without a suppressor are kept at once; the others (a handful) are listed and resolved by ONE warp
+//     iterating the fixed point of kept(i) <=> no kept j < i suppresses i -- identical to the sequential greedy by
+//     induction on i, no CTA-wide barrier per round.  The suppression matrix is the lower triangle only,
+//     [group][word][row] (conflict-free);
+//   * thresholds, shrink factor and class scale come from the host; slab and bucket scales are approximate
+//     reciprocals (any positive scale keeps those maps monotone, which is all the join and the sort need).
 template <int kW>   // kW: words of 32 rows (top_k rounded up / 32) as a constant, 0 = any
-__global__ void __launch_bounds__(kNmsThreads, 12) nms2_kernel(NmsParams P) {
+__global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sortn = P.sortn, mcap = (P.top_k + 31) & ~31, W = mcap >> 5, RL = (4 * W) | 1;
@@ -1069,21 +537,57 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms2_kernel(NmsParams P) {
   const int b = (int)(blockIdx.z * 65535u + blockIdx.y);        // grid (class, image mod 65535, image / 65535)
   if (b >= P.B) return;
   const size_t list = (size_t)b * P.n_fg + blockIdx.x;
-  int n = (int)P.cls_cnt[list];
-  const bool selected = n > P.sortn;   // more candidates than the sort takes: radix select first
-  const u64* cl = P.cls_off ? P.sorted + (size_t)b * P.img_stride + P.cls_off[list]
-                            : P.sorted + list * P.img_stride;   // direct mode: one list per (image, class)
-
-  u32 hmin = ~0u, hmax = 0u, lmin = ~0u, lmax = 0u;   // range of the score and prior words of the keys
-  if (n <= sortn) {
+  // The list is the concatenation of the runs the filter CTAs left in its slots (prior space, DetectParams).
+  // f(key, index in the list) for every key, block-strided; returns the length.  Everything is derived inside (the
+  // counts of the first four runs fetched together: one memory latency in front of the keys, not one per run), so
+  // nothing stays in registers for the rare second use (radix select of an over-long list).
+  auto for_keys = [&](auto&& f) -> int {
+    const u32 t_lo = (u32)b * (u32)P.tpi;                 // first tile of the image in the batch (tiles < 2^31)
+    const u32 s_first = t_lo / (u32)P.chunk;
+    const int nruns = (int)((t_lo + (u32)P.tpi - 1u) / (u32)P.chunk - s_first) + 1;
+    const u32* rc = P.run_cnt + (size_t)b * P.max_slots * P.n_fg + blockIdx.x;
+    const u64* lbase = P.lists + list * P.list_cap;
+    const int c0 = (int)rc[0], c1 = nruns > 1 ? (int)rc[P.n_fg] : 0, c2 = nruns > 2 ? (int)rc[2 * (size_t)P.n_fg] : 0,
+              c3 = nruns > 3 ? (int)rc[3 * (size_t)P.n_fg] : 0;
+    const int n4 = c0 + c1 + c2 + c3;
+    const size_t chunk32 = (size_t)P.chunk * 32;
+    const size_t off1 = (size_t)((s_first + 1u) * (u32)P.chunk - t_lo) * 32;   // slots of the second run (if any)
     NMS_LOOP
-    for (int i = tid; i < n; i += kNmsThreads) {
-      const u64 v = cl[i];
-      keys[i] = v;
-      hmin = min(hmin, (u32)(v >> 32)); hmax = max(hmax, (u32)(v >> 32));
-      lmin = min(lmin, (u32)v); lmax = max(lmax, (u32)v);
+    for (int i = tid; i < n4; i += kNmsThreads) {
+      int j = i;
+      size_t o = 0;
+      if (j >= c0) {
+        j -= c0; o = off1;
+        if (j >= c1) {
+          j -= c1; o += chunk32;
+          if (j >= c2) { j -= c2; o += chunk32; }
+        }
+      }
+      f(lbase[o + j], i);
     }
-  } else {
+    int base = n4;
+    for (int r = 4; r < nruns; ++r) {   // an image in more than four runs: tiny chunks only
+      const int cnt = (int)rc[(size_t)r * P.n_fg];
+      const u64* ptr = lbase + off1 + (size_t)(r - 1) * chunk32;
+      NMS_LOOP
+      for (int i = tid; i < cnt; i += kNmsThreads) f(ptr[i], base + i);
+      base += cnt;
+    }
+    return base;
+  };
+
+  // Lists up to the sort width (all but pathological ones) go straight into the sort buffer; a longer one keeps its
+  // first sortn keys there only until the select below refills the buffer.
+  u32 hmin = ~0u, hmax = 0u, lmin = ~0u, lmax = 0u;   // range of the score and prior words of the keys
+  int n = for_keys([&](u64 v, int i) {
+    if (i < sortn) keys[i] = v;
+    hmin = min(hmin, (u32)(v >> 32)); hmax = max(hmax, (u32)(v >> 32));
+    lmin = min(lmin, (u32)v); lmax = max(lmax, (u32)v);
+  });
+  const bool selected = n > P.sortn;   // more candidates than the sort takes: radix select first
+  if (selected) {
+    hmin = ~0u; hmax = 0u; lmin = ~0u; lmax = 0u;   // taken again from the selected keys
+    __syncthreads();
     // Radix select of the top_k-th largest composite key (keys are unique), 8 bits per pass.
     if (tid == 0) { sel_prefix = 0ull; sel_k = P.top_k; sel_fill = 0; }
     __syncthreads();
@@ -1093,11 +597,9 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms2_kernel(NmsParams P) {
       __syncthreads();
       const u64 pre = sel_prefix;
       const u64 hmask = shift == 56 ? 0ull : (~0ull << (shift + 8));
-      NMS_LOOP
-      for (int i = tid; i < n; i += kNmsThreads) {
-        const u64 v = cl[i];
+      for_keys([&](u64 v, int) {
         if ((v & hmask) == pre) atomicAdd(&hist[(u32)(v >> shift) & 255u], 1u);
-      }
+      });
       __syncthreads();
       if (tid == 0) {
         int k = sel_k, acc = 0, d = 255;
@@ -1111,18 +613,16 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms2_kernel(NmsParams P) {
       __syncthreads();
     }
     const u64 kth = sel_prefix;
-    NMS_LOOP
-    for (int i = tid; i < n; i += kNmsThreads) {
-      const u64 v = cl[i];
+    for_keys([&](u64 v, int) {
       if (v >= kth) {
         const int p = atomicAdd(&sel_fill, 1);
         if (p < sortn) keys[p] = v;
       }
-    }
+    });
     __syncthreads();
     n = min(sel_fill, sortn);
   }
-  // Rank sort, descending (keys are unique): see nms_kernel.
+  // Rank sort, descending (keys are unique), see the head of the kernel.
   {
     u64* tmp = reinterpret_cast<u64*>(crn);   // [n] keys grouped by bucket; crn is filled after the sort
     NMS_LOOP
@@ -1194,7 +694,11 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms2_kernel(NmsParams P) {
   const int mpad = (m + 31) & ~31;
   const int ngroups = mpad >> 5;
 
-  // Decoded boxes; corners in the formula's own float32 operations (utils/bbox.py:13-21); see nms_kernel.
+  // Decoded boxes; corners in the formula's own float32 operations (utils/bbox.py:13-21).
+  // qa = q*(area + 0.5e-10):  iou > thr  <=>  inter > qa_i + qa_j  in exact arithmetic (positive denominator); boxes
+  // that can never overlap anything (w <= 0, h <= 0, non-finite, padding) get qa = +inf so the fast test rejects
+  // them exactly like the formula does (their intersection is 0).  The same pass collects what the join needs: the
+  // extents of all sane boxes (slab domain) and whether every box's corner extents reproduce its area to 0.1 %.
   const float thr = P.iou_thresh;
   const bool fast_ok = P.fast_ok != 0;
   const float q = P.q;
@@ -1236,7 +740,7 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms2_kernel(NmsParams P) {
   inexact = __syncthreads_or(inexact);
 
   if (fast_ok) {
-    // Slab join + size classes: the derivation is in nms_kernel.
+    // Slab join + size classes (derivation at the head of the kernel).
     float dx0, dy0, dsx, dsy, lwx, lwy;
     {
       float4 e = reinterpret_cast<const float4*>(dom)[0];
@@ -1485,10 +989,36 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms2_kernel(NmsParams P) {
   if (tid == 0) P.out_count[list] = total;
 }
 
-static int f_warps_for(int C) {
-  const size_t budget = 220 * 1024;
-  int w = (int)((budget - (size_t)kFWarps * 32 * 8) / ((size_t)32 * C * 4 + 8));
-  return w > kFWarps ? kFWarps : w;
+// Launch geometry of the filter pass, a pure function of the shape (both stages and the workspace size derive it).
+struct FilterGeom {
+  int warps;       // tiles in flight per CTA
+  int grid, chunk; // CTAs and tiles per CTA (one contiguous run each)
+  int max_li;      // images a run can touch
+  int max_slots;   // runs an image can be split into
+  size_t cnt_bytes, smem;
+};
+static bool filter_geom(long long batch, int A, int C, FilterGeom* g) {
+  const long long tpi = ((long long)A + 31) / 32, tiles = batch * tpi, nfg = C - 1;
+  if (tiles <= 0 || tiles > 0x7fffffffll) return false;
+  // shared memory: class counters of the run (a few images' worth), then as many 32-prior tiles as fit
+  const size_t cnt_budget = std::max<size_t>(8192, (size_t)3 * nfg * 4);
+  long long grid0 = sm_count();
+  if (tiles < grid0) grid0 = tiles;
+  long long chunk = (tiles + grid0 - 1) / grid0;
+  if ((size_t)(chunk / tpi + 2) * nfg * 4 > cnt_budget) chunk = std::max<long long>(1, (long long)(cnt_budget / (4 * nfg)) - 2) * tpi;
+  g->chunk = (int)chunk;
+  g->grid = (int)((tiles + chunk - 1) / chunk);
+  g->max_li = (int)(chunk / tpi + 2);
+  g->max_slots = (int)(tpi / chunk + 2);
+  g->cnt_bytes = align_up((size_t)g->max_li * nfg * 4, 16);
+  const size_t budget = 220 * 1024, fixed = (size_t)kFWarps * 8 + (size_t)kFWarps * 32 * 8 + g->cnt_bytes + 128;
+  if (budget <= fixed) return false;
+  long long w = (long long)((budget - fixed) / ((size_t)32 * C * 4));
+  if (w > kFWarps) w = kFWarps;
+  if (w > chunk) w = chunk;
+  g->warps = (int)w;
+  g->smem = (size_t)g->warps * 32 * C * 4 + fixed;
+  return w >= 1;
 }
 static int next_pow2(int v) {
   int p = 32;
@@ -1503,24 +1033,20 @@ static size_t nms_smem_bytes(int sortn, int top_k) {
 }
 
 struct DetectWs {
-  u32 *tile_cnt, *cls_cnt, *cls_off;
-  u64 *seg, *sorted;
+  u32* run_cnt;
+  u64* lists;
   float* boxes;
 };
 static size_t detect_ws_layout(long long batch, int A, int C, DetectWs* out, unsigned char* base) {
+  FilterGeom g;
+  if (!filter_geom(batch, A, C, &g)) return 0;
   size_t o = 0;
   const size_t tpi = ((size_t)A + 31) / 32;
   const size_t nfg = (size_t)C - 1;
-  if (out) out->tile_cnt = (u32*)(base + o);
-  o += align_up((size_t)batch * tpi * 4, 256);
-  if (out) out->cls_cnt = (u32*)(base + o);
-  o += align_up((size_t)batch * nfg * 4, 256);
-  if (out) out->cls_off = (u32*)(base + o);
-  o += align_up((size_t)batch * nfg * 4, 256);
-  if (out) out->seg = (u64*)(base + o);
-  o += align_up((size_t)batch * tpi * 32 * nfg * 8, 256);
-  if (out) out->sorted = (u64*)(base + o);
-  o += align_up((size_t)batch * tpi * 32 * nfg * 8, 256);
+  if (out) out->run_cnt = (u32*)(base + o);
+  o += align_up((size_t)batch * g.max_slots * nfg * 4, 256);
+  if (out) out->lists = (u64*)(base + o);
+  o += align_up((size_t)batch * nfg * tpi * 32 * 8, 256);
   if (out) out->boxes = (float*)(base + o);
   o += align_up((size_t)batch * A * 16, 256);
   return o;
@@ -1528,23 +1054,17 @@ static size_t detect_ws_layout(long long batch, int A, int C, DetectWs* out, uns
 
 template <bool kProbs>
 static int run_filter(DetectParams& P, int prior_dtype, cudaStream_t st) {
-  const int warps = f_warps_for(P.C);
-  if (warps < 1) return SSDG_ERR_LIMIT;
-  const size_t smem = (size_t)warps * 32 * P.C * 4 + kFWarps * 8 + (size_t)kFWarps * 32 * 8 + 128;
-  int grid = sm_count();
-  const long long tiles = (long long)P.B * P.tpi;
-  const long long need = (tiles + warps - 1) / warps;
-  if (need < grid) grid = (int)need;
+  FilterGeom g;
+  if (!filter_geom(P.B, P.A, P.C, &g)) return SSDG_ERR_LIMIT;
+  P.chunk = g.chunk; P.max_li = g.max_li; P.max_slots = g.max_slots;
   P.tma_ok = (((long long)P.A * P.C) % 4 == 0) && (((uintptr_t)P.pred_cls & 15) == 0);
-  if (P.lists) SSDG_CUDA_TRY(cudaMemsetAsync(P.cls_cnt, 0, (size_t)P.B * (P.C - 1) * 4, st));   // the class lists start empty
   prof_begin(SSDG_PROF_FILTER, st);
   // kWrite: the rows must hold exp(x - max) after the pass (probabilities output, score head)
   const bool wr = !kProbs && (P.probs || P.head_score || P.head_cls || P.head_mask);
   auto go = [&](auto kern) -> int {
-    SSDG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSDG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     static const char* env_pf = getenv("SSDG_FILTER_PREFETCH");   // tiles of L2 prefetch distance per warp; experiment knob
-    static const char* env_ch = getenv("SSDG_FILTER_CHUNKED");    // tile walk; experiment knob
-    kern<<<grid, kFThreads, smem, st>>>(P, warps, env_pf ? atoi(env_pf) : 1, env_ch ? atoi(env_ch) : 0);
+    kern<<<g.grid, kFThreads, g.smem, st>>>(P, g.warps, env_pf ? atoi(env_pf) : 1);
     return SSDG_OK;
   };
   int rc;
@@ -1553,32 +1073,16 @@ static int run_filter(DetectParams& P, int prior_dtype, cudaStream_t st) {
   if (rc != SSDG_OK) return rc;
   prof_end(SSDG_PROF_FILTER, st);
   SSDG_LAUNCH_CHECK();
-  if (P.lists) return SSDG_OK;   // direct mode: the filter has appended to the class lists itself
-  SSDG_CUDA_TRY(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  {
-    const size_t bsm = ((size_t)2 * P.C + P.tpi + 1) * 4;
-    if ((int)bsm > max_smem_optin()) return SSDG_ERR_LIMIT;
-    if (bsm > 48 * 1024)
-      SSDG_CUDA_TRY(cudaFuncSetAttribute(bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
-    prof_begin(SSDG_PROF_BUCKET, st);
-    bucket_kernel<<<P.B, kBucketThreads, bsm, st>>>(P);
-    prof_end(SSDG_PROF_BUCKET, st);
-  }
-  SSDG_LAUNCH_CHECK();
   return SSDG_OK;
-}
-
-static bool detect_direct() {   // experiment switch: SSDG_DETECT_BUCKET=1 restores the per-tile segments + bucketing pass
-  static const char* e = getenv("SSDG_DETECT_BUCKET");
-  return !(e && atoi(e));
 }
 
 static int run_nms(const DetectWs& ws, const float* boxes, long long batch, int A, int C, int top_k, float iou_thresh,
                    int* out_kept, int* out_count, float* out_score, cudaStream_t st) {
+  FilterGeom g;
+  if (!filter_geom(batch, A, C, &g)) return SSDG_ERR_LIMIT;
   NmsParams Q;
-  Q.cls_cnt = ws.cls_cnt; Q.cls_off = ws.cls_off; Q.sorted = ws.sorted;
-  Q.img_stride = (size_t)((A + 31) / 32) * 32 * (size_t)(C - 1);
-  if (detect_direct()) { Q.cls_off = nullptr; Q.sorted = ws.seg; Q.img_stride = (size_t)((A + 31) / 32) * 32; }
+  Q.lists = ws.lists; Q.run_cnt = ws.run_cnt;
+  Q.tpi = (A + 31) / 32; Q.list_cap = (size_t)Q.tpi * 32; Q.chunk = g.chunk; Q.max_slots = g.max_slots;
   Q.boxes = boxes; Q.A = A; Q.n_fg = C - 1; Q.top_k = top_k;
   Q.sortn = next_pow2(top_k); Q.iou_thresh = iou_thresh;
   Q.out_kept = out_kept; Q.out_count = out_count; Q.out_score = out_score;
@@ -1592,31 +1096,26 @@ static int run_nms(const DetectWs& ws, const float* boxes, long long batch, int 
   }
   const size_t smem = nms_smem_bytes(Q.sortn, top_k);
   if ((int)smem > max_smem_optin()) return SSDG_ERR_LIMIT;
-  const long long lists = batch * (C - 1);
-  if (lists > 0x7fffffffll) return SSDG_ERR_LIMIT;
-  static const char* env_v1 = getenv("SSDG_NMS_V1");   // the first-generation kernel, for A/B measurements
-  auto go = [&](auto kern, dim3 grid) -> int {
+  auto go = [&](auto kern) -> int {
     if (smem > 48 * 1024)
       SSDG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SSDG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // grid (class, image mod 65535, image / 65535): the lists of an image sit next to each other in the launch order
+    const dim3 grid((unsigned)(C - 1), (unsigned)(batch < 65535 ? batch : 65535), (unsigned)((batch + 65534) / 65535));
     prof_begin(SSDG_PROF_NMS, st);
     kern<<<grid, kNmsThreads, smem, st>>>(Q);
     prof_end(SSDG_PROF_NMS, st);
     return SSDG_OK;
   };
   int rc;
-  const dim3 grid2((unsigned)(C - 1), (unsigned)(batch < 65535 ? batch : 65535), (unsigned)((batch + 65534) / 65535));
-  if (env_v1 && atoi(env_v1)) rc = go(nms_kernel, dim3((unsigned)lists));
-  else {
-    switch ((top_k + 31) / 32) {   // the common list lengths get the join's word loop as straight-line code
-      case 1: rc = go(nms2_kernel<1>, grid2); break;
-      case 2: rc = go(nms2_kernel<2>, grid2); break;
-      case 3: rc = go(nms2_kernel<3>, grid2); break;
-      case 4: rc = go(nms2_kernel<4>, grid2); break;
-      case 7: rc = go(nms2_kernel<7>, grid2); break;
-      case 8: rc = go(nms2_kernel<8>, grid2); break;
-      default: rc = go(nms2_kernel<0>, grid2); break;
-    }
+  switch ((top_k + 31) / 32) {   // the common list lengths get the join's word loop as straight-line code
+    case 1: rc = go(nms_kernel<1>); break;
+    case 2: rc = go(nms_kernel<2>); break;
+    case 3: rc = go(nms_kernel<3>); break;
+    case 4: rc = go(nms_kernel<4>); break;
+    case 7: rc = go(nms_kernel<7>); break;
+    case 8: rc = go(nms_kernel<8>); break;
+    default: rc = go(nms_kernel<0>); break;
   }
   if (rc != SSDG_OK) return rc;
   SSDG_LAUNCH_CHECK();
@@ -1625,8 +1124,7 @@ static int run_nms(const DetectWs& ws, const float* boxes, long long batch, int 
 
 static void fill_params(DetectParams& P, const DetectWs& ws, long long batch, int A, int C) {
   P.B = (int)batch; P.A = A; P.C = C; P.tpi = (A + 31) / 32;
-  P.tile_cnt = ws.tile_cnt; P.seg = ws.seg; P.cls_cnt = ws.cls_cnt; P.cls_off = ws.cls_off; P.sorted = ws.sorted;
-  P.lists = detect_direct() ? ws.seg : nullptr;
+  P.lists = ws.lists; P.run_cnt = ws.run_cnt;
   P.list_cap = (size_t)P.tpi * 32;
 }
 

@@ -402,7 +402,7 @@ def loss_result_to_host(result: D.DeviceArray, stream=None) -> dict:
 def detect(pred_cls, pred_box, priors, score_thresh=0.01, top_k=200, iou_thresh=0.45, want_scores=False,
            want_boxes=False, want_probs=False, head_thresh=None, out=None, stream=None, stage=None,
            want_row_stats=False, ws_key="detect", pool=None) -> dict:
-    """stage: None = the whole post-processing; 0 = filter + decode + bucketing only; 1 = the NMS of a previous
+    """stage: None = the whole post-processing; 0 = filter + decode + candidate lists only; 1 = the NMS of a previous
     stage-0 call with the same arguments (include/ssdgeom.h, ssdg_detect_stage).  ws_key names the pooled
     workspace: calls that overlap on different streams need different keys."""
     pred_cls = D.as_device(pred_cls, np.float32)

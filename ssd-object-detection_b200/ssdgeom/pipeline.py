@@ -42,7 +42,7 @@ class HotPath:
                     "mask": D.empty((b, a), np.uint8)}
         self.loss = {"result": D.empty((N.LOSS_RESULT_LEN,), np.float64)}
         self.det = {"kept": D.empty((b, c - 1, self.top_k), np.int32), "count": D.empty((b, c - 1), np.int32)}
-        # filter + bucketing, the matcher and the loss at high priority, the NMS (20 480 small CTAs that would otherwise
+        # the filter pass, the matcher and the loss at high priority, the NMS (20 480 small CTAs that would otherwise
         # occupy every SM ahead of everything else) at low.  With the matcher at low priority a step of 128 images per
         # GPU -- where the assignment chain is the longer one -- took 0.370 instead of 0.347 ms; at 256 images there is
         # no difference (profiles/r15_stream_priorities.txt).
@@ -60,6 +60,16 @@ class HotPath:
         # the filter pass of the next one (kernels bound by different resources) instead of waiting for the whole
         # batch.  SSDGEOM_DETECT_PARTS overrides for measurements.
         self.detect_parts = max(1, min(int(os.environ.get("SSDGEOM_DETECT_PARTS", "1")), self.batch))
+        # Who takes the SMs first.  Both branches become ready at the same moment (ev_begin); the filter's 148 CTAs of
+        # 171 KB shared memory and the search's 1184 small CTAs then compete for every SM.  Below ~240 images per GPU the
+        # assignment chain (search -> per-image matching -> loss, all latency-bound) is the longer one, and the step is
+        # shorter when the search gets its CTAs placed first and the filter's fill in as they drain: a small zeroing
+        # node in front of the filter pass (a few microseconds) decides that race (128 images: 0.34 -> 0.31 ms per
+        # step; 256 images: 0.530 -> 0.539, so not there).  Ordering the filter behind the search with an event costs
+        # the kernel boundary and is slower than either (0.35 ms).  SSDGEOM_LEAD_ASSIGN=0/1 overrides.
+        la = os.environ.get("SSDGEOM_LEAD_ASSIGN")
+        self.lead_assign = (la == "1") if la in ("0", "1") else self.batch < 240
+        self._lead_pad = D.empty((64 * 1024,), np.uint8)
         self.ev_parts = [D.Event() for _ in range(self.detect_parts)]
         # one pass over the logits serves both branches: the filter leaves per-prior softmax statistics and the
         # loss gathers from them instead of streaming the 724 MB again (only in the chained step)
@@ -84,9 +94,10 @@ class HotPath:
                 raise ValueError("global mining needs comm / allreduce and global_priors")
             self.staged = ops.StagedLoss(self.tgt["cls"], self.tgt["loc"], self.tgt["mask"], self.pred_box, self.pred_cls,
                                          int(global_priors), self.neg_ratio, out=self.loss)
-        # search, match | lossprep (or ce), select x2, final | filter, bucket, nms per slice of the post-processing
-        self.kernel_launches_per_step = 6 + 3 * self.detect_parts
-        self.memsets_per_step = 2                       # matcher head + loss histograms (cudaMemsetAsync)
+        # search, match | lossprep (or ce), select x2, final | filter, nms per slice of the post-processing
+        self.kernel_launches_per_step = 6 + 2 * self.detect_parts
+        # matcher head + loss histograms (cudaMemsetAsync), + the lead node of small batches
+        self.memsets_per_step = 2 + (1 if self.lead_assign else 0)
         self.h2d_bytes = sum(self._sets[0][k].nbytes for k in INPUT_NAMES)
         # results + the matcher's status word
         self.d2h_bytes = self.loss["result"].nbytes + self.det["kept"].nbytes + self.det["count"].nbytes + 4
@@ -166,7 +177,7 @@ class HotPath:
         """One pass of the chain over the resident batch; work is ordered on ``s_main``.
 
         Four streams so that kernels bound by different resources share the SMs:
-          phase A   filter + bucketing (HBM-bound, s_d, high priority)  with  the matcher (latency-bound, s_a, low)
+          phase A   the filter pass (HBM-bound, s_d, high priority)     with  the matcher (latency-bound, s_a, high)
           phase B   NMS (instruction-bound, s_n, low)                   with  the loss (HBM-bound, s_l, high)
         The loss must outrank the NMS or its 148 large-shared-memory CTAs starve behind 20 480 small NMS CTAs."""
         self.ev_begin.record(self.s_main)
@@ -175,6 +186,8 @@ class HotPath:
         fused = self.fused
         if self.split:
             parts = self.detect_parts
+            if self.lead_assign:
+                self._lead_pad.zero_(self.s_d)
             for part in range(parts):
                 self.detect_stage(self.s_d, stage=0, stats=fused, part=part if parts > 1 else None)
                 self.ev_parts[part].record(self.s_d)

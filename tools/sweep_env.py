@@ -17,8 +17,8 @@ for setting in argv:
     try:
         d = json.loads(p.stdout.strip().splitlines()[-1])
         k = d["detail"]["kernels_ms"]
-        print("%-44s %9.0f img/s  step %.4f ms  frac %.3f  filter %.4f bucket %.4f nms %.4f search %.4f match %.4f tail %.4f" % (
+        print("%-44s %9.0f img/s  step %.4f ms  frac %.3f  filter %.4f nms %.4f search %.4f match %.4f tail %.4f" % (
             setting or "(defaults)", d["value"], d["ms_per_step"], d["roofline"]["frac"], k["filter_kernel_with_row_stats"],
-            k["bucket_kernel"], k["nms_kernel"], k["search_kernel"], k["match_kernel"], k["loss_tail"]), flush=True)
+            k["nms_kernel"], k["search_kernel"], k["match_kernel"], k["loss_tail"]), flush=True)
     except Exception as e:   # noqa: BLE001
         print(setting, "FAILED", e, p.stderr[-600:], flush=True)
