@@ -549,29 +549,21 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
     const u64* lbase = P.lists + list * P.list_cap;
     const int c0 = (int)rc[0], c1 = nruns > 1 ? (int)rc[P.n_fg] : 0, c2 = nruns > 2 ? (int)rc[2 * (size_t)P.n_fg] : 0,
               c3 = nruns > 3 ? (int)rc[3 * (size_t)P.n_fg] : 0;
-    const int n4 = c0 + c1 + c2 + c3;
-    const size_t chunk32 = (size_t)P.chunk * 32;
-    const size_t off1 = (size_t)((s_first + 1u) * (u32)P.chunk - t_lo) * 32;   // slots of the second run (if any)
-    NMS_LOOP
-    for (int i = tid; i < n4; i += kNmsThreads) {
-      int j = i;
-      size_t o = 0;
-      if (j >= c0) {
-        j -= c0; o = off1;
-        if (j >= c1) {
-          j -= c1; o += chunk32;
-          if (j >= c2) { j -= c2; o += chunk32; }
-        }
-      }
-      f(lbase[o + j], i);
-    }
-    int base = n4;
-    for (int r = 4; r < nruns; ++r) {   // an image in more than four runs: tiny chunks only
-      const int cnt = (int)rc[(size_t)r * P.n_fg];
-      const u64* ptr = lbase + off1 + (size_t)(r - 1) * chunk32;
+    const u32 chunk32 = (u32)P.chunk * 32u;
+    const u32 off1 = ((s_first + 1u) * (u32)P.chunk - t_lo) * 32u;   // slots of the second run (if any)
+    int base = 0;
+    auto run = [&](const u64* ptr, int cnt) {
       NMS_LOOP
       for (int i = tid; i < cnt; i += kNmsThreads) f(ptr[i], base + i);
       base += cnt;
+    };
+    run(lbase, c0);
+    if (nruns > 1) {
+#pragma unroll 1
+      for (int r = 1; r < nruns; ++r) {
+        const int cnt = r == 1 ? c1 : r == 2 ? c2 : r == 3 ? c3 : (int)rc[(size_t)r * P.n_fg];
+        run(lbase + off1 + (size_t)(r - 1) * chunk32, cnt);
+      }
     }
     return base;
   };
@@ -603,6 +595,7 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
       __syncthreads();
       if (tid == 0) {
         int k = sel_k, acc = 0, d = 255;
+#pragma unroll 1
         for (; d > 0; --d) {
           if (acc + (int)hist[d] >= k) break;
           acc += (int)hist[d];
@@ -685,6 +678,7 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
       const int bk = bucket(v);
       const int s0 = (int)bstart[bk], s1 = (int)hist[bk];
       int r = s0;
+#pragma unroll 1
       for (int t = s0; t < s1; ++t) r += tmp[t] > v;
       keys[r] = v;
     }
@@ -880,8 +874,12 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
     };
     // group g costs g + 1 words: dealt in pairs (last + first, ...) every warp gets the same number of word steps
     for (int k = warp; 2 * k < ngroups; k += kNmsWarps) {
-      join_group(ngroups - 1 - k);
-      if (k != ngroups - 1 - k) join_group(k);
+      const int hi = ngroups - 1 - k;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {   // (one copy of the group code: the kernel is instruction-cache sensitive)
+        if (h == 1 && hi == k) break;
+        join_group(h == 0 ? hi : k);
+      }
     }
   } else {
     // No division-free test for this threshold: all pairs, the formula itself.
@@ -947,6 +945,7 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
         if ((keptw[gi] | remw[gi]) & bit) continue;
         bool hit_kept = false, all_removed = true;
         const int sbase = 16 * gi * (gi + 1) + (i & 31);
+#pragma unroll 1
         for (int w = 0; w <= gi; ++w) {
           const u32 sb = sup[sbase + (w << 5)];
           if (sb & keptw[w]) hit_kept = true;
