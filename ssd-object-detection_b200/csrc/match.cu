@@ -295,7 +295,12 @@ constexpr int kSearchThreads = 128;
 constexpr int kSearchWarps = kSearchThreads / 32;
 
 template <typename TG, typename TP, bool kHier>   // kHier: two-level bound (super-tiles of kSuper tiles, then tiles); up to kTileSmemMax tiles
-__global__ void __launch_bounds__(kSearchThreads, 8) search_kernel(MatchParams P) {
+// 10 CTAs per SM (48 registers): four instead of three of them fit beside a filter CTA of the other branch
+// (chained step 0.513 -> 0.508 ms; alone 0.141 -> 0.139 ms).
+#ifndef SSDG_SEARCH_MINB
+#define SSDG_SEARCH_MINB 10
+#endif
+__global__ void __launch_bounds__(kSearchThreads, SSDG_SEARCH_MINB) search_kernel(MatchParams P) {
   typedef typename Promote<TG, TP>::type R;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -944,7 +949,7 @@ static int launch_match(const MatchParams& P, int grid, size_t smem, cudaStream_
     auto skern = hier ? search_kernel<TG, TP, true> : search_kernel<TG, TP, false>;
     SSDG_CUDA_TRY(cudaFuncSetAttribute(skern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     static const char* env = getenv("SSDG_SEARCH_CTAS_PER_SM");   // experiment knob
-    long long sgrid = (long long)sm_count() * (env ? atoi(env) : 8);
+    long long sgrid = (long long)sm_count() * (env ? atoi(env) : SSDG_SEARCH_MINB);
     const long long want = ((long long)P.B * (P.max_gt > 0 ? P.max_gt : 1) + kSearchWarps - 1) / kSearchWarps;
     if (want < sgrid) sgrid = want;
     prof_begin(SSDG_PROF_SEARCH, st);
