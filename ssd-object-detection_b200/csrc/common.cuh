@@ -194,6 +194,32 @@ __device__ __forceinline__ float exp2_ftz(float x) {
 }
 __device__ __forceinline__ float exp_shifted(float x, float m) { return exp2_ftz((x - m) * SSDG_LOG2E); }
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl is set up while its predecessor in the
+// stream still runs and its CTAs are dispatched as soon as every CTA of the predecessor has exited (or called
+// pdl_trigger()); it must call pdl_wait() before it touches anything the predecessor reads or writes -- pdl_wait()
+// returns when the predecessor grid has completed and its memory is visible.  Takes the launch latency (and any
+// prologue in front of pdl_wait) of the small kernels of a latency-bound chain off the critical path: loss tail
+// 0.038 -> 0.034 ms, chained step 0.508 -> 0.504 ms (B=256), 0.305 -> 0.299 ms (B=128).  An EARLY pdl_trigger() is
+// deliberately not used: the dependents' CTAs would sit on the SMs waiting, and in the chained step those are
+// resources the concurrent NMS needs (measured: 0.508 -> 0.546 ms).  Without the launch attribute both calls are
+// no-ops.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // streaming stores / loads that do not pollute L1
 __device__ __forceinline__ void st_cs(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_cs(float4* p, float4 v) { __stcs(p, v); }

@@ -347,6 +347,7 @@ __global__ void __launch_bounds__(256) select_kernel(LossParams P, int level) {
   __shared__ int sh_bin;
   __shared__ long long sh_above;
   __shared__ double sh_np;
+  pdl_wait();      // the previous level's histogram must be complete
   SelectState st;
   derive_state(P, level, st, sh, threadIdx.x, blockDim.x, &sh_bin, &sh_above, &sh_np);
   if (st.status) return;
@@ -386,6 +387,7 @@ __global__ void __launch_bounds__(256) final_kernel(LossParams P) {
   __shared__ double redd[8];
   __shared__ u32 redc[8], redo[8];
   __shared__ bool is_last;
+  pdl_wait();      // the last level's histogram must be complete
   SelectState st;
   derive_state(P, 3, st, sh, threadIdx.x, blockDim.x, &sh_bin, &sh_above, &sh_np);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -677,13 +679,13 @@ static int loss_run(int stages, int global, long long n_all, const float* row_ml
   if (stages & 6) prof_begin(SSDG_PROF_LOSS_TAIL, st);
   if (stages & 6) {
     SSDG_CUDA_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    if (stages & 2) select_kernel<<<sgrid, 256, 0, st>>>(P, 1);
-    if (stages & 4) select_kernel<<<sgrid, 256, 0, st>>>(P, 2);
+    if (stages & 2) SSDG_CUDA_TRY(launch_pdl(select_kernel, dim3(sgrid), dim3(256), 0, st, P, 1));
+    if (stages & 4) SSDG_CUDA_TRY(launch_pdl(select_kernel, dim3(sgrid), dim3(256), 0, st, P, 2));
     SSDG_LAUNCH_CHECK();
   }
   if (stages & 8) {
     SSDG_CUDA_TRY(cudaFuncSetAttribute(final_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    final_kernel<<<sgrid, 256, 0, st>>>(P);
+    SSDG_CUDA_TRY(launch_pdl(final_kernel, dim3(sgrid), dim3(256), 0, st, P));
     prof_end(SSDG_PROF_LOSS_TAIL, st);
     SSDG_LAUNCH_CHECK();
   }

@@ -540,6 +540,9 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) match_kernel(M
     __syncthreads();
   }
 
+  // everything above is independent of the row search: launched as its programmatic dependent, the CTAs do it while
+  // the search drains, and only now wait for its results
+  pdl_wait();
 #ifdef SSDG_MATCH_TIMING
   long long tk0 = 0;
 #define TICK(slot) do { __syncthreads(); if (tid == 0) { long long n_ = clock64(); atomicAdd((unsigned long long*)&P.ws_head[8 + 2 * (slot)], (unsigned long long)(n_ - tk0)); tk0 = n_; } } while (0)
@@ -957,7 +960,7 @@ static int launch_match(const MatchParams& P, int grid, size_t smem, cudaStream_
     prof_end(SSDG_PROF_SEARCH, st);
     SSDG_LAUNCH_CHECK();
   }
-  match_kernel<TG, TP><<<grid, kMatchThreads, smem, st>>>(P);
+  SSDG_CUDA_TRY(launch_pdl(match_kernel<TG, TP>, dim3(grid), dim3(kMatchThreads), smem, st, P));
   prof_end(SSDG_PROF_MATCH, st);
   SSDG_LAUNCH_CHECK();
   return SSDG_OK;
