@@ -539,31 +539,33 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
   const size_t list = (size_t)b * P.n_fg + blockIdx.x;
   // The list is the concatenation of the runs the filter CTAs left in its slots (prior space, DetectParams).
   // f(key, index in the list) for every key, block-strided; returns the length.  Everything is derived inside (the
-  // counts of the first four runs fetched together: one memory latency in front of the keys, not one per run), so
-  // nothing stays in registers for the rare second use (radix select of an over-long list).
+  // counts of the runs fetched together: one memory latency in front of the keys, not one per run), so nothing
+  // stays in registers for the rare second use (radix select of an over-long list).
   auto for_keys = [&](auto&& f) -> int {
     const u32 t_lo = (u32)b * (u32)P.tpi;                 // first tile of the image in the batch (tiles < 2^31)
     const u32 s_first = t_lo / (u32)P.chunk;
     const int nruns = (int)((t_lo + (u32)P.tpi - 1u) / (u32)P.chunk - s_first) + 1;
     const u32* rc = P.run_cnt + (size_t)b * P.max_slots * P.n_fg + blockIdx.x;
     const u64* lbase = P.lists + list * P.list_cap;
+    // (every thread fetches the counts of the first four runs -- nearly always there are one or two)
     const int c0 = (int)rc[0], c1 = nruns > 1 ? (int)rc[P.n_fg] : 0, c2 = nruns > 2 ? (int)rc[2 * (size_t)P.n_fg] : 0,
               c3 = nruns > 3 ? (int)rc[3 * (size_t)P.n_fg] : 0;
     const u32 chunk32 = (u32)P.chunk * 32u;
     const u32 off1 = ((s_first + 1u) * (u32)P.chunk - t_lo) * 32u;   // slots of the second run (if any)
-    int base = 0;
-    auto run = [&](const u64* ptr, int cnt) {
+    int base = 0, mine = 0;
+#pragma unroll 1
+    for (int r = 0; r < nruns; ++r) {
+      int cnt;
+      if (r < 4) {
+        cnt = r == 0 ? c0 : r == 1 ? c1 : r == 2 ? c2 : c3;
+      } else {   // few images on many SMs: 32 more counts per round trip, one per lane
+        if (((r - 4) & 31) == 0) mine = r + lane < nruns ? (int)rc[(size_t)(r + lane) * P.n_fg] : 0;
+        cnt = __shfl_sync(SSDG_FULL, mine, (r - 4) & 31);
+      }
+      const u64* ptr = lbase + (r ? off1 + (size_t)(r - 1) * chunk32 : 0);
       NMS_LOOP
       for (int i = tid; i < cnt; i += kNmsThreads) f(ptr[i], base + i);
       base += cnt;
-    };
-    run(lbase, c0);
-    if (nruns > 1) {
-#pragma unroll 1
-      for (int r = 1; r < nruns; ++r) {
-        const int cnt = r == 1 ? c1 : r == 2 ? c2 : r == 3 ? c3 : (int)rc[(size_t)r * P.n_fg];
-        run(lbase + off1 + (size_t)(r - 1) * chunk32, cnt);
-      }
     }
     return base;
   };
@@ -1001,9 +1003,10 @@ static bool filter_geom(long long batch, int A, int C, FilterGeom* g) {
   if (tiles <= 0 || tiles > 0x7fffffffll) return false;
   // shared memory: class counters of the run (a few images' worth), then as many 32-prior tiles as fit
   const size_t cnt_budget = std::max<size_t>(8192, (size_t)3 * nfg * 4);
-  long long grid0 = sm_count();
-  if (tiles < grid0) grid0 = tiles;
-  long long chunk = (tiles + grid0 - 1) / grid0;
+  // one run per SM; a small batch gets fewer CTAs rather than runs shorter than the tiles a CTA has in flight anyway
+  // (16: the NMS then reads an SSD300 image in at most 18 runs instead of 273)
+  long long chunk = (tiles + sm_count() - 1) / sm_count();
+  if (chunk < 16) chunk = tiles < 16 ? tiles : 16;
   if ((size_t)(chunk / tpi + 2) * nfg * 4 > cnt_budget) chunk = std::max<long long>(1, (long long)(cnt_budget / (4 * nfg)) - 2) * tpi;
   g->chunk = (int)chunk;
   g->grid = (int)((tiles + chunk - 1) / chunk);

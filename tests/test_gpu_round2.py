@@ -318,3 +318,21 @@ def test_train_batches_prefetch_matches_synchronous_iteration(priors300):
             assert np.array_equal(x, y)
     w = O.assign_encode(cls[off[0]:off[1]], boxes[off[0]:off[1]], priors300, 0.5, sweeps=False)
     assert np.array_equal(pre_batches[0][1][0][0], w[0]) and np.array_equal(pre_batches[0][1][2][0], w[2])
+
+
+# ---- candidate lists in prior space: the run layout must not show in the results -----------------------------
+@pytest.mark.parametrize("bias", [7.0, 0.0])
+def test_detect_is_independent_of_the_batch_it_runs_in(bias, priors300):
+    """The filter CTAs own contiguous runs of tiles and leave per-run counts; how an image is cut into runs depends
+    on the batch (1 image: 137 runs of 2 tiles; 5 images: runs that straddle images; bias 0 makes lists longer than
+    the sort width, i.e. the radix select reads its list through the runs several times).  Same images, same kept
+    lists and scores, bit for bit."""
+    pred_cls, pred_box = synth.make_predictions(977, 5, 8732, bg_bias=bias)
+    for aux in (False, True):   # the streaming variant of the filter pass, and the one that also writes the side outputs
+        full = M.detect(pred_cls, pred_box, priors300, return_aux=aux)
+        for lo, hi in ((0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (1, 4)):
+            part = M.detect(pred_cls[lo:hi], pred_box[lo:hi], priors300, return_aux=aux)
+            assert np.array_equal(part[1], full[1][lo:hi]) and np.array_equal(part[0], full[0][lo:hi])
+            if aux:
+                assert np.array_equal(part[2]["boxes"], full[2]["boxes"][lo:hi])
+                assert np.array_equal(part[2]["kept_score"], full[2]["kept_score"][lo:hi])
