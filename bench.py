@@ -536,6 +536,10 @@ def detail_config(R, args, comm, table_name, global_batch, max_gt, steps=10, war
         out["one_gpu_ms_per_step_same_run"] = solo_ms
         out["one_gpu_value_same_run"] = global_batch / (solo_ms * 1e-3)
         out["efficiency"] = solo_ms / (R.world * ms)
+        out["limiter"] = ("per-GPU latency, not the exchange: at %d images per GPU the step is two chains of latency-bound "
+                          "kernels (filter -> NMS; row search -> per-image matching, one CTA per image -> loss) whose "
+                          "per-image / per-row latencies do not shrink with the batch; the 56-byte all-reduce runs on a "
+                          "stream nobody waits for inside the step (DESIGN.md section 5)" % (global_batch // R.world))
         out["scaling"] = "strong"
     elif with_solo:
         out["efficiency"] = 1.0
