@@ -4,6 +4,8 @@ batch.  The two branches only share the predictions, so they run on separate str
 matcher is latency-bound and the loss/filter passes are HBM-bound, so they overlap."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import _native as N
@@ -17,8 +19,16 @@ INPUT_NAMES = ("gt_boxes", "gt_cls", "gt_off", "pred_cls", "pred_box")
 class HotPath:
     def __init__(self, table=None, batch=256, max_gt=100, classes=81, thresh=0.5, neg_ratio=3,
                  score_thresh=0.01, top_k=200, iou_thresh=0.45, total_gt=None, mining="shard", global_priors=None,
-                 allreduce=None, comm=None):
-        """mining: "shard" -- the hard-negative threshold is mined over this process's batch (what the reference
+                 allreduce=None, comm=None, depth=1):
+        """depth: steps in flight.  1 -- ``step()`` joins both branches on ``s_main`` before it returns the stream to
+        the caller (a step is a closed unit).  2 -- every per-step buffer (targets, row statistics, candidate lists,
+        workspaces, results) exists twice and consecutive steps use them in turn: step k+1 starts as soon as its
+        inputs are there and the buffers of step k-1 are free, so its filter pass and row search run under the NMS
+        and the loss tail of step k (independent batches: an evaluator, or a trainer's target / loss path);
+        ``join()`` / ``download()`` wait for what they need.  Not with mining='global' or a caller-supplied
+        ``loss_exchange``.
+
+        mining: "shard" -- the hard-negative threshold is mined over this process's batch (what the reference
         does per slice under split_batch, models/ssd_model.py:235-256); "global" -- over the batches of all
         data-parallel processes (ops.StagedLoss; ``global_priors`` is the total number of priors over all of them).
 
@@ -29,7 +39,6 @@ class HotPath:
         self.batch, self.max_gt, self.classes = int(batch), int(max_gt), int(classes)
         self.thresh, self.neg_ratio = float(thresh), int(neg_ratio)
         self.score_thresh, self.top_k, self.iou_thresh = float(score_thresh), int(top_k), float(iou_thresh)
-        self.pool = ops.WorkspacePool()                  # this pipeline's own scratch (never shared)
         self.priors = ops.prior_boxes(table["sizes"], table["s_k_refer"], table["aspect_ratio"], table["input_size"])
         self.A = a = int(self.priors.shape[0])
         ops.prior_index(self.priors)                     # one-off, like the priors themselves
@@ -38,10 +47,19 @@ class HotPath:
         self.total_gt = n_gt
         self._sets = [self._alloc_inputs()]
         self._bind(self._sets[0])
-        self.tgt = {"cls": D.empty((b, a), np.int32), "loc": D.empty((b, a, 4), np.float32),
-                    "mask": D.empty((b, a), np.uint8)}
-        self.loss = {"result": D.empty((N.LOSS_RESULT_LEN,), np.float64)}
-        self.det = {"kept": D.empty((b, c - 1, self.top_k), np.int32), "count": D.empty((b, c - 1), np.int32)}
+        self.depth = 1 if mining == "global" else max(1, int(depth))
+        self._n_steps = 0
+
+        def make_slot():   # everything a step writes
+            return {"tgt": {"cls": D.empty((b, a), np.int32), "loc": D.empty((b, a, 4), np.float32),
+                            "mask": D.empty((b, a), np.uint8)},
+                    "loss": {"result": D.empty((N.LOSS_RESULT_LEN,), np.float64)},
+                    "det": {"kept": D.empty((b, c - 1, self.top_k), np.int32), "count": D.empty((b, c - 1), np.int32)},
+                    "det_stats": {"row_ml": D.empty((b, a, 2), np.float32), "row_negbg": D.empty((b, a), np.float32)},
+                    "pool": ops.WorkspacePool(), "ev_a": D.Event(), "ev_d": D.Event(), "ev_x": D.Event(),
+                    "x_pending": False, "used": False, "loss_exchange": None}
+        self._slots = [make_slot() for _ in range(self.depth)]
+        self._bind_slot(0)
         # the filter pass, the matcher and the loss at high priority, the NMS (20 480 small CTAs that would otherwise
         # occupy every SM ahead of everything else) at low.  With the matcher at low priority a step of 128 images per
         # GPU -- where the assignment chain is the longer one -- took 0.370 instead of 0.347 ms; at 256 images there is
@@ -53,8 +71,8 @@ class HotPath:
             return int(v) if v.lstrip("-").isdigit() else v
         self.s_main, self.s_a, self.s_d = D.Stream(), D.Stream(prio("A", "high")), D.Stream(prio("D", "high"))
         self.s_n, self.s_l = D.Stream(prio("N", "low")), D.Stream(prio("L", "high"))
-        self.s_x, self.ev_x, self._x_pending = D.Stream("high"), D.Event(), False   # loss exchange (data parallel)
-        self.ev_begin, self.ev_a, self.ev_d, self.ev_mid, self.ev_m = (D.Event() for _ in range(5))
+        self.s_x = D.Stream("high")                      # loss exchange (data parallel)
+        self.ev_begin, self.ev_mid, self.ev_m = (D.Event() for _ in range(3))
         self.split = True
         # the post-processing chain can run in `detect_parts` slices of the batch: the NMS of a slice then overlaps
         # the filter pass of the next one (kernels bound by different resources) instead of waiting for the whole
@@ -74,7 +92,6 @@ class HotPath:
         # one pass over the logits serves both branches: the filter leaves per-prior softmax statistics and the
         # loss gathers from them instead of streaming the 724 MB again (only in the chained step)
         self.fused = True
-        self.det_stats = {"row_ml": D.empty((b, a, 2), np.float32), "row_negbg": D.empty((b, a), np.float32)}
         if mining not in ("shard", "global"):
             raise ValueError("mining must be 'shard' or 'global'")
         self.mining, self.comm = mining, comm
@@ -83,11 +100,12 @@ class HotPath:
         self.allreduce = allreduce
         # optional callable(stream): the data-parallel exchange of the additive loss sums (per-shard mining),
         # enqueued on a stream of its own right behind the loss so that it hides under the NMS of the other branch
-        self.loss_exchange = None
+        self.loss_exchange = None                        # a caller's own exchange (depth 1 only)
         if comm is not None and mining == "shard" and comm.world > 1:
-            r = self.loss["result"]
-            sums = D.DeviceArray((7,), np.float64, ptr=r.ptr + 4 * 8, owner=r)    # result[4..10], include/ssdgeom.h
-            self.loss_exchange = lambda stream: comm.allreduce(sums, stream)
+            for sl in self._slots:
+                r = sl["loss"]["result"]
+                sums = D.DeviceArray((7,), np.float64, ptr=r.ptr + 4 * 8, owner=r)    # result[4..10], include/ssdgeom.h
+                sl["loss_exchange"] = (lambda stream, sums=sums: comm.allreduce(sums, stream))
         self.staged = None
         if mining == "global":
             if allreduce is None or not global_priors:
@@ -104,6 +122,21 @@ class HotPath:
         self._status_host = D.PinnedArray((2,), np.uint32)
         self._status_host.array[...] = 0
         self._match_out = None
+
+    # ---- per-step buffers -----------------------------------------------------------------------------------
+    def _bind_slot(self, k: int):
+        sl = self._slots[k]
+        self._cur = sl
+        self.tgt, self.loss, self.det, self.det_stats, self.pool = sl["tgt"], sl["loss"], sl["det"], sl["det_stats"], sl["pool"]
+        self.ev_a, self.ev_d, self.ev_x = sl["ev_a"], sl["ev_d"], sl["ev_x"]
+
+    @property
+    def _x_pending(self):
+        return self._cur["x_pending"]
+
+    @_x_pending.setter
+    def _x_pending(self, v):
+        self._cur["x_pending"] = v
 
     # ---- input buffers --------------------------------------------------------------------------------------
     def _alloc_inputs(self):
@@ -180,9 +213,22 @@ class HotPath:
           phase A   the filter pass (HBM-bound, s_d, high priority)     with  the matcher (latency-bound, s_a, high)
           phase B   NMS (instruction-bound, s_n, low)                   with  the loss (HBM-bound, s_l, high)
         The loss must outrank the NMS or its 148 large-shared-memory CTAs starve behind 20 480 small NMS CTAs."""
+        if self.depth > 1:
+            if self.loss_exchange is not None:
+                raise RuntimeError("a caller-supplied loss_exchange needs depth=1")
+            self._bind_slot(self._n_steps % self.depth)
+        self._n_steps += 1
         self.ev_begin.record(self.s_main)
         D.stream_wait_event(self.s_a, self.ev_begin)
         D.stream_wait_event(self.s_d, self.ev_begin)
+        if self.depth > 1 and self._cur["used"]:
+            # the step that used these buffers last must be through with them (its NMS reads the lists and boxes, its
+            # loss the targets and row statistics); everything else of that step is ordered before these two events
+            for st in (self.s_a, self.s_d):
+                D.stream_wait_event(st, self.ev_a)
+                D.stream_wait_event(st, self.ev_d)
+        self._cur["used"] = True
+        loss_exchange = self._cur["loss_exchange"] or self.loss_exchange
         fused = self.fused
         if self.split:
             parts = self.detect_parts
@@ -205,13 +251,13 @@ class HotPath:
                 D.stream_wait_event(self.s_l, self.ev_x)
             self.loss_stage(self.s_l, stats=fused)
             self.ev_a.record(self.s_l)
-            if self.loss_exchange is not None:
+            if loss_exchange is not None:
                 # The data-parallel exchange of the additive loss sums runs on a stream of its own and nobody in
                 # THIS step waits for it (finish_exchange() / download() do): the processes need not meet inside
                 # every step -- a rendezvous there costs the slowest process's skew plus the collective's latency
                 # on the critical path once the loss ends less than that before the NMS (8 GPUs: 0.71 ms per step).
                 D.stream_wait_event(self.s_x, self.ev_a)
-                self.loss_exchange(self.s_x)
+                loss_exchange(self.s_x)
                 self.ev_x.record(self.s_x)
                 self._x_pending = True
             self.ev_d.record(self.s_n)
@@ -219,12 +265,20 @@ class HotPath:
             self.detect_stage(self.s_d)
             self.assign(self.s_a)
             self.loss_stage(self.s_a)
-            if self.loss_exchange is not None:
-                self.loss_exchange(self.s_a)
+            if loss_exchange is not None:
+                loss_exchange(self.s_a)
             self.ev_a.record(self.s_a)
             self.ev_d.record(self.s_d)
-        D.stream_wait_event(self.s_main, self.ev_a)
-        D.stream_wait_event(self.s_main, self.ev_d)
+        if self.depth == 1:
+            self.join()
+
+    def join(self, stream=None):
+        """Make ``stream`` (s_main) wait for every step enqueued so far (both branches)."""
+        st = self.s_main if stream is None else stream
+        for sl in self._slots:
+            if sl["used"]:
+                D.stream_wait_event(st, sl["ev_a"])
+                D.stream_wait_event(st, sl["ev_d"])
 
     # ---- host-facing -------------------------------------------------------------------------------------
     def _check_gt(self, gt_off):
@@ -253,11 +307,14 @@ class HotPath:
 
     def finish_exchange(self, stream=None):
         """Make ``stream`` (s_main) wait for the data-parallel exchange of the last step's loss sums."""
-        if self._x_pending:
-            D.stream_wait_event(self.s_main if stream is None else stream, self.ev_x)
+        for sl in self._slots:
+            if sl["x_pending"]:
+                D.stream_wait_event(self.s_main if stream is None else stream, sl["ev_x"])
 
     def download(self, out_result, out_kept, out_count, stream=None):
         st = self.s_main if stream is None else stream
+        if self.depth > 1:
+            self.join(st)             # the results of the LAST step (the slot bound now)
         self.finish_exchange(st)
         lib = N.lib()
         for src, dst in ((self.loss["result"], out_result), (self.det["kept"], out_kept), (self.det["count"], out_count)):

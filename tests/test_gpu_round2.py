@@ -336,3 +336,52 @@ def test_detect_is_independent_of_the_batch_it_runs_in(bias, priors300):
             if aux:
                 assert np.array_equal(part[2]["boxes"], full[2]["boxes"][lo:hi])
                 assert np.array_equal(part[2]["kept_score"], full[2]["kept_score"][lo:hi])
+
+
+# ---- two steps in flight: alternate buffers, no result may depend on it ------------------------------------------
+def test_hotpath_two_steps_in_flight_equal_closed_steps(priors300):
+    """HotPath(depth=2) lets step k+1 start under the tail of step k on a second set of per-step buffers.  Seven steps
+    over three different resident batches, results fetched only where a consumer would fetch them (after every
+    step, and once after a burst of steps): loss block, kept lists, counts and targets equal the closed steps'."""
+    b, gtmax = 6, 30
+    gts = [synth.make_gt(300 + k, b, gtmax, "max") for k in range(3)]
+    total = max(g[0].shape[0] for g in gts)
+    preds = [synth.make_predictions(50 + 10 * k, b, 8732) for k in range(3)]
+
+    def build(depth):
+        hp = HotPath(synth.SSD300, batch=b, max_gt=gtmax, total_gt=total, depth=depth)
+        for k in range(3):
+            if k:
+                hp.add_input_set()
+            hp.use_set(k)
+            boxes, cls, off = gts[k]
+            pad = total - boxes.shape[0]
+            hp.upload(np.concatenate([boxes, np.zeros((pad, 4), np.float32)]), np.concatenate([cls, np.zeros((pad,), np.float32)]),
+                      off, *preds[k])
+        hp.s_main.sync()
+        return hp
+
+    def fetch(hp):
+        out = (np.zeros(N.LOSS_RESULT_LEN), np.zeros((b, 80, 200), np.int32), np.zeros((b, 80), np.int32))
+        hp.download(*out)
+        hp.s_main.sync()
+        return out + (hp.tgt["cls"].to_host(), hp.tgt["mask"].to_host(), hp.tgt["loc"].to_host())
+
+    order = [0, 1, 2, 1, 0, 2, 2]
+    closed, hp1 = [], build(1)
+    for k in order:
+        hp1.use_set(k)
+        hp1.step()
+        closed.append(fetch(hp1))
+    hp2 = build(2)
+    for n, k in enumerate(order):        # fetched after every step
+        hp2.use_set(k)
+        hp2.step()
+        for x, y in zip(fetch(hp2), closed[n]):
+            assert np.array_equal(x, y)
+    for k in order:                      # a burst: nothing waits in between
+        hp2.use_set(k)
+        hp2.step()
+    for x, y in zip(fetch(hp2), closed[-1]):
+        assert np.array_equal(x, y)
+    hp2.check_status()
