@@ -406,3 +406,46 @@ def test_detect_many_tiny_images_run_geometry():
         w_kept, w_count, _, _ = O.detect(pred_cls[i], pred_box[i], pri, **kw)
         same = sum(int(np.array_equal(kept[i, cc, :count[i, cc]], w_kept[cc, :w_count[cc]])) for cc in range(c - 1))
         assert same >= c - 1 - 2      # near-ties of the float32 scores aside (see the A9 tests)
+
+
+# ---- BASELINE config 4's table on two shards ------------------------------------------------------------------
+def test_ssd512_two_shards_chained_step_against_the_oracle():
+    """SSD512 (24 564 priors), a batch of 4 images cut into 2 shards by image as the data-parallel path cuts it
+    (parallel.shard_csr): every shard runs the chained step (HotPath) on its slice.  Targets per image equal the
+    oracle's bit for bit, each shard's loss is the oracle's _ssd_loss of that slice (per-shard mining: the reference's
+    split_batch semantics, models/ssd_model.py:235-256), the pooled combination of the additive sums equals the one
+    computed from the oracle's per-shard terms, and the detections equal the single-device call on the whole batch."""
+    t512 = synth.TABLES["ssd512"]
+    priors = O.build_prior_box(t512["sizes"], t512["s_k_refer"], t512["aspect_ratio"], t512["input_size"])
+    a = priors.shape[0]
+    assert a == 24564
+    batch, world = 4, 2
+    boxes, cls, off = synth.make_gt(512, batch, 60, "max")
+    pred_cls, pred_box = synth.make_predictions(513, batch, a, bg_bias=7.0)
+    kept_all, count_all = M.detect(pred_cls, pred_box, priors)
+    sums, want_sums = [], []
+    for rank in range(world):
+        (lo, hi), (r0, r1), soff = parallel.shard_csr(off, world, rank)
+        n = hi - lo
+        hp = HotPath(t512, batch=n, max_gt=60, total_gt=r1 - r0)
+        out = (np.zeros(N.LOSS_RESULT_LEN), np.zeros((n, 80, 200), np.int32), np.zeros((n, 80), np.int32))
+        hp.step_host(boxes[r0:r1], cls[r0:r1], soff, pred_cls[lo:hi], pred_box[lo:hi], *out)
+        g_cls, g_loc, g_mask = hp.tgt["cls"].to_host(), hp.tgt["loc"].to_host(), hp.tgt["mask"].to_host()
+        w = [O.assign_encode(cls[off[i]:off[i + 1]], boxes[off[i]:off[i + 1]], priors, 0.5, sweeps=False) for i in range(lo, hi)]
+        for k in range(n):
+            assert np.array_equal(g_cls[k], w[k][0]) and np.array_equal(g_mask[k], w[k][2])
+            np.testing.assert_allclose(g_loc[k], w[k][1], rtol=1e-5, atol=1e-7)
+        y_true = (np.stack([x[0] for x in w]), np.stack([x[1] for x in w]).astype(np.float32), np.stack([x[2] for x in w]))
+        w_total, w_info, w_aux = O.ssd_loss(y_true, (pred_box[lo:hi], pred_cls[lo:hi]), return_masks=True)
+        np.testing.assert_allclose(out[0][0], w_total, rtol=1e-5)
+        assert out[0][4] == w_aux["num_pos"] and out[0][5] == w_aux["num_neg"]
+        # the chained step's detections are the streaming filter variant of the stand-alone call
+        assert np.array_equal(out[2], count_all[lo:hi]) and np.array_equal(out[1], kept_all[lo:hi])
+        sums.append(parallel.block_sums(out[0]))
+        want_sums.append({"num_pos": w_aux["num_pos"], "num_neg": w_aux["num_neg"],
+                          "sum_pos_ce": w_info["cls loss pos"] * w_aux["num_pos"],
+                          "sum_neg_ce": w_info["cls loss neg"] * w_aux["num_neg"],
+                          "sum_l1": w_info["loc loss"] * w_aux["num_pos"]})
+    got, _ = parallel.combine_loss(sums, "pooled")
+    want, _ = parallel.combine_loss(want_sums, "pooled")
+    np.testing.assert_allclose(got, want, rtol=1e-5)
