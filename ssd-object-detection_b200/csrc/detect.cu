@@ -752,15 +752,13 @@ __global__ void __launch_bounds__(kNmsThreads, 12) nms_kernel(NmsParams P) {
       lwx = (e.z > e.x) ? __log2f(e.z - e.x) : 0.f;
       lwy = (e.w > e.y) ? __log2f(e.w - e.y) : 0.f;
     }
-    auto slab = [&](float v, float o, float sc) {   // monotone in v
-      const float f = (v - o) * sc;
-      return f >= (float)(kSlabs - 1) ? kSlabs - 1 : (f > 0.f ? (int)f : 0);
+    auto slab = [&](float v, float o, float sc) {   // monotone in v (the conversion saturates, NaN -> 0)
+      return min(max(__float2int_rd((v - o) * sc), 0), kSlabs - 1);
     };
     const float tq = inexact ? 0.f : P.tq0;
     const float inv_l = inexact ? 0.f : P.inv_l;
     auto size_cls = [&](float ext, float lref) {   // monotone in ext, clamped (clamping only merges classes)
-      const float f = (lref - __log2f(ext)) * inv_l;
-      return f >= (float)(kSizeCls - 1) ? kSizeCls - 1 : (f > 0.f ? (int)f : 0);
+      return min(max(__float2int_rd((lref - __log2f(ext)) * inv_l), 0), kSizeCls - 1);
     };
     NMS_LOOP
     for (int i = tid; i < m; i += kNmsThreads) {
